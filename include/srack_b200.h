@@ -1,0 +1,227 @@
+/* ============================================================================
+ * srack_b200.h -- C ABI of the B200-native s-rack voice renderer.
+ *
+ * Drop-in boundary for the reference's module-graph tick (sharph/s-rack,
+ * src/synth.rs + src/synth/{oscillator,filter,adsr,vca,mixer,math,output}.rs).
+ * The reference has no FFI of its own: its seam is the Rust `SynthModule`
+ * trait plus the free functions `plan_execution`, `execute`, `get_catalog`.
+ * Every entry point below names the reference interface (file:line) it
+ * replaces; INTEGRATION.md shows the Rust binding a maintainer would add.
+ *
+ * Conventions
+ *   - plain C: opaque handles, pointers and sizes only; no C++/torch types.
+ *   - every function returns an `int` status (SRK_OK == 0) unless documented
+ *     otherwise; the reference's `Err(())` maps to SRK_ERR_PORT, its
+ *     `.unwrap()` panics map to error codes -- nothing aborts across the ABI.
+ *   - a patch handle is single-threaded (the caller serialises, as the
+ *     reference does with `Mutex<plan>`, src/main.rs:60); distinct patches may
+ *     be used from distinct threads.
+ *   - the library owns modules, per-voice state and all device memory; the
+ *     caller owns output buffers (host by default, device with
+ *     SRK_RENDER_DEVICE_OUT).
+ *   - there is NO CPU fallback: rendering without a CUDA device fails with
+ *     SRK_ERR_NO_DEVICE.
+ * ==========================================================================*/
+#ifndef SRACK_B200_H
+#define SRACK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SRK_API __attribute__((visibility("default")))
+#else
+#define SRK_API
+#endif
+
+/* ---- status codes ------------------------------------------------------- */
+enum srk_status {
+  SRK_OK = 0,
+  SRK_ERR_ARG = 1,         /* NULL / foreign handle, bad argument                 */
+  SRK_ERR_PORT = 2,        /* port index out of range: the reference's Err(())    */
+  SRK_ERR_KIND = 3,        /* unknown module kind / catalog name                  */
+  SRK_ERR_UNSUPPORTED = 4, /* catalog entry outside the hot path  */
+  SRK_ERR_PARAM = 5,       /* unknown parameter id for this kind                  */
+  SRK_ERR_SELF_LOOP = 6,   /* module wired to itself (deadlocks in the reference) */
+  SRK_ERR_NO_OUTPUT = 7,   /* patch has no Output module (ui.rs:84-96 -> empty plan) */
+  SRK_ERR_NOT_PLANNED = 8, /* wiring changed since the last srk_plan()            */
+  SRK_ERR_SIZE = 9,        /* per-voice array shorter than the voices rendered... */
+  SRK_ERR_NO_DEVICE = 10,  /* no CUDA device: the product has no CPU path         */
+  SRK_ERR_CUDA = 11,       /* CUDA runtime failure, see srk_last_error()          */
+  SRK_ERR_LIMIT = 12       /* patch too large for one thread block's shared memory */
+};
+
+/* ---- module kinds: the reference catalog (src/synth.rs:421-515) + Output,
+ *      which the app creates itself (src/main.rs:130) -------------------- */
+enum srk_kind {
+  SRK_KIND_OUTPUT = 0,      /* src/synth/output.rs      "Output"      */
+  SRK_KIND_OSCILLATOR = 1,  /* src/synth/oscillator.rs  "Oscillator"  */
+  SRK_KIND_NOISE = 2,       /* src/synth/oscillator.rs  "Noise"       */
+  SRK_KIND_ADSR = 3,        /* src/synth/adsr.rs        "ADSR"        */
+  SRK_KIND_VCA = 4,         /* src/synth/vca.rs         "VCA"         */
+  SRK_KIND_MOOG_FILTER = 5, /* src/synth/filter.rs      "Moog Filter" */
+  SRK_KIND_MONO_MIXER = 6,  /* src/synth/mixer.rs       "Mono Mixer"  */
+  SRK_KIND_ADD = 7,         /* src/synth/math.rs        "Add"         */
+  SRK_KIND_SUBTRACT = 8,    /* src/synth/math.rs        "Subtract"    */
+  SRK_KIND_MULTIPLY = 9,    /* src/synth/math.rs        "Multiply"    */
+  SRK_KIND_NON_LINEAR = 10, /* src/synth/math.rs        "Non-Linear"  */
+  SRK_KIND_COUNT = 11
+};
+
+/* ---- parameter ids (the reference mutates struct fields from ui(); there
+ *      is no generic setter -- these enumerate those fields) -------------- */
+enum srk_param {
+  /* Oscillator: oscillator.rs:12 (val, UI range -9..6 at :221), :22 antialiasing */
+  SRK_OSC_VAL = 0,
+  SRK_OSC_ANTIALIASING = 1, /* 0 / 1, uniform only */
+  /* ADSR: adsr.rs:10-13, defaults :39-42 */
+  SRK_ADSR_A_SEC = 0,
+  SRK_ADSR_D_SEC = 1,
+  SRK_ADSR_S_VAL = 2,
+  SRK_ADSR_R_SEC = 3,
+  /* VCA: vca.rs:14 */
+  SRK_VCA_NEGATIVE = 0, /* 0 / 1, uniform only */
+  /* Moog filter: filter.rs:21-23, defaults :36-38 */
+  SRK_MOOG_FREQ = 0,
+  SRK_MOOG_RES = 1,
+  SRK_MOOG_EXP_AMT = 2,
+  /* Mono mixer: mixer.rs:11, gains of inputs 0..3 */
+  SRK_MIXER_GAIN0 = 0,
+  SRK_MIXER_GAIN1 = 1,
+  SRK_MIXER_GAIN2 = 2,
+  SRK_MIXER_GAIN3 = 3,
+  /* Add/Subtract/Multiply/Non-Linear: math.rs:21,184 */
+  SRK_MATH_CONSTANT = 0
+};
+
+/* ---- render flags ------------------------------------------------------- */
+enum srk_render_flags {
+  SRK_RENDER_DEVICE_OUT = 1u << 0, /* `stems` / `mix` are device pointers on the patch's device */
+  SRK_RENDER_ASYNC = 1u << 1       /* return after enqueueing (device outputs only); srk_sync() waits */
+};
+
+/* src/synth.rs:20-25 `AudioConfig { sample_rate: u16, buffer_size: usize, channels: u8 }` */
+typedef struct srk_audio_config {
+  uint16_t sample_rate;
+  size_t buffer_size;
+  uint8_t channels;
+} srk_audio_config;
+
+typedef struct srk_patch srk_patch;   /* the module list + plan (ui.rs:51-60 SynthModuleWorkspaceImpl) */
+typedef struct srk_module srk_module; /* one SharedSynthModule (src/synth.rs:270); owned by its patch */
+
+/* ---- library ------------------------------------------------------------ */
+SRK_API const char* srk_version(void);
+SRK_API const char* srk_status_string(int status);
+
+/* ---- catalog: get_catalog(), src/synth.rs:421-515 ----------------------- */
+/* Number of catalog entries (the reference's 14, in its order, then "Output"). */
+SRK_API int srk_catalog_size(void);
+/* Name of entry i, e.g. "Oscillator"; NULL when i is out of range. */
+SRK_API const char* srk_catalog_name(int i);
+/* srk_kind of entry i, or -1 for entries outside the hot path
+ * ("Grid Sequencer", "Pattern Sequencer", "Sample", "Freeverb"). */
+SRK_API int srk_catalog_kind(int i);
+
+/* ---- patch lifetime ----------------------------------------------------- */
+/* Replaces the workspace that owns `modules` and `plan` (ui.rs:51-60, main.rs:103-125). */
+SRK_API int srk_patch_create(const srk_audio_config* cfg, srk_patch** out);
+SRK_API void srk_patch_destroy(srk_patch* patch);
+/* SynthModule::set_audio_config for every module (synth.rs:261; ui.rs set_audio_config).
+ * As in the reference, ADSR keeps the sample rate it was built with (adsr.rs:69-71)
+ * and Output drops its connections (output.rs:40-45).  Resets all voice state. */
+SRK_API int srk_set_audio_config(srk_patch* patch, const srk_audio_config* cfg);
+SRK_API int srk_get_audio_config(const srk_patch* patch, srk_audio_config* out);
+/* Seed of the counter-based noise generator that stands in for the reference's
+ * unseeded rand::random (oscillator.rs:385).  Default 0x5EED5EED. */
+SRK_API int srk_set_seed(srk_patch* patch, uint64_t seed);
+/* CUDA device ordinal used by this patch (default: current device at first render). */
+SRK_API int srk_set_device(srk_patch* patch, int device);
+SRK_API const char* srk_last_error(const srk_patch* patch);
+
+/* ---- modules: X::new(&AudioConfig) via the catalog closures (synth.rs:421-515,
+ *      main.rs:130,151-159); appended to the patch's module list ----------- */
+SRK_API int srk_module_create(srk_patch* patch, int kind, srk_module** out);
+SRK_API int srk_module_create_by_name(srk_patch* patch, const char* catalog_name, srk_module** out);
+/* ui.rs delete_module: disconnects every input fed by `module`, removes it from the list. */
+SRK_API int srk_module_remove(srk_patch* patch, srk_module* module);
+SRK_API size_t srk_module_count(const srk_patch* patch);
+SRK_API srk_module* srk_module_at(const srk_patch* patch, size_t index);
+
+/* SynthModule getters, src/synth.rs:223-232 */
+SRK_API const char* srk_get_id(const srk_module* m);   /* uuid-v4 text, valid until the module is removed */
+SRK_API const char* srk_get_name(const srk_module* m); /* "Oscillator", ... */
+SRK_API int srk_get_kind(const srk_module* m);         /* srk_kind, -1 on NULL */
+SRK_API int srk_get_num_inputs(const srk_module* m);   /* u8 in the reference; -1 on NULL */
+SRK_API int srk_get_num_outputs(const srk_module* m);
+/* *label is NULL for the reference's Ok(None); SRK_ERR_PORT for its Err(()). */
+SRK_API int srk_get_input_label(const srk_module* m, uint8_t input_idx, const char** label);
+SRK_API int srk_get_output_label(const srk_module* m, uint8_t output_idx, const char** label);
+
+/* set_input / disconnect_input / disconnect_inputs / get_input, src/synth.rs:228,234-246.
+ * Unlike the reference the source port is validated here (SRK_ERR_PORT) instead of
+ * panicking later in resolve_input (synth.rs:251). */
+SRK_API int srk_connect(srk_module* sink, uint8_t input_idx, srk_module* src, uint8_t src_port);
+SRK_API int srk_disconnect(srk_module* sink, uint8_t input_idx);
+SRK_API int srk_disconnect_inputs(srk_module* sink);
+/* *src is NULL when the input is not connected. */
+SRK_API int srk_get_input(const srk_module* sink, uint8_t input_idx, srk_module** src, uint8_t* src_port);
+
+/* parameters (struct fields set from ui(): oscillator.rs:12,221; filter.rs:226-236;
+ * adsr.rs:223-257; mixer.rs:126-131; math.rs:165,318) */
+SRK_API int srk_set_param_f32(srk_module* m, int param_id, float value);
+SRK_API int srk_get_param_f32(const srk_module* m, int param_id, float* value);
+/* New axis: one value per voice (global voice index), e.g. detune.  The array is copied. */
+SRK_API int srk_set_param_f32_per_voice(srk_module* m, int param_id, const float* values, size_t n_voices);
+
+/* ---- planning: plan_execution(output, &all_modules, &mut plan), src/synth.rs:128-212,
+ *      called as in ui.rs:63-82 (output = first Output in the module list) -------- */
+SRK_API int srk_plan(srk_patch* patch);
+/* Plan order; `cap` entries available in `out`, *n receives the plan length. */
+SRK_API int srk_plan_get(const srk_patch* patch, srk_module** out, size_t cap, size_t* n);
+/* Wires removed by the cycle breaker (synth.rs:168-192) as (reader, writer) pairs. */
+SRK_API int srk_plan_cuts(const srk_patch* patch, srk_module** readers, srk_module** writers, size_t cap, size_t* n);
+/* Reorders the module list (`all_modules`), as the reference test's shuffle does
+ * (synth.rs:561-567).  `order` must be a permutation of the patch's modules. */
+SRK_API int srk_set_module_order(srk_patch* patch, srk_module* const* order, size_t n);
+
+/* ---- rendering: execute(&plan) (src/synth.rs:97-101, called from main.rs:62-63)
+ *      + reading OutputModule.bufs (main.rs:64-75), for n_voices instances of the
+ *      patch at once.  Voices [voice_offset, voice_offset + n_voices) of the global
+ *      voice axis are rendered for n_samples samples; all module state persists
+ *      across calls exactly as the reference's modules persist across blocks.
+ *        stems: [channels][n_samples][n_voices] f32, or NULL
+ *        mix:   [channels][n_samples] f32 (sum over the rendered voices), or NULL
+ *      Host pointers unless SRK_RENDER_DEVICE_OUT.  Changing n_voices/voice_offset
+ *      between calls resets the voice state. ------------------------------- */
+SRK_API int srk_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t n_samples,
+                       unsigned flags, float* stems, float* mix);
+/* Same, enqueued on a caller-supplied cudaStream_t (passed as void*). */
+SRK_API int srk_render_on_stream(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t n_samples,
+                                 unsigned flags, float* stems, float* mix, void* cuda_stream);
+SRK_API int srk_sync(srk_patch* patch);
+/* Back to X::new() state for every module of every voice (and empty feedback history). */
+SRK_API int srk_reset(srk_patch* patch);
+
+/* ---- instrumentation ---------------------------------------------------- */
+/* Device time (CUDA events on the render stream) of the voice kernel alone and of the
+ * whole call, for the last completed render; kernel launches issued so far. */
+SRK_API int srk_last_render_ms(srk_patch* patch, float* kernel_ms, float* total_ms);
+SRK_API uint64_t srk_launch_count(const srk_patch* patch);
+/* Compiled-program facts for the last plan: samples per inner step, threads per block,
+ * shared-memory bytes per block, wires, state words and parameter words per voice,
+ * feedback rings (delayed wires). */
+typedef struct srk_program_info {
+  uint32_t n_instr, step_samples, block_threads, smem_bytes;
+  uint32_t n_wires, state_words, param_words, n_rings;
+} srk_program_info;
+SRK_API int srk_get_program_info(srk_patch* patch, size_t n_voices, srk_program_info* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRACK_B200_H */

@@ -1,0 +1,97 @@
+"""ctypes binding of libsrack_b200.so (the C ABI in include/srack_b200.h).
+
+There is no fallback of any kind: if the CUDA library has not been built this
+module raises at import time, and rendering without a CUDA device fails with
+SRK_ERR_NO_DEVICE.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsrack_b200.so")
+
+
+class srk_audio_config(C.Structure):
+    # src/synth.rs:20-25
+    _fields_ = [("sample_rate", C.c_uint16), ("buffer_size", C.c_size_t), ("channels", C.c_uint8)]
+
+
+class srk_program_info(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("n_instr", "step_samples", "block_threads", "smem_bytes",
+                                          "n_wires", "state_words", "param_words", "n_rings")]
+
+
+# status codes / kinds / params / flags: keep in sync with include/srack_b200.h
+# (tests/test_abi.py parses the header and compares)
+STATUS = dict(OK=0, ERR_ARG=1, ERR_PORT=2, ERR_KIND=3, ERR_UNSUPPORTED=4, ERR_PARAM=5, ERR_SELF_LOOP=6,
+              ERR_NO_OUTPUT=7, ERR_NOT_PLANNED=8, ERR_SIZE=9, ERR_NO_DEVICE=10, ERR_CUDA=11, ERR_LIMIT=12)
+KIND = dict(OUTPUT=0, OSCILLATOR=1, NOISE=2, ADSR=3, VCA=4, MOOG_FILTER=5, MONO_MIXER=6, ADD=7, SUBTRACT=8,
+            MULTIPLY=9, NON_LINEAR=10)
+PARAM = dict(OSC_VAL=0, OSC_ANTIALIASING=1, ADSR_A_SEC=0, ADSR_D_SEC=1, ADSR_S_VAL=2, ADSR_R_SEC=3, VCA_NEGATIVE=0,
+             MOOG_FREQ=0, MOOG_RES=1, MOOG_EXP_AMT=2, MIXER_GAIN0=0, MIXER_GAIN1=1, MIXER_GAIN2=2, MIXER_GAIN3=3,
+             MATH_CONSTANT=0)
+RENDER_DEVICE_OUT = 1
+RENDER_ASYNC = 2
+
+_P = C.c_void_p
+_SIGNATURES = {
+    "srk_version": (C.c_char_p, []),
+    "srk_status_string": (C.c_char_p, [C.c_int]),
+    "srk_catalog_size": (C.c_int, []),
+    "srk_catalog_name": (C.c_char_p, [C.c_int]),
+    "srk_catalog_kind": (C.c_int, [C.c_int]),
+    "srk_patch_create": (C.c_int, [C.POINTER(srk_audio_config), C.POINTER(_P)]),
+    "srk_patch_destroy": (None, [_P]),
+    "srk_set_audio_config": (C.c_int, [_P, C.POINTER(srk_audio_config)]),
+    "srk_get_audio_config": (C.c_int, [_P, C.POINTER(srk_audio_config)]),
+    "srk_set_seed": (C.c_int, [_P, C.c_uint64]),
+    "srk_set_device": (C.c_int, [_P, C.c_int]),
+    "srk_last_error": (C.c_char_p, [_P]),
+    "srk_module_create": (C.c_int, [_P, C.c_int, C.POINTER(_P)]),
+    "srk_module_create_by_name": (C.c_int, [_P, C.c_char_p, C.POINTER(_P)]),
+    "srk_module_remove": (C.c_int, [_P, _P]),
+    "srk_module_count": (C.c_size_t, [_P]),
+    "srk_module_at": (_P, [_P, C.c_size_t]),
+    "srk_get_id": (C.c_char_p, [_P]),
+    "srk_get_name": (C.c_char_p, [_P]),
+    "srk_get_kind": (C.c_int, [_P]),
+    "srk_get_num_inputs": (C.c_int, [_P]),
+    "srk_get_num_outputs": (C.c_int, [_P]),
+    "srk_get_input_label": (C.c_int, [_P, C.c_uint8, C.POINTER(C.c_char_p)]),
+    "srk_get_output_label": (C.c_int, [_P, C.c_uint8, C.POINTER(C.c_char_p)]),
+    "srk_connect": (C.c_int, [_P, C.c_uint8, _P, C.c_uint8]),
+    "srk_disconnect": (C.c_int, [_P, C.c_uint8]),
+    "srk_disconnect_inputs": (C.c_int, [_P]),
+    "srk_get_input": (C.c_int, [_P, C.c_uint8, C.POINTER(_P), C.POINTER(C.c_uint8)]),
+    "srk_set_param_f32": (C.c_int, [_P, C.c_int, C.c_float]),
+    "srk_get_param_f32": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float)]),
+    "srk_set_param_f32_per_voice": (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
+    "srk_plan": (C.c_int, [_P]),
+    "srk_plan_get": (C.c_int, [_P, C.POINTER(_P), C.c_size_t, C.POINTER(C.c_size_t)]),
+    "srk_plan_cuts": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.c_size_t, C.POINTER(C.c_size_t)]),
+    "srk_set_module_order": (C.c_int, [_P, C.POINTER(_P), C.c_size_t]),
+    "srk_render": (C.c_int, [_P, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint, _P, _P]),
+    "srk_render_on_stream": (C.c_int, [_P, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint, _P, _P, _P]),
+    "srk_sync": (C.c_int, [_P]),
+    "srk_reset": (C.c_int, [_P]),
+    "srk_last_render_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "srk_launch_count": (C.c_uint64, [_P]),
+    "srk_get_program_info": (C.c_int, [_P, C.c_size_t, C.POINTER(srk_program_info)]),
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build the CUDA extension first "
+            "(python -c 'import __graft_entry__ as g; g.build()' or make -C s-rack_b200/csrc). "
+            "srack_b200 has no CPU or pure-Python path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header and library out of sync
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()

@@ -1,0 +1,21 @@
+// Host-visible interface of the device engine (engine.cu).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+#include "patch.hpp"
+#include "program.hpp"
+
+namespace srk {
+
+void engine_destroy(Engine* e);
+int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t n_samples, unsigned flags,
+                  float* stems, float* mix, void* user_stream, bool use_user_stream);
+int engine_sync(srk_patch* patch);
+int engine_reset(srk_patch* patch);
+void engine_invalidate_state(srk_patch* patch);  // next render starts from X::new() state
+int engine_last_ms(srk_patch* patch, float* kernel_ms, float* total_ms);
+uint64_t engine_launches(const srk_patch* patch);
+int engine_program_info(srk_patch* patch, size_t n_voices, srk_program_info* out);
+
+}  // namespace srk

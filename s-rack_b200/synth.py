@@ -1,0 +1,302 @@
+"""Host-side mirror of the reference's module-graph API (src/synth.rs) over the C ABI.
+
+Names follow the reference: `AudioConfig` (synth.rs:20-25), `SynthModule` with
+`get_id/get_name/get_num_inputs/get_num_outputs/get_input/get_input_label/
+get_output_label/set_input/disconnect_input/disconnect_inputs` (synth.rs:222-246),
+`plan_execution` (synth.rs:128), `execute` (synth.rs:97), `get_inputs` (synth.rs:214),
+`get_catalog` (synth.rs:421).  The reference's `Err(())` becomes `PortError`.
+The new axis is voices: a `Patch` renders `n_voices` independent instances of its
+graph in lockstep on one B200.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import KIND, PARAM, STATUS, lib
+
+_STATUS_NAME = {v: k for k, v in STATUS.items()}
+_KIND_NAME = {v: k for k, v in KIND.items()}
+
+
+class SrackError(RuntimeError):
+    def __init__(self, status, detail=""):
+        self.status = status
+        name = _STATUS_NAME.get(status, str(status))
+        super().__init__(f"SRK_{name}: {detail or lib.srk_status_string(status).decode()}")
+
+
+class PortError(SrackError):
+    """The reference's Err(()) for an out-of-range port index."""
+
+
+@dataclass
+class AudioConfig:
+    sample_rate: int = 48000
+    buffer_size: int = 1024
+    channels: int = 2
+
+    def _c(self):
+        return _ffi.srk_audio_config(self.sample_rate, self.buffer_size, self.channels)
+
+
+class SynthModule:
+    """One module of a patch (the reference's SharedSynthModule). Identity == handle."""
+
+    def __init__(self, patch, handle):
+        self._patch = patch
+        self._h = handle
+
+    def __eq__(self, other):  # shared_are_eq, synth.rs:272-274
+        return isinstance(other, SynthModule) and other._h == self._h
+
+    def __hash__(self):
+        return hash(self._h)
+
+    def __repr__(self):
+        return f"<{self.get_name()} {self.get_id()[:8]}>"
+
+    def _check(self, rc):
+        if rc == STATUS["ERR_PORT"]:
+            raise PortError(rc, self._patch._err())
+        if rc:
+            raise SrackError(rc, self._patch._err())
+
+    def get_id(self):
+        return lib.srk_get_id(self._h).decode()
+
+    def get_name(self):
+        return lib.srk_get_name(self._h).decode()
+
+    def get_kind(self):
+        return _KIND_NAME[lib.srk_get_kind(self._h)]
+
+    def get_num_inputs(self):
+        return lib.srk_get_num_inputs(self._h)
+
+    def get_num_outputs(self):
+        return lib.srk_get_num_outputs(self._h)
+
+    def get_input(self, input_idx):
+        src, port = C.c_void_p(), C.c_uint8()
+        self._check(lib.srk_get_input(self._h, input_idx, C.byref(src), C.byref(port)))
+        if not src.value:
+            return None
+        return self._patch._wrap(src.value), port.value
+
+    def get_input_label(self, input_idx):
+        s = C.c_char_p()
+        self._check(lib.srk_get_input_label(self._h, input_idx, C.byref(s)))
+        return s.value.decode() if s.value is not None else None
+
+    def get_output_label(self, output_idx):
+        s = C.c_char_p()
+        self._check(lib.srk_get_output_label(self._h, output_idx, C.byref(s)))
+        return s.value.decode() if s.value is not None else None
+
+    def set_input(self, input_idx, src_module, src_port):
+        self._check(lib.srk_connect(self._h, input_idx, src_module._h, src_port))
+
+    def disconnect_input(self, input_idx):
+        self._check(lib.srk_disconnect(self._h, input_idx))
+
+    def disconnect_inputs(self):
+        self._check(lib.srk_disconnect_inputs(self._h))
+
+    # parameters: struct fields in the reference, ids from include/srack_b200.h
+    def set_param(self, param, value):
+        self._check(lib.srk_set_param_f32(self._h, _pid(param), float(value)))
+
+    def get_param(self, param):
+        v = C.c_float()
+        self._check(lib.srk_get_param_f32(self._h, _pid(param), C.byref(v)))
+        return v.value
+
+    def set_param_per_voice(self, param, values):
+        a = np.ascontiguousarray(values, dtype=np.float32)
+        self._check(lib.srk_set_param_f32_per_voice(self._h, _pid(param), a.ctypes.data, a.size))
+
+
+def _pid(param):
+    return PARAM[param] if isinstance(param, str) else int(param)
+
+
+def get_inputs(module):
+    """synth.rs:214-218"""
+    return [module.get_input(i) for i in range(module.get_num_inputs())]
+
+
+class Patch:
+    """The module list + plan of one patch (ui.rs:51-60), rendered for many voices."""
+
+    def __init__(self, audio_config=None, device=None):
+        self.audio_config = audio_config or AudioConfig()
+        h = C.c_void_p()
+        cfg = self.audio_config._c()
+        rc = lib.srk_patch_create(C.byref(cfg), C.byref(h))
+        if rc:
+            raise SrackError(rc)
+        self._h = h
+        self._wrappers = {}
+        if device is not None:
+            self._check(lib.srk_set_device(self._h, int(device)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.srk_patch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _err(self):
+        return lib.srk_last_error(self._h).decode()
+
+    def _check(self, rc):
+        if rc == STATUS["ERR_PORT"]:
+            raise PortError(rc, self._err())
+        if rc:
+            raise SrackError(rc, self._err())
+
+    def _wrap(self, handle):
+        w = self._wrappers.get(handle)
+        if w is None:
+            w = self._wrappers[handle] = SynthModule(self, handle)
+        return w
+
+    # -- module list ---------------------------------------------------------
+    def add_module(self, kind):
+        """`kind`: catalog name ("Moog Filter"), enum name ("MOOG_FILTER") or srk_kind int."""
+        h = C.c_void_p()
+        if isinstance(kind, str) and kind in KIND:
+            rc = lib.srk_module_create(self._h, KIND[kind], C.byref(h))
+        elif isinstance(kind, str):
+            rc = lib.srk_module_create_by_name(self._h, kind.encode(), C.byref(h))
+        else:
+            rc = lib.srk_module_create(self._h, int(kind), C.byref(h))
+        self._check(rc)
+        return self._wrap(h.value)
+
+    def delete_module(self, module):
+        self._check(lib.srk_module_remove(self._h, module._h))
+        self._wrappers.pop(module._h, None)
+
+    @property
+    def modules(self):
+        return [self._wrap(lib.srk_module_at(self._h, i)) for i in range(lib.srk_module_count(self._h))]
+
+    def set_module_order(self, modules):
+        arr = (C.c_void_p * len(modules))(*[m._h for m in modules])
+        self._check(lib.srk_set_module_order(self._h, arr, len(modules)))
+
+    def set_audio_config(self, audio_config):
+        cfg = audio_config._c()
+        self._check(lib.srk_set_audio_config(self._h, C.byref(cfg)))
+        self.audio_config = audio_config
+
+    def set_seed(self, seed):
+        self._check(lib.srk_set_seed(self._h, int(seed)))
+
+    # -- same verbs as oracle.orc.OraclePatch so one patch description drives both ----
+    def module_create(self, kind):
+        return self.add_module(kind)
+
+    def connect(self, sink, in_idx, src, src_port):
+        sink.set_input(in_idx, src, src_port)
+
+    def disconnect(self, sink, in_idx):
+        sink.disconnect_input(in_idx)
+
+    def set_param(self, module, pid, value):
+        module.set_param(pid, value)
+
+    def set_param_per_voice(self, module, pid, values):
+        module.set_param_per_voice(pid, values)
+
+    # -- planning ------------------------------------------------------------
+    def plan(self):
+        """plan_execution (synth.rs:128-212) -> modules in execution order."""
+        self._check(lib.srk_plan(self._h))
+        n = C.c_size_t()
+        cap = lib.srk_module_count(self._h)
+        arr = (C.c_void_p * max(cap, 1))()
+        self._check(lib.srk_plan_get(self._h, arr, cap, C.byref(n)))
+        return [self._wrap(arr[i]) for i in range(n.value)]
+
+    def plan_cuts(self):
+        """Wires removed by the cycle breaker, as (reader, writer) pairs."""
+        n = C.c_size_t()
+        self._check(lib.srk_plan_cuts(self._h, None, None, 0, C.byref(n)))
+        r = (C.c_void_p * max(n.value, 1))()
+        w = (C.c_void_p * max(n.value, 1))()
+        self._check(lib.srk_plan_cuts(self._h, r, w, n.value, C.byref(n)))
+        return [(self._wrap(r[i]), self._wrap(w[i])) for i in range(n.value)]
+
+    def program_info(self, n_voices=0):
+        info = _ffi.srk_program_info()
+        self._check(lib.srk_get_program_info(self._h, n_voices, C.byref(info)))
+        return {f: getattr(info, f) for f, _ in info._fields_}
+
+    # -- rendering -----------------------------------------------------------
+    def render(self, n_voices, n_samples, voice_offset=0, stems=False, mix=True):
+        """Render to freshly allocated host arrays -> (stems [C][N][V] or None, mix [C][N] or None)."""
+        ch = self.audio_config.channels
+        st = np.empty((ch, n_samples, n_voices), dtype=np.float32) if stems else None
+        mx = np.empty((ch, n_samples), dtype=np.float32) if mix else None
+        self.render_into(n_voices, n_samples, voice_offset, st.ctypes.data if stems else None,
+                         mx.ctypes.data if mix else None)
+        return st, mx
+
+    def render_into(self, n_voices, n_samples, voice_offset=0, stems_ptr=None, mix_ptr=None, device_out=False,
+                    async_=False, stream=None):
+        """Raw-pointer render (host pointers, or device pointers with device_out=True)."""
+        flags = (_ffi.RENDER_DEVICE_OUT if device_out else 0) | (_ffi.RENDER_ASYNC if async_ else 0)
+        if stream is None:
+            rc = lib.srk_render(self._h, n_voices, voice_offset, n_samples, flags, stems_ptr, mix_ptr)
+        else:
+            rc = lib.srk_render_on_stream(self._h, n_voices, voice_offset, n_samples, flags, stems_ptr, mix_ptr,
+                                          C.c_void_p(stream))
+        self._check(rc)
+
+    def execute(self, n_voices, voice_offset=0, stems=False, mix=True):
+        """One `execute(&plan)` of the reference (synth.rs:97-101): one block of buffer_size samples."""
+        return self.render(n_voices, self.audio_config.buffer_size, voice_offset, stems, mix)
+
+    def sync(self):
+        self._check(lib.srk_sync(self._h))
+
+    def reset(self):
+        self._check(lib.srk_reset(self._h))
+
+    def last_render_ms(self):
+        k, t = C.c_float(), C.c_float()
+        self._check(lib.srk_last_render_ms(self._h, C.byref(k), C.byref(t)))
+        return k.value, t.value
+
+    def launch_count(self):
+        return lib.srk_launch_count(self._h)
+
+
+def plan_execution(patch):
+    """synth.rs:128: output = first Output in the list (ui.rs:84-96), all_modules = the patch's list."""
+    return patch.plan()
+
+
+def execute(patch, n_voices, **kw):
+    return patch.execute(n_voices, **kw)
+
+
+def get_catalog():
+    """synth.rs:421-515 -> [(name, constructor(patch) -> SynthModule)]; entries outside the hot
+    path raise SrackError(SRK_ERR_UNSUPPORTED) when constructed."""
+    out = []
+    for i in range(lib.srk_catalog_size()):
+        name = lib.srk_catalog_name(i).decode()
+        if name == "Output":
+            continue  # created by the app (main.rs:130), not in the reference catalog
+        out.append((name, (lambda n: (lambda patch: patch.add_module(n)))(name)))
+    return out

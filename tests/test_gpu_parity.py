@@ -1,0 +1,373 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI, against the CPU
+oracle on the same seeded inputs and against the committed golden fixtures; plus the
+size-independent properties the domain offers (determinism, chunk invariance, mix == sum of
+stems, shard invariance) at BASELINE.json's full sizes.
+
+Tolerance (BASELINE.json north_star): |gpu - ref| <= 1e-5 * max(|ref|, 1) per sample.
+Expected better than that: bit-identical wherever no f64 sin/exp2/pow is involved (those go
+through CUDA's libm instead of glibc: <= 2 ulp f64 apart => a rare 1-ulp f32 flip)."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from util import assert_mix_parity, assert_parity, build_both, parity_stats
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def render_pair(srk, orc, builder, V, N, B=1024, channels=2, **kw):
+    gp, op, _, _ = build_both(srk, orc, builder, V, buffer_size=B, channels=channels, **kw)
+    gp.plan()
+    g_st, g_mix = gp.render(V, N, stems=True, mix=True)
+    o_st, o_mix = op.render(V, N)
+    return gp, op, g_st, g_mix, o_st, o_mix
+
+
+def test_cfg1_single_sine(srk, orc, cuda_device):
+    gp, op, g, g_mix, o, o_mix = render_pair(srk, orc, srk.patches.cfg1, 1, 48000)
+    s = assert_parity(g, o, what="cfg1")
+    assert s["max_ulp"] <= 1 or s["max_abs"] < 1e-12  # <= 1 f32 ulp on the sine path
+    assert_mix_parity(g_mix, o_mix, 1)
+    # dco_tests::produces_440 through the GPU: sr = 1760, 17-sample buffers, phase carries over
+    p = srk.Patch(srk.AudioConfig(440 * 4, 17, 2))
+    srk.patches.cfg1(p, 1)
+    p.plan()
+    buf = p.execute(1, stems=True)[0][0, :, 0]
+    assert buf[0] == 0.0 and abs(buf[1] - 1) < 1e-5 and abs(buf[2]) < 1e-5 and abs(buf[3] + 1) < 1e-5 and abs(buf[4]) < 1e-5
+    assert abs(p.execute(1, stems=True)[0][0, 0, 0] - 1.0) < 1e-5
+
+
+def test_cfg2_subtractive_is_bit_exact(srk, orc, cuda_device):
+    # saw/square oscillators with host-computed delta, filter, ADSR, VCA: no libm on the path
+    gp, op, g, g_mix, o, o_mix = render_pair(srk, orc, srk.patches.cfg2, 100, 26000)
+    assert np.abs(o).max() > 0.1
+    assert_parity(g, o, exact=True, what="cfg2")
+    assert_mix_parity(g_mix, o_mix, 100, what="cfg2 mix")
+
+
+def test_cfg3_fm(srk, orc, cuda_device):
+    gp, op, g, g_mix, o, o_mix = render_pair(srk, orc, srk.patches.cfg3, 99, 8192)
+    s = assert_parity(g, o, what="cfg3")
+    assert s["bit_identical"] > 0.99
+    assert_mix_parity(g_mix, o_mix, 99)
+
+
+@pytest.mark.parametrize("B", [1, 7, 256, 1024])
+def test_cfg3b_feedback_delay_equals_buffer_size(srk, orc, cuda_device, B):
+    N = 4 * 1024 if B > 7 else 1022 // B * B
+    gp, op, g, g_mix, o, o_mix = render_pair(srk, orc, srk.patches.cfg3b, 70, N, B=B)
+    assert len(gp.plan_cuts()) == 1
+    s = assert_parity(g, o, what=f"cfg3b B={B}")
+    assert s["bit_identical"] > 0.98
+
+
+def test_cfg4_full_subtractive(srk, orc, cuda_device):
+    gp, op, g, g_mix, o, o_mix = render_pair(srk, orc, srk.patches.cfg4, 70, 26000)
+    assert np.abs(o).max() > 0.1
+    s = assert_parity(g, o, what="cfg4")
+    assert s["bit_identical"] > 0.99
+    assert_mix_parity(g_mix, o_mix, 70)
+
+
+@pytest.mark.parametrize("idx", range(8))
+def test_cfg5_graphs(srk, orc, cuda_device, idx):
+    builder = srk.patches.CFG5_GRAPHS[idx]
+    gp, op, g, g_mix, o, o_mix = render_pair(srk, orc, builder, 37, 14336)
+    assert np.abs(o).max() > 0.01
+    assert_parity(g, o, what=f"cfg5[{idx}]")
+    assert_mix_parity(g_mix, o_mix, 37)
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg3b", "cfg4"])
+def test_against_committed_golden_vectors(srk, cuda_device, name):
+    g = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    V, N, B = int(g["n_voices"]), int(g["n_samples"]), int(g["buffer_size"])
+    p = srk.Patch(srk.AudioConfig(48000, B, 2))
+    srk.patches.CONFIGS[name][0](p, V)
+    p.plan()
+    st, _ = p.render(V, N, stems=True)
+    assert_parity(st, g["stems"], exact=(name == "cfg2"), what=f"golden {name}")
+
+
+def test_every_module_kind_and_port(srk, orc, cuda_device):
+    """Sync input, antialiasing off, band/high-pass taps, VCA negative, mixer gains, Subtract,
+    Non-Linear with constant and with a second input, unconnected-input defaults."""
+    P = srk.PARAM
+
+    def build(b, n_voices, seed=0):
+        master = b.module_create("OSCILLATOR")
+        slave = b.module_create("OSCILLATOR")
+        raw = b.module_create("OSCILLATOR")
+        filt = b.module_create("MOOG_FILTER")
+        sub = b.module_create("SUBTRACT")
+        nl = b.module_create("NON_LINEAR")
+        nl2 = b.module_create("NON_LINEAR")
+        vca = b.module_create("VCA")
+        mix = b.module_create("MONO_MIXER")
+        add = b.module_create("ADD")
+        adsr = b.module_create("ADSR")
+        out = b.module_create("OUTPUT")
+        b.set_param(master, P["OSC_VAL"], -2.0)
+        b.set_param_per_voice(slave, P["OSC_VAL"], srk.patches._u(7, 0, n_voices, -1.0, 1.5))
+        b.connect(slave, 1, master, 1)            # hard sync from the master's square
+        b.set_param(raw, P["OSC_ANTIALIASING"], 0.0)
+        b.set_param(raw, P["OSC_VAL"], -0.5)
+        b.connect(filt, 0, slave, 2)
+        b.set_param(filt, P["MOOG_RES"], 0.8)
+        b.connect(sub, 0, filt, 1)                # bandpass - highpass
+        b.connect(sub, 1, filt, 2)
+        b.connect(nl, 0, sub, 0)
+        b.set_param(nl, P["MATH_CONSTANT"], 0.7)  # signed |x|^0.7
+        b.connect(nl2, 0, raw, 1)                 # square ^ (something varying)
+        b.connect(nl2, 1, add, 0)
+        b.set_param(add, P["MATH_CONSTANT"], 1.25)  # (None, None) -> 0 + constant
+        b.connect(vca, 0, nl, 0)
+        b.connect(vca, 1, master, 0)              # sine CV, negative half multiplies too
+        b.set_param(vca, P["VCA_NEGATIVE"], 1.0)
+        b.connect(mix, 0, vca, 0)
+        b.connect(mix, 2, nl2, 0)
+        b.connect(mix, 3, adsr, 0)                # ADSR with no gate: stays at 0
+        b.set_param(mix, P["MIXER_GAIN0"], 0.9)
+        b.set_param(mix, P["MIXER_GAIN2"], 0.1)
+        b.connect(out, 0, mix, 0)
+        b.connect(out, 1, raw, 2)                 # non-antialiased saw
+        return {}
+
+    gp, op, g, g_mix, o, o_mix = render_pair(srk, orc, build, 45, 6000)
+    assert np.abs(o[0]).max() > 0.05 and np.abs(o[1]).max() > 0.5
+    assert_parity(g[1], o[1], exact=True, what="naive saw")
+    assert_parity(g[0], o[0], what="everything else")
+
+
+def test_more_than_four_and_single_channel_outputs(srk, orc, cuda_device):
+    for channels in (1, 6):
+        def build(b, n_voices, seed=0):
+            osc = b.module_create("OSCILLATOR")
+            out = b.module_create("OUTPUT")
+            for c in range(channels):
+                if c != 2:
+                    b.connect(out, c, osc, c % 3)
+            return {}
+        gp, op, g, g_mix, o, o_mix = render_pair(srk, orc, build, 33, 2000, channels=channels)
+        assert g.shape == (channels, 2000, 33)
+        assert_parity(g, o, what=f"{channels} channels")
+        assert_mix_parity(g_mix, o_mix, 33)
+        if channels > 2:
+            assert (g[2] == 0).all() and (g_mix[2] == 0).all()  # unconnected channel -> zeros (output.rs:56)
+
+
+def test_adsr_corner_cases(srk, orc, cuda_device):
+    """a_sec == 0 (1/0 = +inf -> straight to Decay, adsr.rs:152-156), retrigger during attack/decay/
+    release, gate high at sample 0 is not a transition (detector starts `last = true`, synth.rs:283)."""
+    P = srk.PARAM
+    for a_sec, gate_hz, d, s_, r in [(0.0, 40.0, 0.004, 0.25, 0.5), (0.02, 90.0, 0.5, 0.5, 0.5), (0.001, 25.0, 0.002, 0.7, 0.05)]:
+        def build(b, n_voices, seed=0):
+            gate = b.module_create("OSCILLATOR")
+            const = b.module_create("ADD")
+            gsum = b.module_create("ADD")
+            adsr = b.module_create("ADSR")
+            out = b.module_create("OUTPUT")
+            b.set_param(gate, P["OSC_VAL"], srk.patches.hz_to_val(gate_hz))
+            b.set_param_per_voice(const, P["MATH_CONSTANT"], np.linspace(-0.5, 1.5, n_voices).astype(np.float32))
+            b.connect(gsum, 0, gate, 1)
+            b.connect(gsum, 1, const, 0)          # per-voice gate offset: some voices start high / never fall
+            b.connect(adsr, 0, gsum, 0)
+            for pid, v in zip(("ADSR_A_SEC", "ADSR_D_SEC", "ADSR_S_VAL", "ADSR_R_SEC"), (a_sec, d, s_, r)):
+                b.set_param(adsr, P[pid], v)
+            b.connect(out, 0, adsr, 0)
+            return {}
+        gp, op, g, g_mix, o, o_mix = render_pair(srk, orc, build, 41, 9000, channels=1)
+        assert o.max() > 0.2
+        assert_parity(g, o, exact=True, what=f"adsr a={a_sec}")
+
+
+def _fuzz_patch(rng, n_modules):
+    from test_planner import KINDS, N_IN, N_OUT
+    kinds = [rng.choice(KINDS) for _ in range(n_modules)] + ["OUTPUT"]
+    # make sure something audible reaches the output
+    kinds[0] = "OSCILLATOR"
+    wires = [(len(kinds) - 1, 0, 0, rng.randrange(3))]
+    for sink, k in enumerate(kinds[:-1]):
+        for i in range(N_IN[k]):
+            if rng.random() < 0.55:
+                src = rng.randrange(len(kinds) - 1)
+                if src != sink:
+                    wires.append((sink, i, src, rng.randrange(N_OUT[kinds[src]])))
+    src = rng.randrange(len(kinds) - 1)
+    wires.append((len(kinds) - 1, 1, src, rng.randrange(N_OUT[kinds[src]])))
+    return kinds, wires
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_patches(srk, orc, cuda_device, seed):
+    """Random (often cyclic) graphs over every module kind with random parameters: exercises the
+    patch compiler (wire liveness, rings, unconnected-input defaults) against the oracle."""
+    rng = random.Random(1000 + seed)
+    kinds, wires = _fuzz_patch(rng, rng.randrange(3, 12))
+    B = rng.choice([1, 5, 64, 1024])
+    V = rng.choice([1, 31, 33, 64])
+    N = 64 * max(1, 1024 // 64) if B > 64 else 640 // B * B
+    n_par = dict(OSCILLATOR=1, ADSR=4, MOOG_FILTER=3, MONO_MIXER=4, ADD=1, SUBTRACT=1, MULTIPLY=1, NON_LINEAR=1)
+    ranges = dict(OSCILLATOR=(-3, 3), ADSR=(0.0, 0.01), MOOG_FILTER=(0.05, 0.9), MONO_MIXER=(0, 1), ADD=(-1, 1),
+                  SUBTRACT=(-1, 1), MULTIPLY=(-1, 1), NON_LINEAR=(0.5, 2.0))
+    pvals = {(m, pid): (rng.random() < 0.5, srk.patches._u(seed, 17 * m + pid, V, *ranges[k]))
+             for m, k in enumerate(kinds) if k in n_par for pid in range(n_par[k])}
+
+    def build(b, n_voices, seed=0):
+        mods = [b.module_create(k) for k in kinds]
+        for sink, i, src, port in wires:
+            b.connect(mods[sink], i, mods[src], port)
+        for (m, pid), (per_voice, vals) in pvals.items():
+            if per_voice:
+                b.set_param_per_voice(mods[m], pid, vals)
+            else:
+                b.set_param(mods[m], pid, float(vals[0]))
+        return {}
+
+    gp, op, g, g_mix, o, o_mix = render_pair(srk, orc, build, V, N, B=B)
+    assert [kinds.index(m.get_kind()) >= 0 for m in gp.plan()]
+    libm_free = not any(k == "NON_LINEAR" for k in kinds) and not any(
+        (kinds[src] == "OSCILLATOR" and port == 0) or (kinds[sink] == "OSCILLATOR" and i == 0)
+        for sink, i, src, port in wires)
+    finite = np.isfinite(o).all()
+    if libm_free and finite:
+        assert_parity(g, o, exact=True, what=f"fuzz {seed} (no libm on the path)")
+    elif finite:
+        s = parity_stats(g, o)
+        # chaotic feedback can amplify a 1-ulp libm difference; demand the bulk agrees
+        within = np.abs(g.astype(np.float64) - o) <= 1e-5 * np.maximum(np.abs(o), 1.0)
+        assert within.mean() > 0.98, (seed, s)
+    else:
+        assert (np.isfinite(g) == np.isfinite(o)).mean() > 0.98
+
+
+def test_determinism_reset_and_chunk_invariance(srk, orc, cuda_device):
+    V, N = 130, 9000
+    p = srk.Patch()
+    srk.patches.cfg4(p, V)
+    p.plan()
+    a_st, a_mix = p.render(V, N, stems=True)
+    p.reset()
+    b_st, b_mix = p.render(V, N, stems=True)
+    assert (a_st.view(np.uint32) == b_st.view(np.uint32)).all()  # run to run bit-identical
+    assert (a_mix.view(np.uint32) == b_mix.view(np.uint32)).all()
+    p.reset()
+    chunks, done = [], 0
+    for n in (1, 15, 16, 17, 1000, 4096, N - 5145):  # state persists across calls like across blocks
+        chunks.append(p.render(V, n, stems=True)[0])
+        done += n
+    assert done == N
+    c_st = np.concatenate(chunks, axis=1)
+    assert (a_st.view(np.uint32) == c_st.view(np.uint32)).all()
+
+
+def test_chunked_feedback_patch_keeps_ring_phase(srk, orc, cuda_device):
+    V, B = 40, 64
+    p = srk.Patch(srk.AudioConfig(48000, B, 2))
+    srk.patches.cfg3b(p, V)
+    p.plan()
+    whole = p.render(V, 1000, stems=True)[0]
+    p.reset()
+    parts = np.concatenate([p.render(V, n, stems=True)[0] for n in (3, 61, 64, 100, 772)], axis=1)
+    assert (whole.view(np.uint32) == parts.view(np.uint32)).all()
+
+
+def test_voice_offset_sharding_is_exact(srk, orc, cuda_device):
+    """Rendering voices [0, V) in one go or as two shards with voice_offset gives the same stems
+    bit for bit (incl. the per-voice noise key) and the shard mixes add up to the full mix."""
+    V, N = 101, 13500
+    full = srk.Patch()
+    srk.patches.cfg4(full, V)
+    full.plan()
+    f_st, f_mix = full.render(V, N, stems=True)
+    parts, mixes = [], []
+    for rank in range(2):
+        off, cnt = srk.shard.voice_range(V, rank, 2)
+        p = srk.Patch()
+        srk.patches.cfg4(p, V)
+        p.plan()
+        st, mx = p.render(cnt, N, voice_offset=off, stems=True)
+        parts.append(st)
+        mixes.append(mx)
+    assert (np.concatenate(parts, axis=2).view(np.uint32) == f_st.view(np.uint32)).all()
+    assert np.abs(mixes[0] + mixes[1] - f_mix).max() <= 1e-5 * np.sqrt(V)
+
+
+def test_mix_equals_sum_of_stems_and_mix_only_mode(srk, orc, cuda_device):
+    V, N = 300, 14000
+    p = srk.Patch()
+    srk.patches.cfg2(p, V)
+    p.plan()
+    st, mx = p.render(V, N, stems=True, mix=True)
+    assert_mix_parity(mx, st.astype(np.float64).sum(axis=2), V)
+    p.reset()
+    _, mx2 = p.render(V, N, stems=False, mix=True)
+    assert (mx.view(np.uint32) == mx2.view(np.uint32)).all()
+
+
+def test_per_voice_array_too_short_is_an_error(srk, cuda_device):
+    p = srk.Patch()
+    srk.patches.cfg2(p, 8)
+    p.plan()
+    with pytest.raises(srk.SrackError) as e:
+        p.render(16, 64)
+    assert e.value.status == srk.STATUS["ERR_SIZE"]
+
+
+def test_baseline_size_cfg2_properties(srk, orc, cuda_device):
+    """BASELINE configs[1] at full size (4096 voices x 48000 samples), outputs kept in HBM:
+    determinism, mix == sum(stems), boundedness, and per-voice parity for a sample of voices."""
+    import torch
+
+    V, N = 4096, 48000
+    p = srk.Patch(device=0)
+    srk.patches.cfg2(p, V)
+    p.plan()
+    stems = torch.empty((2, N, V), dtype=torch.float32, device="cuda:0")
+    mix = torch.empty((2, N), dtype=torch.float32, device="cuda:0")
+    p.render_into(V, N, 0, stems.data_ptr(), mix.data_ptr(), device_out=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(stems).all() and float(stems.abs().max()) <= 1.0  # VCA of a clamped filter
+    assert float(stems.abs().max()) > 0.3
+    ref_mix = stems.double().sum(dim=2)
+    assert float((mix.double() - ref_mix).abs().max()) <= 1e-5 * max(np.sqrt(V), float(ref_mix.abs().max()))
+    assert torch.equal(stems[0], stems[1])  # both channels read the same wire
+    stems2 = torch.empty_like(stems)
+    p.reset()
+    p.render_into(V, N, 0, stems2.data_ptr(), None, device_out=True)
+    torch.cuda.synchronize()
+    assert torch.equal(stems, stems2)
+    for v in (0, 1, 2047, 4095):
+        op = orc.OraclePatch()
+        srk.patches.cfg2(op, V)
+        ref, _ = op.render(1, N, voice_offset=v)
+        assert_parity(stems[:, :, v].cpu().numpy(), ref[:, :, 0], exact=True, what=f"cfg2 voice {v}")
+
+
+def test_baseline_size_cfg3_sampled_parity(srk, orc, cuda_device):
+    """BASELINE configs[2] (65536 voices x 48000): mix-only render at full size, stems for a voice
+    slice rendered separately with voice_offset and compared with the oracle."""
+    import torch
+
+    V, N = 65536, 48000
+    p = srk.Patch(device=0)
+    srk.patches.cfg3(p, V)
+    p.plan()
+    mix = torch.empty((2, N), dtype=torch.float32, device="cuda:0")
+    p.render_into(V, N, 0, None, mix.data_ptr(), device_out=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(mix).all() and float(mix.abs().max()) <= V
+    assert float(mix.abs().max()) > 10.0
+    q = srk.Patch(device=0)
+    srk.patches.cfg3(q, V)
+    q.plan()
+    off, cnt = 65536 - 48, 48
+    st, _ = q.render(cnt, N, voice_offset=off, stems=True)
+    op = orc.OraclePatch()
+    srk.patches.cfg3(op, V)
+    ref, _ = op.render(cnt, N, voice_offset=off)
+    s = assert_parity(st, ref, what="cfg3 voice slice")
+    assert s["bit_identical"] > 0.99
