@@ -107,6 +107,7 @@ class SynthModule:
     # parameters: struct fields in the reference, ids from include/srack_b200.h
     def set_param(self, param, value):
         self._check(lib.srk_set_param_f32(self._h, _pid(param), float(value)))
+        self._patch.per_voice.pop((self, _pid(param)), None)
 
     def get_param(self, param):
         v = C.c_float()
@@ -116,6 +117,7 @@ class SynthModule:
     def set_param_per_voice(self, param, values):
         a = np.ascontiguousarray(values, dtype=np.float32)
         self._check(lib.srk_set_param_f32_per_voice(self._h, _pid(param), a.ctypes.data, a.size))
+        self._patch.per_voice[(self, _pid(param))] = a  # host copy, e.g. to re-send or re-shard
 
 
 def _pid(param):
@@ -139,6 +141,7 @@ class Patch:
             raise SrackError(rc)
         self._h = h
         self._wrappers = {}
+        self.per_voice = {}  # (module, param id) -> f32 array indexed by global voice
         if device is not None:
             self._check(lib.srk_set_device(self._h, int(device)))
 
