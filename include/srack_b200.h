@@ -212,12 +212,14 @@ SRK_API int srk_reset(srk_patch* patch);
  * whole call, for the last completed render; kernel launches issued so far. */
 SRK_API int srk_last_render_ms(srk_patch* patch, float* kernel_ms, float* total_ms);
 SRK_API uint64_t srk_launch_count(const srk_patch* patch);
-/* Compiled-program facts for the last plan: samples per inner step, threads per block,
- * shared-memory bytes per block, wires, state words and parameter words per voice,
- * feedback rings (delayed wires). */
+/* Compiled-program facts for the last plan and `n_voices`: samples per chunk, threads per
+ * block, shared-memory bytes per block, wire slots, state words and parameter words per
+ * voice, feedback rings (delayed wires), warps per 32-voice group, pipeline stages and
+ * wire tiles per group. */
 typedef struct srk_program_info {
   uint32_t n_instr, step_samples, block_threads, smem_bytes;
   uint32_t n_wires, state_words, param_words, n_rings;
+  uint32_t n_warps, n_stages, n_tiles, reserved;
 } srk_program_info;
 SRK_API int srk_get_program_info(srk_patch* patch, size_t n_voices, srk_program_info* out);
 

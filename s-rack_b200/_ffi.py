@@ -18,7 +18,8 @@ class srk_audio_config(C.Structure):
 
 class srk_program_info(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("n_instr", "step_samples", "block_threads", "smem_bytes",
-                                          "n_wires", "state_words", "param_words", "n_rings")]
+                                          "n_wires", "state_words", "param_words", "n_rings",
+                                          "n_warps", "n_stages", "n_tiles", "reserved")]
 
 
 # status codes / kinds / params / flags: keep in sync with include/srack_b200.h

@@ -1,6 +1,6 @@
-// Device side of the renderer: the voice kernel (one resident thread per voice,
-// the whole sample loop in-kernel), the deterministic mixdown, and the Engine that
-// owns HBM state for one patch.  sm_100a only; there is no CPU path.
+// Device side of the renderer: the voice kernel (one resident lane per voice, the
+// whole sample loop in-kernel), the deterministic mixdown, and the Engine that owns
+// HBM state for one patch.  sm_100a only; there is no CPU path.
 //
 // HBM layout (all structure-of-arrays, voice index fastest => every warp access is
 // one contiguous 128-byte line):
@@ -9,11 +9,13 @@
 //   params  u32 [P][V]      per-voice parameters (uniform ones broadcast at upload)
 //   rings   f32 [R][B][V]   history of delayed (feedback) wires, B = buffer_size
 //   stems   f32 [C][N][V]   optional per-voice output
-//   partial f32 [G][C][N]   per-block mix partials (G = grid size), reduced in a
-//                           fixed order by mix_reduce_kernel => bit-reproducible mix
-// Shared memory per block (T threads, K samples per inner step):
-//   program (32 B / instr, staged once) | state [S][T] | params [P][T] |
-//   wires [W][K][T] | reduction scratch [T]
+//   partial f32 [G][C][N]   per-group mix partials (G = voice groups of 32), reduced in
+//                           a fixed order by mix_reduce_kernel => bit-reproducible mix
+// One thread block = one group of 32 voices (lane = voice) x S warps.  Shared memory:
+//   program blob (instructions, wire table, per-warp ranges; staged once) |
+//   state [S][32] | params [P][32] | wire tiles [n_tiles][K][32]
+// Pipelined schedule (S > 1): at iteration i a warp runs each of its instructions on
+// chunk i - stage; one __syncthreads per iteration publishes the tiles (program.hpp).
 #include "engine.hpp"
 
 #include <cuda_runtime.h>
@@ -23,120 +25,134 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "dsp.cuh"
 
 namespace srk {
 
 struct RenderArgs {
-  const Instr* prog;
+  const uint4* blob;      // [Instr x n_instr][WireDesc x n_wires][u16 warp_begin x (n_warps + 1)]
   uint32_t* state;
   const uint32_t* params;
   float* rings;
   float* stems;
   float* partial;
-  uint32_t n_instr;
+  uint32_t blob_vec;      // blob size in uint4
+  uint32_t n_instr, n_wires, n_warps, n_stages, n_tiles;
   uint32_t V;             // voices rendered by this launch
   uint32_t voice_offset;  // global index of voice 0 (noise key)
   uint32_t n_samples;
-  uint32_t S, P, W, C, B;
-  uint32_t step;          // samples per inner step, <= K and <= B
+  uint32_t S, P, C, B;
+  uint32_t K;             // samples per chunk: power of two <= 32
   uint32_t ring_phase;    // absolute sample index of sample 0, mod B
   uint32_t seed_lo, seed_hi;
 };
 
-template <int K>
-__global__ void __launch_bounds__(256) render_voices_kernel(const RenderArgs a) {
+constexpr int kMaxThreads = kMaxWarps * 32;
+
+__global__ void __launch_bounds__(kMaxThreads, 1) render_voices_kernel(const RenderArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int T = blockDim.x;
-  const int tid = threadIdx.x;
-  Instr* prog = reinterpret_cast<Instr*>(smem_raw);
-  uint32_t* st = reinterpret_cast<uint32_t*>(prog + a.n_instr);
-  uint32_t* pr = st + (size_t)a.S * T;
-  float* wires = reinterpret_cast<float*>(pr + (size_t)a.P * T);
-  float* red = wires + (size_t)a.W * K * T;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const Instr* prog = reinterpret_cast<const Instr*>(smem_raw);
+  const WireDesc* wd = reinterpret_cast<const WireDesc*>(prog + a.n_instr);
+  const uint16_t* warp_begin = reinterpret_cast<const uint16_t*>(wd + a.n_wires);
+  uint32_t* st = reinterpret_cast<uint32_t*>(smem_raw + (size_t)a.blob_vec * 16);
+  uint32_t* pr = st + a.S * 32;
+  float* tiles = reinterpret_cast<float*>(pr + a.P * 32);
 
   // stage the patch program (port/wire table) once per block
-  for (uint32_t i = tid; i < a.n_instr * 2; i += T)
-    reinterpret_cast<uint4*>(prog)[i] = reinterpret_cast<const uint4*>(a.prog)[i];
-  const uint32_t v_raw = blockIdx.x * T + tid;
-  const bool active = v_raw < a.V;
-  const uint32_t v = active ? v_raw : a.V - 1;  // idle lanes shadow the last voice, never store
-  for (uint32_t w = 0; w < a.S; ++w) st[w * T + tid] = a.state[(size_t)w * a.V + v];
-  for (uint32_t w = 0; w < a.P; ++w) pr[w * T + tid] = a.params[(size_t)w * a.V + v];
+  for (uint32_t i = tid; i < a.blob_vec; i += blockDim.x) reinterpret_cast<uint4*>(smem_raw)[i] = a.blob[i];
+  const uint32_t v0 = blockIdx.x * 32;
+  const uint32_t n_active = min(32u, a.V - v0);
+  const bool active = (uint32_t)lane < n_active;
+  const uint32_t v = active ? v0 + lane : a.V - 1;  // idle lanes shadow the last voice, never store
+  for (uint32_t w = wid; w < a.S; w += a.n_warps) st[w * 32 + lane] = a.state[(size_t)w * a.V + v];
+  for (uint32_t w = wid; w < a.P; w += a.n_warps) pr[w * 32 + lane] = a.params[(size_t)w * a.V + v];
   __syncthreads();
 
-  const dsp::Lane L{st + tid, pr + tid, wires + tid, T};
-  float mix_prev = 0.0f;
-  for (uint32_t n0 = 0; n0 < a.n_samples; n0 += a.step) {
-    const int kk = (int)min(a.step, a.n_samples - n0);
-    for (uint32_t pc = 0;; ++pc) {
+  dsp::Lane ln{st + lane, pr + lane, tiles + lane, wd, a.K * 32, 0};
+  const uint32_t pc0 = warp_begin[wid], pc1 = warp_begin[wid + 1];
+  const uint32_t K = a.K;
+  const uint32_t n_chunks = (a.n_samples + K - 1) / K;
+  const uint32_t n_iter = n_chunks + a.n_stages - 1;
+  const bool solo = a.n_warps == 1;
+  for (uint32_t it = 0; it < n_iter; ++it) {
+    for (uint32_t pc = pc0; pc < pc1; ++pc) {
       const Instr ins = prog[pc];
-      if (ins.op == OP_END) break;
+      const uint32_t chunk = it - ins.stage;
+      if (chunk >= n_chunks) continue;  // also catches it < stage (wraps)
+      const uint32_t n0 = chunk * K;
+      const int kk = (int)min(K, a.n_samples - n0);
+      ln.chunk = chunk;
       switch (ins.op) {
-        case OP_OSC: dsp::op_osc<K>(ins, L, kk); break;
-        case OP_MOOG: dsp::op_moog<K>(ins, L, kk); break;
-        case OP_ADSR: dsp::op_adsr<K>(ins, L, kk); break;
-        case OP_VCA: dsp::op_vca<K>(ins, L, kk); break;
-        case OP_MIXER: dsp::op_mixer<K>(ins, L, kk); break;
-        case OP_MATH: dsp::op_math<K>(ins, L, kk); break;
-        case OP_NOISE: dsp::op_noise<K>(ins, L, kk, a.voice_offset + v, a.seed_lo, a.seed_hi); break;
+        case OP_OSC: dsp::op_osc_dispatch(ins, ln, kk); break;
+        case OP_MOOG: dsp::op_moog_dispatch(ins, ln, kk); break;
+        case OP_ADSR: dsp::op_adsr(ins, ln, kk); break;
+        case OP_VCA: dsp::op_vca(ins, ln, kk); break;
+        case OP_MIXER: dsp::op_mixer(ins, ln, kk); break;
+        case OP_MATH: dsp::op_math_dispatch(ins, ln, kk); break;
+        case OP_NOISE: dsp::op_noise(ins, ln, kk, a.voice_offset + v, a.seed_lo, a.seed_hi); break;
         case OP_RING_LOAD: {
-          const float* ring = a.rings + (size_t)ins.aux * a.B * a.V;
-          float* out = dsp::wire<K>(L, ins.out[0]);
+          const float* ring = a.rings + (size_t)ins.aux * a.B * a.V + v;
+          float* out = dsp::wire(ln, ins.out[0]);
           uint32_t idx = (a.ring_phase + n0) % a.B;
           for (int k = 0; k < kk; ++k) {
-            out[k * T] = ring[(size_t)idx * a.V + v];
+            out[k * 32] = ring[(size_t)idx * a.V];
             idx = idx + 1 == a.B ? 0 : idx + 1;
           }
           break;
         }
         case OP_RING_STORE: {
-          float* ring = a.rings + (size_t)ins.aux * a.B * a.V;
-          const float* in = dsp::wire<K>(L, ins.in[0]);
+          float* ring = a.rings + (size_t)ins.aux * a.B * a.V + v;
+          const float* in = dsp::wire(ln, ins.in[0]);
           uint32_t idx = (a.ring_phase + n0) % a.B;
           for (int k = 0; k < kk; ++k) {
-            if (active) ring[(size_t)idx * a.V + v] = in[k * T];
+            if (active) ring[(size_t)idx * a.V] = in[k * 32];
             idx = idx + 1 == a.B ? 0 : idx + 1;
           }
           break;
         }
         case OP_OUTPUT: {  // OutputModule::calc, src/synth/output.rs:46-60, + mixdown
-          const uint32_t c = ins.aux;
-          const float* src = dsp::wire<K>(L, ins.in[0]);
-          if (a.stems && active) {
-            float* dst = a.stems + ((size_t)c * a.n_samples + n0) * a.V + v;
-            for (int k = 0; k < kk; ++k) dst[(size_t)k * a.V] = src ? src[k * T] : 0.0f;
-          }
-          if (a.partial) {
-            float* dst = a.partial + ((size_t)blockIdx.x * a.C + c) * a.n_samples + n0;
-            if (!src) {
-              if (tid < kk) dst[tid] = 0.0f;
-            } else if (ins.flags & F_OUT_SAME_AS_PREV) {
-              if (tid < kk) dst[tid] = mix_prev;
-            } else {
-              __syncthreads();  // every column of the wire is final
-              // thread (k, seg) adds K columns of sample row k; the rotated start column
-              // keeps the 32 lanes on 32 different banks
-              const int k = tid & (K - 1), seg = tid / K;
-              const float* row = wires + ((size_t)ins.in[0] * K + k) * T + seg * K;
-              const uint32_t col0 = blockIdx.x * T + seg * K;
-              float acc = 0.0f;
+          if (solo) __syncwarp();  // the tile was written by this warp a moment ago
+          float sum = 0.0f;
+          for (int j = 0; j < ins.n_ch; ++j) {
+            const uint32_t c = ins.aux + j;
+            const float* src = dsp::wire(ln, ins.in[j]);
+            if (a.stems && active) {
+              float* dst = a.stems + ((size_t)c * a.n_samples + n0) * a.V + v;
+              if (src) {
+                dsp::for_groups(kk, [&](auto u, int k0) {
+                  constexpr int U = decltype(u)::value;
+                  float x[U];
 #pragma unroll
-              for (int j = 0; j < K; ++j) {
-                const int jj = (j + k) & (K - 1);
-                const float x = row[jj];
-                acc = dsp::fadd(acc, col0 + jj < a.V ? x : 0.0f);
+                  for (int q = 0; q < U; ++q) x[q] = src[(k0 + q) * 32];
+#pragma unroll
+                  for (int q = 0; q < U; ++q) __stcs(dst + (size_t)(k0 + q) * a.V, x[q]);
+                });
+              } else {
+                for (int k = 0; k < kk; ++k) __stcs(dst + (size_t)k * a.V, 0.0f);
               }
-              red[tid] = acc;
-              __syncthreads();
-              if (tid < K) {
-                float sum = 0.0f;
-                for (int s = 0; s < T / K; ++s) sum = dsp::fadd(sum, red[s * K + tid]);
-                mix_prev = sum;
-                if (tid < kk) dst[tid] = sum;
-              }
-              __syncthreads();  // scratch and wire may be rewritten from here on
+            }
+            if (a.partial) {
+              if (!src) {
+                sum = 0.0f;
+              } else if (j == 0 || ins.in[j] != ins.in[j - 1]) {
+                // Transposed read of the [K][32] tile: lane (k, seg) adds K columns of sample
+                // row k (rotated start => 32 lanes on 32 banks), then a butterfly over seg.
+                const uint32_t k = lane & (K - 1), seg = lane / K;
+                const float* row = src - lane + k * 32 + seg * K;
+                const uint32_t col0 = seg * K;
+                float acc = 0.0f;
+                for (uint32_t q = 0; q < K; ++q) {
+                  const uint32_t col = (q + k) & (K - 1);
+                  const float x = row[col];
+                  acc = dsp::fadd(acc, col0 + col < n_active ? x : 0.0f);
+                }
+                for (uint32_t off = K; off < 32; off <<= 1) acc = dsp::fadd(acc, __shfl_xor_sync(0xFFFFFFFFu, acc, off));
+                sum = acc;
+              }  // else: same wire as the previous channel, same sums
+              if (lane < kk) a.partial[((size_t)blockIdx.x * a.C + c) * a.n_samples + n0 + lane] = sum;
             }
           }
           break;
@@ -144,9 +160,11 @@ __global__ void __launch_bounds__(256) render_voices_kernel(const RenderArgs a) 
         default: break;
       }
     }
+    if (solo) __syncwarp(); else __syncthreads();
   }
+  __syncthreads();
   if (active)
-    for (uint32_t w = 0; w < a.S; ++w) a.state[(size_t)w * a.V + v] = st[w * T + tid];
+    for (uint32_t w = wid; w < a.S; w += a.n_warps) a.state[(size_t)w * a.V + v] = st[w * 32 + lane];
 }
 
 // mix[c][n] = sum over blocks, in block order (fixed tree => run-to-run identical bits)
@@ -168,7 +186,7 @@ __global__ void state_init_kernel(uint32_t* state, const uint32_t* init, uint32_
 // ----------------------------------------------------------------------------
 // Engine
 // ----------------------------------------------------------------------------
-int compile_program(const srk_patch& patch, Program& prog, std::string& err);
+int compile_program(const srk_patch& patch, int max_warps, Program& prog, std::string& err);
 
 namespace {
 
@@ -205,6 +223,9 @@ struct Engine {
   bool timed = false;
   Program prog;
   uint64_t compiled_epoch = 0, uploaded_param_epoch = 0;
+  int compiled_max_warps = 0;       // schedule the program was compiled for
+  int chunk = 0;                    // samples per chunk (K) for the compiled program
+  std::vector<uint4> blob;          // device image of the program (see RenderArgs::blob)
   size_t V = 0, voice_offset = 0;
   uint64_t n_abs = 0;  // samples rendered since reset
   bool state_valid = false;
@@ -214,7 +235,7 @@ struct Engine {
   uint64_t launches = 0;
   int smem_optin = 0, n_sm = 0;
   // geometry of the last launch
-  int block_threads = 0, step = 0;
+  int block_threads = 0, step = 0, n_warps = 0, n_stages = 0;
   size_t smem_bytes = 0;
 
   ~Engine() {
@@ -262,24 +283,58 @@ static int engine_open(srk_patch* patch) {
   return SRK_OK;
 }
 
-// Threads per block / samples per step for V voices of this program.
-static void choose_geometry(const Engine& e, const Program& prog, size_t V, int& T, int& K, size_t& smem) {
-  (void)V;
-  T = env_int("SRK_BLOCK_THREADS", 32);
-  K = env_int("SRK_STEP", 16);
-  if (K != 8 && K != 16 && K != 32) K = 16;
-  if (T < 32) T = 32;
-  if (T > 256) T = 256;
-  T = (T + 31) / 32 * 32;
-  if (T < K) T = K;
-  auto bytes = [&](int t, int k) {
-    return prog.code.size() * sizeof(Instr) +
-           ((size_t)prog.state_init.size() + prog.param_src.size() + (size_t)prog.n_wires * k + 1) * t * sizeof(uint32_t);
-  };
-  while (bytes(T, K) > (size_t)e.smem_optin && K > 8) K /= 2;
-  while (bytes(T, K) > (size_t)e.smem_optin && T > 32) T -= 32;
-  if (T < K) T = K;
-  smem = bytes(T, K);
+// Device image of a compiled program: instructions, wire table, per-warp ranges.
+static void build_blob(const Program& prog, std::vector<uint4>& blob) {
+  const size_t bytes = prog.code.size() * sizeof(Instr) + prog.wires.size() * sizeof(WireDesc) +
+                       prog.warp_begin.size() * sizeof(uint16_t);
+  blob.assign((bytes + 15) / 16, uint4{0, 0, 0, 0});
+  unsigned char* p = reinterpret_cast<unsigned char*>(blob.data());
+  std::memcpy(p, prog.code.data(), prog.code.size() * sizeof(Instr));
+  p += prog.code.size() * sizeof(Instr);
+  if (!prog.wires.empty()) std::memcpy(p, prog.wires.data(), prog.wires.size() * sizeof(WireDesc));
+  p += prog.wires.size() * sizeof(WireDesc);
+  std::memcpy(p, prog.warp_begin.data(), prog.warp_begin.size() * sizeof(uint16_t));
+}
+
+// How many warps may share one 32-voice group for V voices: with few groups per SM the
+// render is bound by the dependent-instruction latency of one voice, so the modules of a
+// group are spread over warps as a pipeline; with many groups the SMs are already full
+// and one warp per group (no barriers, smallest tiles) is the throughput shape.
+static int choose_max_warps(const Engine& e, size_t V) {
+  const int forced = env_int("SRK_WARPS", 0);
+  if (forced > 0) return std::min(forced, (int)kMaxWarps);
+  const size_t groups = (V + kVoicesPerGroup - 1) / kVoicesPerGroup;
+  const size_t per_sm = (groups + std::max(e.n_sm, 1) - 1) / std::max(e.n_sm, 1);
+  if (per_sm <= 2) return kMaxWarps;
+  if (per_sm <= 4) return 8;
+  if (per_sm <= 8) return 4;
+  return 1;
+}
+
+static size_t smem_bytes_for(const Program& prog, size_t blob_vec, int K) {
+  return blob_vec * 16 + ((size_t)prog.state_init.size() + prog.param_src.size() + (size_t)prog.n_tiles * K) *
+                             kVoicesPerGroup * sizeof(uint32_t);
+}
+
+// Samples per chunk (a power of two <= 32) for this program; 0 when it cannot fit.
+static int choose_chunk(const Engine& e, const Program& prog, size_t blob_vec) {
+  int K = env_int("SRK_STEP", prog.n_warps > 1 ? 32 : 8);
+  if (K < 1) K = 1;
+  if (K > 32) K = 32;
+  while (K & (K - 1)) K &= K - 1;  // power of two
+  if (prog.n_rings) {
+    // a delayed wire's sample n - B must have been stored in an EARLIER iteration than the one
+    // that loads sample n: K <= B when one warp runs everything in order, K * (stage + 2) <= B
+    // when the store runs `stage` iterations behind the load.
+    const size_t B = std::max<uint32_t>(prog.ring_len, 1);
+    const size_t lim = prog.n_warps > 1 ? B / (prog.max_ring_store_stage + 2) : B;
+    while (K > 1 && (size_t)K > lim) K /= 2;
+    if ((size_t)K > lim) return 0;
+  }
+  while (K > 1 && smem_bytes_for(prog, blob_vec, K) > (size_t)e.smem_optin) K /= 2;
+  if (smem_bytes_for(prog, blob_vec, K) > (size_t)e.smem_optin) return 0;
+  if (prog.n_warps > 1 && K < 8) return 0;  // a barrier every few samples: not worth pipelining
+  return K;
 }
 
 static int build_param_table(srk_patch* patch, Engine& e) {
@@ -355,13 +410,22 @@ static int reset_state(srk_patch* patch, Engine& e) {
 static int engine_prepare(srk_patch* patch, size_t n_voices, size_t voice_offset) {
   Engine& e = *patch->engine;
   bool fresh = false;
-  if (e.compiled_epoch != patch->wiring_epoch) {
+  const int want_warps = choose_max_warps(e, n_voices);
+  if (e.compiled_epoch != patch->wiring_epoch || e.compiled_max_warps != want_warps) {
     std::string err;
-    int rc = compile_program(*patch, e.prog, err);
+    int rc = compile_program(*patch, want_warps, e.prog, err);
     if (rc != SRK_OK) { patch->last_error = err; return rc; }
-    SRK_CUDA(e.d_prog.ensure(e.prog.code.size() * sizeof(Instr)));
-    SRK_CUDA(cudaMemcpyAsync(e.d_prog.p, e.prog.code.data(), e.prog.code.size() * sizeof(Instr),
-                             cudaMemcpyHostToDevice, e.stream));
+    build_blob(e.prog, e.blob);
+    e.chunk = choose_chunk(e, e.prog, e.blob.size());
+    if (e.chunk == 0 && e.prog.n_warps > 1) {  // does not fit as a pipeline: one warp, plan order
+      rc = compile_program(*patch, 1, e.prog, err);
+      if (rc != SRK_OK) { patch->last_error = err; return rc; }
+      build_blob(e.prog, e.blob);
+      e.chunk = choose_chunk(e, e.prog, e.blob.size());
+    }
+    if (e.chunk == 0) { patch->last_error = "patch needs more shared memory than one block can have"; return SRK_ERR_LIMIT; }
+    SRK_CUDA(e.d_prog.ensure(e.blob.size() * sizeof(uint4)));
+    SRK_CUDA(cudaMemcpyAsync(e.d_prog.p, e.blob.data(), e.blob.size() * sizeof(uint4), cudaMemcpyHostToDevice, e.stream));
     SRK_CUDA(e.d_state_init.ensure(std::max<size_t>(e.prog.state_init.size(), 1) * sizeof(uint32_t)));
     if (!e.prog.state_init.empty())
       SRK_CUDA(cudaMemcpyAsync(e.d_state_init.p, e.prog.state_init.data(), e.prog.state_init.size() * sizeof(uint32_t),
@@ -369,6 +433,7 @@ static int engine_prepare(srk_patch* patch, size_t n_voices, size_t voice_offset
     // the host vectors must outlive the async copies
     SRK_CUDA(cudaStreamSynchronize(e.stream));
     e.compiled_epoch = patch->wiring_epoch;
+    e.compiled_max_warps = want_warps;
     fresh = true;
   }
   if (fresh || e.V != n_voices || e.voice_offset != voice_offset || !e.state_valid) {
@@ -387,14 +452,6 @@ static int engine_prepare(srk_patch* patch, size_t n_voices, size_t voice_offset
     e.uploaded_param_epoch = patch->param_epoch;
   }
   return SRK_OK;
-}
-
-template <int K>
-static cudaError_t launch_voices(const RenderArgs& a, unsigned grid, int T, size_t smem, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute(render_voices_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  render_voices_kernel<K><<<grid, T, smem, s>>>(a);
-  return cudaGetLastError();
 }
 
 int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t n_samples, unsigned flags,
@@ -421,11 +478,10 @@ int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t
 
   const Program& prog = e.prog;
   const size_t C = prog.channels;
-  int T, K;
-  size_t smem;
-  choose_geometry(e, prog, n_voices, T, K, smem);
-  if (smem > (size_t)e.smem_optin) { patch->last_error = "patch needs more shared memory than one block can have"; return SRK_ERR_LIMIT; }
-  const unsigned grid = (unsigned)((n_voices + T - 1) / T);
+  const int K = e.chunk;
+  const int T = (int)prog.n_warps * 32;
+  const size_t smem = smem_bytes_for(prog, e.blob.size(), K);
+  const unsigned grid = (unsigned)((n_voices + kVoicesPerGroup - 1) / kVoicesPerGroup);
   const bool device_out = flags & SRK_RENDER_DEVICE_OUT;
 
   float* d_stems = nullptr;
@@ -441,31 +497,34 @@ int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t
   }
 
   RenderArgs a{};
-  a.prog = (const Instr*)e.d_prog.p;
+  a.blob = (const uint4*)e.d_prog.p;
   a.state = (uint32_t*)e.d_state.p;
   a.params = (const uint32_t*)e.d_params.p;
   a.rings = (float*)e.d_rings.p;
   a.stems = d_stems;
   a.partial = mix ? (float*)e.d_partial.p : nullptr;
+  a.blob_vec = (uint32_t)e.blob.size();
   a.n_instr = (uint32_t)prog.code.size();
+  a.n_wires = (uint32_t)prog.wires.size();
+  a.n_warps = prog.n_warps;
+  a.n_stages = prog.n_stages;
+  a.n_tiles = prog.n_tiles;
   a.V = (uint32_t)n_voices;
   a.voice_offset = (uint32_t)voice_offset;
   a.n_samples = (uint32_t)n_samples;
   a.S = (uint32_t)prog.state_init.size();
   a.P = (uint32_t)prog.param_src.size();
-  a.W = prog.n_wires;
   a.C = (uint32_t)C;
   a.B = std::max<uint32_t>(prog.ring_len, 1);
-  a.step = (uint32_t)std::min<size_t>(K, prog.n_rings ? a.B : (size_t)K);
+  a.K = (uint32_t)K;
   a.ring_phase = (uint32_t)(e.n_abs % a.B);
   a.seed_lo = (uint32_t)patch->seed;
   a.seed_hi = (uint32_t)(patch->seed >> 32);
 
   SRK_CUDA(cudaEventRecord(e.ev[1], work));
-  cudaError_t le = K == 8 ? launch_voices<8>(a, grid, T, smem, work)
-                   : K == 16 ? launch_voices<16>(a, grid, T, smem, work)
-                             : launch_voices<32>(a, grid, T, smem, work);
-  SRK_CUDA(le);
+  SRK_CUDA(cudaFuncSetAttribute(render_voices_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  render_voices_kernel<<<grid, T, smem, work>>>(a);
+  SRK_CUDA(cudaGetLastError());
   ++e.launches;
   SRK_CUDA(cudaEventRecord(e.ev[2], work));
   if (mix) {
@@ -482,7 +541,9 @@ int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t
   e.timed = true;
   e.n_abs += n_samples;
   e.block_threads = T;
-  e.step = (int)a.step;
+  e.step = K;
+  e.n_warps = (int)prog.n_warps;
+  e.n_stages = (int)prog.n_stages;
   e.smem_bytes = smem;
   if (foreign) SRK_CUDA(cudaStreamWaitEvent(caller, e.ev[3], 0));  // caller's stream sees the results
   if (!(flags & SRK_RENDER_ASYNC)) SRK_CUDA(cudaStreamSynchronize(work));
@@ -522,23 +583,34 @@ uint64_t engine_launches(const srk_patch* patch) { return patch->engine ? patch-
 
 int engine_program_info(srk_patch* patch, size_t n_voices, srk_program_info* out) {
   if (!patch->planned) { patch->last_error = "not planned"; return SRK_ERR_NOT_PLANNED; }
+  Engine probe;  // geometry without a device: assume the sm_100 limits
+  probe.smem_optin = patch->engine ? patch->engine->smem_optin : 227 * 1024;
+  probe.n_sm = patch->engine ? patch->engine->n_sm : 148;
   Program prog;
   std::string err;
-  int rc = compile_program(*patch, prog, err);
+  std::vector<uint4> blob;
+  int rc = compile_program(*patch, choose_max_warps(probe, n_voices), prog, err);
   if (rc != SRK_OK) { patch->last_error = err; return rc; }
-  Engine probe;  // geometry without a device: assume the sm_100 opt-in limit
-  probe.smem_optin = patch->engine ? patch->engine->smem_optin : 227 * 1024;
-  int T, K;
-  size_t smem;
-  choose_geometry(probe, prog, n_voices, T, K, smem);
+  build_blob(prog, blob);
+  int K = choose_chunk(probe, prog, blob.size());
+  if (K == 0 && prog.n_warps > 1) {
+    rc = compile_program(*patch, 1, prog, err);
+    if (rc != SRK_OK) { patch->last_error = err; return rc; }
+    build_blob(prog, blob);
+    K = choose_chunk(probe, prog, blob.size());
+  }
+  if (K == 0) { patch->last_error = "patch needs more shared memory than one block can have"; return SRK_ERR_LIMIT; }
   out->n_instr = (uint32_t)prog.code.size();
-  out->step_samples = (uint32_t)std::min<size_t>(K, prog.n_rings ? std::max<uint32_t>(prog.ring_len, 1) : (size_t)K);
-  out->block_threads = (uint32_t)T;
-  out->smem_bytes = (uint32_t)smem;
-  out->n_wires = prog.n_wires;
+  out->step_samples = (uint32_t)K;
+  out->block_threads = prog.n_warps * 32;
+  out->smem_bytes = (uint32_t)smem_bytes_for(prog, blob.size(), K);
+  out->n_wires = (uint32_t)prog.wires.size();
   out->state_words = (uint32_t)prog.state_init.size();
   out->param_words = (uint32_t)prog.param_src.size();
   out->n_rings = prog.n_rings;
+  out->n_warps = prog.n_warps;
+  out->n_stages = prog.n_stages;
+  out->n_tiles = prog.n_tiles;
   return SRK_OK;
 }
 

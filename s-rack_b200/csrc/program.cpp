@@ -1,4 +1,4 @@
-// Patch compiler (host): planned module graph -> flat device program.
+// Patch compiler (host): planned module graph -> flat, scheduled device program.
 //
 // Wire semantics follow block execution in the reference (src/synth.rs:97-101):
 // a reader placed AFTER its source in the plan sees the source's samples of the
@@ -6,6 +6,10 @@
 // (only possible across a wire the cycle breaker removed, synth.rs:168-192) sees
 // the source's previous block, i.e. exactly buffer_size samples of delay with
 // zero initial history (synth.rs:32) -> a per-voice ring in HBM.
+//
+// Scheduling: see program.hpp.  The reference's block-based execute() only needs
+// block c of a module's inputs to compute block c of its outputs, so modules of
+// one voice group can run as a software pipeline over chunks, one warp each.
 #include "program.hpp"
 
 #include <algorithm>
@@ -15,7 +19,39 @@
 
 namespace srk {
 
-int compile_program(const srk_patch& patch, Program& prog, std::string& err) {
+namespace {
+
+struct Pending {
+  Instr ins;
+  int in_vw[4];
+  int out_vw[3];
+  int cost;
+};
+
+// Rough issue cost per sample, only used to balance warps over the 4 SM sub-partitions.
+int op_cost(const Pending& p) {
+  switch (p.ins.op) {
+    case OP_MOOG: return 100;
+    case OP_OSC: return 30 + (p.out_vw[0] >= 0 ? 60 : 0) + (p.out_vw[1] >= 0 ? 20 : 0) + (p.out_vw[2] >= 0 ? 10 : 0) +
+                        (p.in_vw[0] >= 0 ? 90 : 0);
+    case OP_ADSR: return 40;
+    case OP_NOISE: return 25;
+    case OP_OUTPUT: return 12;
+    case OP_MIXER: return 10;
+    case OP_MATH: return p.ins.flags == F_MATH_NONLIN ? 150 : 4;
+    default: return 4;
+  }
+}
+
+uint16_t pow2_ceil(int x) {
+  uint16_t p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+}  // namespace
+
+int compile_program(const srk_patch& patch, int max_warps, Program& prog, std::string& err) {
   prog = Program();
   const int n = (int)patch.modules.size();
   const srk_module* output = patch.find_output();
@@ -75,8 +111,7 @@ int compile_program(const srk_patch& patch, Program& prog, std::string& err) {
   }
   prog.n_rings = (uint32_t)ring_load_wire.size();
 
-  // ---- instruction emission ------------------------------------------------
-  struct Pending { Instr ins; int in_vw[4]; int out_vw[3]; };
+  // ---- instruction emission (plan order) -------------------------------------
   std::vector<Pending> code;
   auto blank = [] {
     Pending p{};
@@ -150,14 +185,12 @@ int compile_program(const srk_patch& patch, Program& prog, std::string& err) {
         break;
       case SRK_KIND_OUTPUT: {
         if (mod != output) continue;  // only the first Output's bufs are ever read (ui.rs:84-96, main.rs:66)
-        int prev = -2;
-        for (size_t c = 0; c < mod->inputs.size(); ++c) {
+        for (size_t c0 = 0; c0 < mod->inputs.size(); c0 += kOutputChannelsPerInstr) {
           Pending q = blank();
           q.ins.op = OP_OUTPUT;
-          q.ins.aux = (uint16_t)c;
-          q.in_vw[0] = in_wire[m][c];
-          if (c > 0 && q.in_vw[0] >= 0 && q.in_vw[0] == prev) q.ins.flags = F_OUT_SAME_AS_PREV;
-          prev = q.in_vw[0];
+          q.ins.aux = (uint16_t)c0;
+          q.ins.n_ch = (uint8_t)std::min<size_t>(kOutputChannelsPerInstr, mod->inputs.size() - c0);
+          for (int j = 0; j < q.ins.n_ch; ++j) q.in_vw[j] = in_wire[m][c0 + j];
           code.push_back(q);
         }
         continue;
@@ -177,46 +210,142 @@ int compile_program(const srk_patch& patch, Program& prog, std::string& err) {
       code.push_back(s);
     }
   }
-
-  // ---- liveness + physical slot assignment (no in-place reuse inside one instr)
-  for (size_t i = 0; i < code.size(); ++i) {
-    for (int k = 0; k < 3; ++k)
-      if (code[i].out_vw[k] >= 0) vw[code[i].out_vw[k]].def = (int)i;
-    for (int k = 0; k < 4; ++k)
-      if (code[i].in_vw[k] >= 0) vw[code[i].in_vw[k]].last_use = std::max(vw[code[i].in_vw[k]].last_use, (int)i);
-  }
-  std::vector<int> free_slots;
-  int n_slots = 0;
-  for (size_t i = 0; i < code.size(); ++i) {
-    for (int k = 0; k < 3; ++k) {
-      int w = code[i].out_vw[k];
-      if (w < 0) continue;
-      if (vw[w].last_use < 0) { code[i].out_vw[k] = -1; continue; }  // nobody reads it
-      if (free_slots.empty()) vw[w].slot = n_slots++;
-      else { vw[w].slot = free_slots.back(); free_slots.pop_back(); }
-    }
-    for (int k = 0; k < 4; ++k) {
-      int w = code[i].in_vw[k];
-      if (w >= 0 && vw[w].last_use == (int)i && vw[w].slot >= 0) {
-        // an instr may list the same wire twice (e.g. VCA audio == cv): free once
-        bool dup = false;
-        for (int j = 0; j < k; ++j) dup |= code[i].in_vw[j] == w;
-        if (!dup) free_slots.push_back(vw[w].slot);
-      }
-    }
-  }
-  prog.n_wires = (uint32_t)n_slots;
-  for (auto& p : code) {
-    for (int k = 0; k < 4; ++k) p.ins.in[k] = p.in_vw[k] >= 0 ? (int16_t)vw[p.in_vw[k]].slot : (int16_t)-1;
-    for (int k = 0; k < 3; ++k) p.ins.out[k] = p.out_vw[k] >= 0 ? (int16_t)vw[p.out_vw[k]].slot : (int16_t)-1;
-    prog.code.push_back(p.ins);
-  }
-  Pending end = blank();
-  prog.code.push_back(end.ins);
-  if (prog.code.size() > 4096 || prog.state_init.size() > 60000 || prog.param_src.size() > 60000) {
+  if (code.size() > 4000 || prog.state_init.size() > 60000 || prog.param_src.size() > 60000) {
     err = "patch too large";
     return SRK_ERR_LIMIT;
   }
+
+  // ---- liveness: drop output ports nobody reads --------------------------------
+  const int nc = (int)code.size();
+  for (int i = 0; i < nc; ++i) {
+    for (int k = 0; k < 3; ++k)
+      if (code[i].out_vw[k] >= 0) vw[code[i].out_vw[k]].def = i;
+    for (int k = 0; k < 4; ++k)
+      if (code[i].in_vw[k] >= 0) vw[code[i].in_vw[k]].last_use = std::max(vw[code[i].in_vw[k]].last_use, i);
+  }
+  for (int i = 0; i < nc; ++i)
+    for (int k = 0; k < 3; ++k) {
+      int w = code[i].out_vw[k];
+      if (w >= 0 && vw[w].last_use < 0) code[i].out_vw[k] = -1;
+    }
+  for (auto& p : code) p.cost = op_cost(p);
+
+  const bool pipelined = max_warps > 1 && nc > 1;
+  std::vector<int> stage(nc, 0), warp(nc, 0);
+  if (!pipelined) {
+    // One warp, plan order, physical tiles shared by liveness (no in-place reuse inside one instr).
+    std::vector<int> free_slots;
+    int n_slots = 0;
+    for (int i = 0; i < nc; ++i) {
+      for (int k = 0; k < 3; ++k) {
+        int w = code[i].out_vw[k];
+        if (w < 0) continue;
+        if (free_slots.empty()) vw[w].slot = n_slots++;
+        else { vw[w].slot = free_slots.back(); free_slots.pop_back(); }
+      }
+      for (int k = 0; k < 4; ++k) {
+        int w = code[i].in_vw[k];
+        if (w >= 0 && vw[w].last_use == i && vw[w].slot >= 0) {
+          // an instr may list the same wire twice (e.g. VCA audio == cv): free once
+          bool dup = false;
+          for (int j = 0; j < k; ++j) dup |= code[i].in_vw[j] == w;
+          if (!dup) free_slots.push_back(vw[w].slot);
+        }
+      }
+    }
+    prog.wires.assign(n_slots, WireDesc{0, 0});
+    for (int s = 0; s < n_slots; ++s) prog.wires[s].base = (uint16_t)s;
+    prog.n_tiles = (uint32_t)n_slots;
+    prog.n_warps = 1;
+    prog.n_stages = 1;
+  } else {
+    // ASAP stages, then pull every non-sink instruction as late as its readers allow
+    // (shorter rings), then one ring of tiles per wire.
+    for (int i = 0; i < nc; ++i)
+      for (int k = 0; k < 4; ++k) {
+        int w = code[i].in_vw[k];
+        if (w >= 0) stage[i] = std::max(stage[i], stage[vw[w].def] + 1);
+      }
+    for (int i = nc - 1; i >= 0; --i) {
+      int latest = -1;
+      for (int k = 0; k < 3; ++k) {
+        int w = code[i].out_vw[k];
+        if (w < 0) continue;
+        for (int j = 0; j < nc; ++j)
+          for (int q = 0; q < 4; ++q)
+            if (code[j].in_vw[q] == w) latest = latest < 0 ? stage[j] - 1 : std::min(latest, stage[j] - 1);
+      }
+      if (latest >= 0) stage[i] = std::max(stage[i], latest);
+    }
+    int n_slots = 0, n_tiles = 0;
+    for (int i = 0; i < nc; ++i)
+      for (int k = 0; k < 3; ++k) {
+        int w = code[i].out_vw[k];
+        if (w < 0) continue;
+        int max_delta = 1;
+        for (int j = 0; j < nc; ++j)
+          for (int q = 0; q < 4; ++q)
+            if (code[j].in_vw[q] == w) max_delta = std::max(max_delta, stage[j] - stage[i]);
+        vw[w].slot = n_slots++;
+        uint16_t depth = pow2_ceil(max_delta + 1);
+        prog.wires.push_back(WireDesc{(uint16_t)n_tiles, (uint16_t)(depth - 1)});
+        n_tiles += depth;
+      }
+    prog.n_tiles = (uint32_t)n_tiles;
+    // Warps: hardware warp w issues from SM sub-partition w % 4.  Longest-processing-time
+    // packing over the 4 sub-partitions, one instruction per warp while warps last.
+    std::vector<int> order(nc);
+    for (int i = 0; i < nc; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return code[a].cost > code[b].cost; });
+    const int cap = std::min(max_warps, kMaxWarps);
+    int load[4] = {0, 0, 0, 0}, count[4] = {0, 0, 0, 0};
+    std::vector<int> warp_load(cap, 0);
+    int n_warps = 1;
+    for (int idx : order) {
+      int best = -1;
+      for (int s = 0; s < 4; ++s) {
+        if (s + 4 * count[s] >= cap) continue;  // no free warp left on this sub-partition
+        if (best < 0 || load[s] < load[best]) best = s;
+      }
+      int w;
+      if (best >= 0) {
+        w = best + 4 * count[best]++;
+        load[best] += code[idx].cost;
+      } else {  // all warps taken: add to the least loaded warp
+        w = (int)(std::min_element(warp_load.begin(), warp_load.end()) - warp_load.begin());
+        load[w % 4] += code[idx].cost;
+      }
+      warp_load[w] += code[idx].cost;
+      warp[idx] = w;
+      n_warps = std::max(n_warps, w + 1);
+    }
+    prog.n_warps = (uint32_t)n_warps;
+    int max_stage = 0;
+    for (int i = 0; i < nc; ++i) {
+      max_stage = std::max(max_stage, stage[i]);
+      if (code[i].ins.op == OP_RING_STORE) prog.max_ring_store_stage = std::max<uint32_t>(prog.max_ring_store_stage, stage[i]);
+    }
+    prog.n_stages = (uint32_t)max_stage + 1;
+    if (max_stage > 250) { err = "patch too deep to pipeline"; return SRK_ERR_LIMIT; }
+  }
+
+  // ---- emit, sorted by (warp, plan order) ------------------------------------
+  std::vector<int> emit(nc);
+  for (int i = 0; i < nc; ++i) emit[i] = i;
+  std::stable_sort(emit.begin(), emit.end(), [&](int a, int b) { return warp[a] < warp[b]; });
+  prog.warp_begin.assign(prog.n_warps + 1, 0);
+  for (int i : emit) {
+    Pending& p = code[i];
+    for (int k = 0; k < 4; ++k) p.ins.in[k] = p.in_vw[k] >= 0 ? (int16_t)vw[p.in_vw[k]].slot : (int16_t)-1;
+    for (int k = 0; k < 3; ++k) p.ins.out[k] = p.out_vw[k] >= 0 ? (int16_t)vw[p.out_vw[k]].slot : (int16_t)-1;
+    p.ins.warp = (uint8_t)warp[i];
+    p.ins.stage = (uint8_t)stage[i];
+    prog.warp_begin[warp[i] + 1]++;
+    prog.code.push_back(p.ins);
+  }
+  for (uint32_t w = 0; w < prog.n_warps; ++w) prog.warp_begin[w + 1] += prog.warp_begin[w];
+  Pending end = blank();
+  prog.code.push_back(end.ins);
   return SRK_OK;
 }
 

@@ -1,7 +1,15 @@
 // The flat device program a planned patch compiles to: one instruction per module
-// (per channel for Output) in plan order, plus ring loads/stores for wires whose
-// source runs later in the plan than their reader (the reference's one-block
-// feedback latency, src/synth.rs:168-192 + :32).  Shared by host and device code.
+// (one for Output) in plan order, plus ring loads/stores for wires whose source
+// runs later in the plan than their reader (the reference's one-block feedback
+// latency, src/synth.rs:168-192 + :32).  Shared by host and device code.
+//
+// Scheduling (v2).  A 32-voice group is rendered by S warps.  Every instruction
+// carries the warp that executes it and a pipeline `stage`: at iteration i the
+// instruction works on chunk (i - stage) of K samples.  A reader's stage is
+// strictly greater than its writer's, so the tile it reads was finished in an
+// earlier iteration (one block barrier per iteration); each wire is a ring of
+// `mask + 1` tiles indexed by chunk & mask.  With S == 1 all stages are 0, the
+// instructions run in plan order and wires share single tiles by liveness.
 #pragma once
 #include <cstdint>
 #include <string>
@@ -20,17 +28,18 @@ enum Op : uint8_t {
   OP_VCA,
   OP_MIXER,
   OP_MATH,
-  OP_OUTPUT,
+  OP_OUTPUT,      // channels aux .. aux+3 <- in[0..3]; stems + per-group mix partial
 };
 
 // Instr::flags
-enum : uint8_t {
-  F_MATH_ADD = 0, F_MATH_SUB = 1, F_MATH_MUL = 2, F_MATH_NONLIN = 3,
-  F_OUT_SAME_AS_PREV = 1,  // this channel reads the same wire as the previous channel's instr
-};
+enum : uint8_t { F_MATH_ADD = 0, F_MATH_SUB = 1, F_MATH_MUL = 2, F_MATH_NONLIN = 3 };
 
 // ADSR mode encoding in the state word (adsr.rs:26-33 order)
 enum : uint32_t { ADSR_ATTACK = 0, ADSR_DECAY = 1, ADSR_SUSTAIN = 2, ADSR_RELEASE = 3, ADSR_NONE = 4 };
+
+constexpr int kVoicesPerGroup = 32;  // one lane per voice
+constexpr int kMaxWarps = 16;        // warps per group (512 threads x 128 registers)
+constexpr int kOutputChannelsPerInstr = 4;
 
 struct alignas(16) Instr {
   uint8_t op;
@@ -39,12 +48,20 @@ struct alignas(16) Instr {
   int16_t out[3];   // wire slot per output port, -1 = nobody reads it (not materialised)
   uint16_t state;   // first per-voice state word
   uint16_t param;   // first per-voice parameter word
-  uint16_t aux;     // ring id / module index (noise key) / channel (output)
-  uint16_t pad;
+  uint16_t aux;     // ring id / module index (noise key) / first channel (output)
+  uint8_t warp;     // warp of the group that executes this instruction
+  uint8_t stage;    // pipeline delay in chunks
   float imm;        // oscillator / ADSR sample rate
-  uint32_t pad2;
+  uint8_t n_ch;     // OUTPUT: channels covered by this instruction (1..4)
+  uint8_t pad[3];
 };
 static_assert(sizeof(Instr) == 32, "Instr must stay 32 bytes (staged to shared memory as uint4 pairs)");
+
+// One wire slot: a ring of (mask + 1) tiles of [K samples][32 voices] f32, first tile `base`.
+struct WireDesc {
+  uint16_t base;
+  uint16_t mask;
+};
 
 // Per-voice state words (u32 slots, SoA [word][voice] in HBM)
 //   OSC   : pos (f64, 2 words), sync_last                         oscillator.rs:21,23
@@ -65,13 +82,18 @@ struct ParamSource {
 };
 
 struct Program {
-  std::vector<Instr> code;        // terminated by OP_END
-  std::vector<uint32_t> state_init;  // one initial value per state word
+  std::vector<Instr> code;             // sorted by (warp, plan order), terminated by OP_END
+  std::vector<uint16_t> warp_begin;    // n_warps + 1 offsets into `code`
+  std::vector<WireDesc> wires;         // one per wire slot
+  std::vector<uint32_t> state_init;    // one initial value per state word
   std::vector<ParamSource> param_src;  // one per parameter word
-  uint32_t n_wires = 0;           // physical wire slots
+  uint32_t n_tiles = 0;                // wire tiles per group
+  uint32_t n_warps = 1;                // S
+  uint32_t n_stages = 1;               // max stage + 1
+  uint32_t max_ring_store_stage = 0;
   uint32_t n_rings = 0;
   uint32_t channels = 0;
-  uint32_t ring_len = 0;          // buffer_size
+  uint32_t ring_len = 0;               // buffer_size
 };
 
 }  // namespace srk

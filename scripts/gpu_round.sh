@@ -1,14 +1,17 @@
 #!/bin/bash
 # One gpurun call: GPU parity tests, bench line, ncu launch list and one full capture of the voice kernel.
-# Usage (from the repo root, on the GPU box):  bash scripts/gpu_round.sh [tag]
+# Usage (from the repo root, on the GPU box):  bash scripts/gpu_round.sh [tag] [quick]
 TAG=${1:-r01}
+MODE=${2:-full}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu_$TAG.txt 2>&1
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.log 2>&1
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu_$TAG.log
-tail -3 gpurun_out/pytest_gpu_$TAG.log
+tail -15 gpurun_out/pytest_gpu_$TAG.log
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 cat gpurun_out/bench_$TAG.json
+tail -5 gpurun_out/bench_$TAG.err
+if [ "$MODE" = "quick" ]; then exit 0; fi
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>> gpurun_out/bench_$TAG.err
 cat gpurun_out/bench_ref_$TAG.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \

@@ -371,3 +371,35 @@ def test_baseline_size_cfg3_sampled_parity(srk, orc, cuda_device):
     ref, _ = op.render(cnt, N, voice_offset=off)
     s = assert_parity(st, ref, what="cfg3 voice slice")
     assert s["bit_identical"] > 0.99
+
+
+@pytest.mark.parametrize("name,B", [("cfg2", 1024), ("cfg4", 1024), ("cfg3b", 256), ("cfg5_two_osc", 1024)])
+def test_schedule_invariance(srk, orc, cuda_device, monkeypatch, name, B):
+    """The same patch rendered as one warp per voice group in plan order (SRK_WARPS=1) and as a
+    software pipeline over 4/16 warps, with different chunk sizes, gives the same bits: the
+    schedule only moves work between warps, never changes a voice's arithmetic."""
+    V, N = 77, 5003
+    builder = getattr(srk.patches, name)
+    results = []
+    for warps, step in [(1, 8), (1, 32), (1, 1), (4, 16), (16, 32), (16, 8), (2, 32)]:
+        monkeypatch.setenv("SRK_WARPS", str(warps))
+        monkeypatch.setenv("SRK_STEP", str(step))
+        p = srk.Patch(srk.AudioConfig(48000, B, 2))
+        builder(p, V)
+        p.plan()
+        info = p.program_info(V)
+        assert info["n_warps"] <= max(warps, 1) and info["step_samples"] <= step
+        assert (info["n_warps"] > 1) == (info["n_stages"] > 1)
+        st, mx = p.render(V, N, stems=True, mix=True)
+        # a second call continues from the persisted state under the same schedule
+        st2, _ = p.render(V, 997, stems=True, mix=True)
+        results.append((info, np.concatenate([st, st2], axis=1), mx))
+    monkeypatch.delenv("SRK_WARPS")
+    monkeypatch.delenv("SRK_STEP")
+    assert any(r[0]["n_warps"] > 1 for r in results) and any(r[0]["n_warps"] == 1 for r in results)
+    for info, st, mx in results[1:]:
+        assert (st.view(np.uint32) == results[0][1].view(np.uint32)).all(), info
+        assert np.abs(mx - results[0][2]).max() <= 1e-5 * np.sqrt(V), info
+    gp, op, _, _ = build_both(srk, orc, builder, V, buffer_size=B)
+    o_st, _ = op.render(V, N + 997)
+    assert_parity(results[0][1], o_st, what=f"{name} schedule 0")
