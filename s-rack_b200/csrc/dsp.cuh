@@ -8,14 +8,28 @@
 // of the oscillator and Non-Linear module, where the reference itself goes through
 // the platform libm (<= 2 ulp f64 here vs glibc => at most a rare 1-ulp f32 flip).
 //
-// Shape of every op: the chunk is walked in groups of 8 samples (then single
-// samples for a ragged tail).  Inside a group the code is straight-line: inputs are
-// loaded first, the *stateless* per-sample work (coefficients, 2^x, sin, polyBLEP)
-// is independent across the 8 samples, and only the true recurrence (phase, ladder
-// stages, envelope state machine) forms a dependent chain -- ptxas overlaps the two.
-// "Is this port connected" is decided once per op or per group, never per sample.
-// Wire tiles are [K samples][32 voices] f32 in shared memory: sample k of this lane
-// is p[k * 32], so offsets inside a group are immediates.
+// Every op is a small struct: load() brings the voice's state and parameters from the
+// group's shared-memory tables into registers, run() advances one chunk of a wire tile,
+// store() writes the state back.  A warp that owns a single instruction (pipelined
+// schedule) calls load() once, run() per chunk and store() once -- the recurrence state
+// lives in registers for the whole render; the one-warp schedule calls all three per
+// chunk.
+//
+// Shape of run(): the chunk is walked in groups of kGroup samples (then single samples
+// for a ragged tail).  Inside a group the code is straight-line: inputs are loaded
+// first, the *stateless* per-sample work (coefficients, 2^x, sin, polyBLEP) is
+// independent across the samples, and only the true recurrence (phase, ladder stages,
+// envelope state machine) forms a dependent chain -- ptxas overlaps the two.  "Is this
+// port connected" is decided once per op or per group, never per sample.
+// Two measured facts shape the code (profiles/r01c_*, r01d_*): (1) with one or two warps
+// per SM sub-partition a taken branch or a reconvergence point costs tens of cycles of
+// instruction fetch, so the per-sample paths are select-based with bitwise (not
+// short-circuit) predicates, and rare cases are tested once per group; (2) the
+// instruction caches are small (L0 ~6 KB per sub-partition, 32 KB per SM) and the warps
+// of a voice group run *different* op bodies concurrently, so every hot body has to stay
+// a few KB -- hence groups of 4, and rare paths behind __noinline__ calls.
+// Wire tiles are [K samples][32 voices] f32 in shared memory: sample k of this lane is
+// p[k * 32], so offsets inside a group are immediates.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -38,34 +52,26 @@ __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a,
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 
 // f64 `x % 1.0` (Rust) == fmod(x, 1.0): exact, sign of x.  x - trunc(x) is exact for
-// every finite x, NaN for +-inf like fmod.  The phase accumulator only ever sees
-// x in [0, 2), where the result is x or x - 1 (both exact): that path avoids the
-// slow f64 round instruction on the recurrence.
-__device__ __forceinline__ double fmod1(double x) {
-  if (x >= 0.0 && x < 1.0) return x;
-  if (x >= 1.0 && x < 2.0) return dsub(x, 1.0);
-  return dsub(x, trunc(x));
-}
+// every finite x, NaN for +-inf like fmod.  Kept out of line: the phase accumulator only
+// ever sees x in [0, 2), where the result is x or x - 1 (both exact), and tests once per
+// group whether anything else turned up (wrap01 / the `odd` flag in OscOp).
+__device__ __noinline__ double fmod1_exact(double x) { return dsub(x, trunc(x)); }
+// fmod(x, 1.0) for x in [0, 2); NaN stays NaN.
+__device__ __forceinline__ double wrap01(double x) { return x >= 1.0 ? dsub(x, 1.0) : x; }
 
-// TransitionDetector::is_transition, src/synth.rs:292-297
-__device__ __forceinline__ bool transition(bool& last, float val) {
-  bool above = val > 0.0f;
-  bool t = above && !last;
-  last = above;
-  return t;
-}
-
-// OscillatorModule::poly_blep, src/synth/oscillator.rs:50-67
-__device__ __forceinline__ double poly_blep(double t, double dt) {
-  if (dt == 0.0) return 0.0;
-  if (t < dt) {
-    t = __ddiv_rn(t, dt);
-    return dsub(dsub(dadd(t, t), dmul(t, t)), 1.0);
-  } else if (t > dsub(1.0, dt)) {
-    t = __ddiv_rn(dsub(t, 1.0), dt);
-    return dadd(dadd(dadd(dmul(t, t), t), t), 1.0);
-  }
-  return 0.0;
+// OscillatorModule::poly_blep, src/synth/oscillator.rs:50-67, select-based: both arms
+// divide by dt, so ONE IEEE division of the selected numerator serves whichever arm is
+// live.  A sample needs it only when `t < dt || t > 1 - dt` (the other case returns 0.0;
+// dt == 0 can satisfy neither for t in [0, 1)), which callers test once per group.
+__device__ __forceinline__ double blep_eval(double t, double dt, double one_minus_dt) {
+  const bool lo = t < dt;
+  const bool hi = !lo & (t > one_minus_dt);
+  const double q = __ddiv_rn(lo ? t : dsub(t, 1.0), dt);
+  const double qq = dmul(q, q);
+  const double r_lo = dsub(dsub(dadd(q, q), qq), 1.0);
+  const double r_hi = dadd(dadd(dadd(qq, q), q), 1.0);
+  const double r = lo ? r_lo : (hi ? r_hi : 0.0);
+  return dt == 0.0 ? 0.0 : r;
 }
 
 // Philox4x32-10 (Salmon et al. 2011): the seeded stand-in for the reference's
@@ -90,6 +96,8 @@ struct Lane {
   const WireDesc* wd;  // wire slot -> (first tile, ring mask)
   uint32_t tile_elems; // K * 32
   uint32_t chunk;      // chunk the current instruction works on
+  uint32_t voice;      // global voice index (noise key)
+  uint32_t seed_lo, seed_hi;
 };
 
 __device__ __forceinline__ float* wire(const Lane& ln, int slot) {
@@ -101,138 +109,208 @@ __device__ __forceinline__ float* wire(const Lane& ln, int slot) {
 template <int U>
 using UC = std::integral_constant<int, U>;
 
-// Runs body(UC<8>, k0) over full groups of 8 samples, body(UC<1>, k) over the tail.
+constexpr int kGroup = 4;
+
+// Runs body(UC<kGroup>, k0) over full groups of samples, body(UC<1>, k) over the tail.
 template <class Body>
 __device__ __forceinline__ void for_groups(int kk, Body&& body) {
   int k0 = 0;
-  for (; k0 + 8 <= kk; k0 += 8) body(UC<8>(), k0);
+#pragma unroll 1
+  for (; k0 + kGroup <= kk; k0 += kGroup) body(UC<kGroup>(), k0);
+#pragma unroll 1
   for (; k0 < kk; ++k0) body(UC<1>(), k0);
 }
 
 // ---- OscillatorModule::calc, src/synth/oscillator.rs:108-158 ----------------
-template <bool HAS_CV, bool HAS_SYNC>
-__device__ __forceinline__ void op_osc(const Instr& ins, const Lane& ln, int kk) {
-  uint32_t* s = ln.st + ins.state * L;
-  double pos = __hiloint2double((int)s[L], (int)s[0]);
-  bool last = s[2 * L] != 0u;
-  const uint32_t* p = ln.pr + ins.param * L;
-  const double val = (double)__uint_as_float(p[0]);
-  const double delta_const = __hiloint2double((int)p[2 * L], (int)p[L]);
-  const double sr = (double)ins.imm;
-  const bool aa = __uint_as_float(p[3 * L]) != 0.0f;
-  const float* cv = wire(ln, ins.in[0]);
-  const float* sync = wire(ln, ins.in[1]);
-  float* sine = wire(ln, ins.out[0]);
-  float* square = wire(ln, ins.out[1]);
-  float* saw = wire(ln, ins.out[2]);
-  for_groups(kk, [&](auto u, int k0) {
-    constexpr int U = decltype(u)::value;
-    float cvv[U], syv[U];
-    double ps[U], dl[U];
-    if (HAS_CV) {
+struct OscOp {
+  uint32_t* s;
+  double pos, val, delta_const, sr;
+  bool last, aa;
+
+  __device__ __forceinline__ void load(const Instr& ins, const Lane& ln) {
+    s = ln.st + ins.state * L;
+    pos = __hiloint2double((int)s[L], (int)s[0]);
+    last = s[2 * L] != 0u;
+    const uint32_t* p = ln.pr + ins.param * L;
+    val = (double)__uint_as_float(p[0]);
+    delta_const = __hiloint2double((int)p[2 * L], (int)p[L]);
+    sr = (double)ins.imm;
+    aa = __uint_as_float(p[3 * L]) != 0.0f;
+  }
+  __device__ __forceinline__ void store() {
+    s[0] = (uint32_t)__double2loint(pos);
+    s[L] = (uint32_t)__double2hiint(pos);
+    s[2 * L] = last ? 1u : 0u;
+  }
+
+  template <bool HAS_CV, bool HAS_SYNC>
+  __device__ __forceinline__ void run_t(const Instr& ins, const Lane& ln, int kk) {
+    const float* cv = wire(ln, ins.in[0]);
+    const float* sync = wire(ln, ins.in[1]);
+    float* sine = wire(ln, ins.out[0]);
+    float* square = wire(ln, ins.out[1]);
+    float* saw = wire(ln, ins.out[2]);
+    for_groups(kk, [&](auto u, int k0) {
+      constexpr int U = decltype(u)::value;
+      float cvv[U], syv[U];
+      double ps[U], dl[U];
+      if (HAS_CV) {
 #pragma unroll
-      for (int j = 0; j < U; ++j) cvv[j] = cv[(k0 + j) * L];
-    }
-    if (HAS_SYNC) {
+        for (int j = 0; j < U; ++j) cvv[j] = cv[(k0 + j) * L];
+      }
+      if (HAS_SYNC) {
 #pragma unroll
-      for (int j = 0; j < U; ++j) syv[j] = sync[(k0 + j) * L];
-    }
-    // get_freq_in_hz (:43-48) then / sample_rate (:132): stateless
-#pragma unroll
-    for (int j = 0; j < U; ++j)
-      dl[j] = HAS_CV ? __ddiv_rn(dmul(440.0, exp2(dadd((double)cvv[j], val))), sr) : delta_const;
-    // the recurrence: sync reset (:125-131), pos += delta; pos %= 1.0 (:151-152)
-#pragma unroll
-    for (int j = 0; j < U; ++j) {
-      if (HAS_SYNC && transition(last, syv[j])) pos = 0.0;
-      ps[j] = pos;
-      pos = fmod1(dadd(pos, dl[j]));
-    }
-    if (sine) {
+        for (int j = 0; j < U; ++j) syv[j] = sync[(k0 + j) * L];
+      }
+      // get_freq_in_hz (:43-48) then / sample_rate (:132): stateless
 #pragma unroll
       for (int j = 0; j < U; ++j)
-        sine[(k0 + j) * L] = __double2float_rn(sin(dmul(dmul(ps[j], 3.14159265358979323846), 2.0)));
-    }
-    if (square || saw) {
-      double pb0[U];
+        dl[j] = HAS_CV ? __ddiv_rn(dmul(440.0, exp2(dadd((double)cvv[j], val))), sr) : delta_const;
+      // the recurrence: sync reset (:125-131), pos += delta; pos %= 1.0 (:151-152)
+      const double pos0 = pos;
+      const bool last0 = last;
+      bool odd = false;
 #pragma unroll
-      for (int j = 0; j < U; ++j) pb0[j] = aa ? poly_blep(ps[j], dl[j]) : 0.0;
-      if (square) {
+      for (int j = 0; j < U; ++j) {
+        if (HAS_SYNC) {
+          const bool above = syv[j] > 0.0f;
+          pos = (above & !last) ? 0.0 : pos;
+          last = above;
+        }
+        ps[j] = pos;
+        const double x = dadd(pos, dl[j]);
+        odd |= !(x < 2.0);  // NaN, inf or a step of more than one period: exact path below
+        pos = wrap01(x);
+      }
+      if (odd) {
+        pos = pos0;
+        last = last0;
 #pragma unroll
         for (int j = 0; j < U; ++j) {
-          const float base = ps[j] < 0.5 ? -1.0f : 1.0f;
-          const float corr = aa ? __double2float_rn(dsub(pb0[j], poly_blep(fmod1(dadd(ps[j], 0.5)), dl[j]))) : 0.0f;
-          square[(k0 + j) * L] = fsub(base, corr);
+          if (HAS_SYNC) {
+            const bool above = syv[j] > 0.0f;
+            pos = (above & !last) ? 0.0 : pos;
+            last = above;
+          }
+          ps[j] = pos;
+          pos = fmod1_exact(dadd(pos, dl[j]));
         }
       }
-      if (saw) {
+      if (sine) {
+#pragma unroll
+        for (int j = 0; j < U; ++j)
+          sine[(k0 + j) * L] = __double2float_rn(sin(dmul(dmul(ps[j], 3.14159265358979323846), 2.0)));
+      }
+      if (square || saw) {
+        // polyBLEP corrections (:135-149): zero unless a sample sits within dt of a
+        // discontinuity; one branch per group decides whether the evaluation runs at all
+        double om[U], p2[U], pb0[U], pb1[U];
+        bool near = false;
 #pragma unroll
         for (int j = 0; j < U; ++j) {
-          const float corr = aa ? __double2float_rn(pb0[j]) : 0.0f;
-          saw[(k0 + j) * L] = fsub(fsub(fmul(__double2float_rn(ps[j]), 2.0f), 1.0f), corr);
+          om[j] = dsub(1.0, dl[j]);
+          pb0[j] = 0.0;
+          pb1[j] = 0.0;
+          p2[j] = 0.0;
+          near |= (ps[j] < dl[j]) | (ps[j] > om[j]);
+        }
+        if (square) {
+#pragma unroll
+          for (int j = 0; j < U; ++j) {
+            // (pos + 0.5) % 1.0: pos is in [0, 1) or NaN (it is itself the result of `% 1.0`
+            // of a non-negative sum), so the sum is in [0.5, 1.5)
+            p2[j] = wrap01(dadd(ps[j], 0.5));
+            near |= (p2[j] < dl[j]) | (p2[j] > om[j]);
+          }
+        }
+        if (aa & near) {
+#pragma unroll
+          for (int j = 0; j < U; ++j) pb0[j] = blep_eval(ps[j], dl[j], om[j]);
+          if (square) {
+#pragma unroll
+            for (int j = 0; j < U; ++j) pb1[j] = blep_eval(p2[j], dl[j], om[j]);
+          }
+        }
+        if (square) {
+#pragma unroll
+          for (int j = 0; j < U; ++j) {
+            const float base = ps[j] < 0.5 ? -1.0f : 1.0f;
+            square[(k0 + j) * L] = fsub(base, __double2float_rn(dsub(pb0[j], pb1[j])));
+          }
+        }
+        if (saw) {
+#pragma unroll
+          for (int j = 0; j < U; ++j)
+            saw[(k0 + j) * L] = fsub(fsub(fmul(__double2float_rn(ps[j]), 2.0f), 1.0f), __double2float_rn(pb0[j]));
         }
       }
-    }
-  });
-  // with no sync input the detector sees 0.0 every sample: `last` just goes false
-  if (!HAS_SYNC && kk > 0) last = false;
-  s[0] = (uint32_t)__double2loint(pos);
-  s[L] = (uint32_t)__double2hiint(pos);
-  s[2 * L] = last ? 1u : 0u;
-}
-
-__device__ __forceinline__ void op_osc_dispatch(const Instr& ins, const Lane& ln, int kk) {
-  const bool cv = ins.in[0] >= 0, sync = ins.in[1] >= 0;
-  if (cv) {
-    if (sync) op_osc<true, true>(ins, ln, kk);
-    else op_osc<true, false>(ins, ln, kk);
-  } else {
-    if (sync) op_osc<false, true>(ins, ln, kk);
-    else op_osc<false, false>(ins, ln, kk);
+    });
+    // with no sync input the detector sees 0.0 every sample: `last` just goes false
+    if (!HAS_SYNC && kk > 0) last = false;
   }
-}
+
+  __device__ __forceinline__ void run(const Instr& ins, const Lane& ln, int kk) {
+    const bool cv = ins.in[0] >= 0, sync = ins.in[1] >= 0;
+    if (cv) {
+      if (sync) run_t<true, true>(ins, ln, kk);
+      else run_t<true, false>(ins, ln, kk);
+    } else {
+      if (sync) run_t<false, true>(ins, ln, kk);
+      else run_t<false, false>(ins, ln, kk);
+    }
+  }
+};
 
 // ---- NoiseModule::calc, src/synth/oscillator.rs:381-388 (seeded generator) ----
-__device__ __forceinline__ void op_noise(const Instr& ins, const Lane& ln, int kk, uint32_t voice, uint32_t seed_lo,
-                                         uint32_t seed_hi) {
-  uint32_t* s = ln.st + ins.state * L;
-  uint64_t n = ((uint64_t)s[L] << 32) | s[0];
-  float* out = wire(ln, ins.out[0]);
-  if (out) {
-    auto draw = [&](uint64_t blk, uint32_t (&c)[4]) {
-      c[0] = (uint32_t)blk; c[1] = (uint32_t)(blk >> 32); c[2] = voice; c[3] = ins.aux;
-      philox4x32_10(c, seed_lo, seed_hi);
-    };
-    auto shape = [](uint32_t r) {
-      const float u = fmul((float)(r >> 8), 1.0f / 16777216.0f);  // rand 0.8.5 Standard f32
-      return fmul(fsub(u, 0.5f), 2.0f);
-    };
-    int k = 0;
-    uint32_t c[4];
-    // ragged head up to the next multiple of 4 of the absolute sample counter
-    if ((n & 3) != 0 && kk > 0) {
-      draw(n >> 2, c);
-      for (; k < kk && ((n + k) & 3) != 0; ++k) {
-        const uint32_t q = (uint32_t)((n + k) & 3);
-        out[k * L] = shape(q == 1 ? c[1] : q == 2 ? c[2] : c[3]);
+struct NoiseOp {
+  uint32_t* s;
+  uint64_t n;
+
+  __device__ __forceinline__ void load(const Instr& ins, const Lane& ln) {
+    s = ln.st + ins.state * L;
+    n = ((uint64_t)s[L] << 32) | s[0];
+  }
+  __device__ __forceinline__ void store() {
+    s[0] = (uint32_t)n;
+    s[L] = (uint32_t)(n >> 32);
+  }
+  __device__ __forceinline__ void run(const Instr& ins, const Lane& ln, int kk) {
+    float* out = wire(ln, ins.out[0]);
+    if (out) {
+      auto draw = [&](uint64_t blk, uint32_t (&c)[4]) {
+        c[0] = (uint32_t)blk; c[1] = (uint32_t)(blk >> 32); c[2] = ln.voice; c[3] = ins.aux;
+        philox4x32_10(c, ln.seed_lo, ln.seed_hi);
+      };
+      auto shape = [](uint32_t r) {
+        const float u = fmul((float)(r >> 8), 1.0f / 16777216.0f);  // rand 0.8.5 Standard f32
+        return fmul(fsub(u, 0.5f), 2.0f);
+      };
+      int k = 0;
+      uint32_t c[4];
+      // ragged head up to the next multiple of 4 of the absolute sample counter
+      if ((n & 3) != 0 && kk > 0) {
+        draw(n >> 2, c);
+        for (; k < kk && ((n + k) & 3) != 0; ++k) {
+          const uint32_t q = (uint32_t)((n + k) & 3);
+          out[k * L] = shape(q == 1 ? c[1] : q == 2 ? c[2] : c[3]);
+        }
+      }
+#pragma unroll 1
+      for (; k + 4 <= kk; k += 4) {  // one Philox block per 4 samples
+        draw((n + k) >> 2, c);
+        out[(k + 0) * L] = shape(c[0]);
+        out[(k + 1) * L] = shape(c[1]);
+        out[(k + 2) * L] = shape(c[2]);
+        out[(k + 3) * L] = shape(c[3]);
+      }
+      if (k < kk) {
+        draw((n + k) >> 2, c);
+        for (int q = 0; k < kk; ++k, ++q) out[k * L] = shape(q == 0 ? c[0] : q == 1 ? c[1] : c[2]);
       }
     }
-    for (; k + 4 <= kk; k += 4) {  // one Philox block per 4 samples
-      draw((n + k) >> 2, c);
-      out[(k + 0) * L] = shape(c[0]);
-      out[(k + 1) * L] = shape(c[1]);
-      out[(k + 2) * L] = shape(c[2]);
-      out[(k + 3) * L] = shape(c[3]);
-    }
-    if (k < kk) {
-      draw((n + k) >> 2, c);
-      for (int q = 0; k < kk; ++k, ++q) out[k * L] = shape(q == 0 ? c[0] : q == 1 ? c[1] : c[2]);
-    }
+    n += kk;
   }
-  n += kk;
-  s[0] = (uint32_t)n;
-  s[L] = (uint32_t)(n >> 32);
-}
+};
 
 // ---- MoogFilterModule::calc, src/synth/filter.rs:182-221 with
 //      InternalMoogFilterState::calc :60-83 and clamp_buffers :86-91 -------------
@@ -252,250 +330,322 @@ __device__ __forceinline__ void moog_coef(float fc, float r, float& f, float& p,
 // that zero cache, where they stay 0 (moog_coef(0,0) has f = -1, so `f == 0` with a zero
 // cache key identifies it).  That makes the coefficients stateless per sample: they are
 // computed off the ladder's dependency chain.
-template <bool HAS_AUDIO, bool HAS_CV>
-__device__ __forceinline__ void op_moog(const Instr& ins, const Lane& ln, int kk) {
-  uint32_t* s = ln.st + ins.state * L;
-  float f = __uint_as_float(s[0]), p = __uint_as_float(s[L]), q = __uint_as_float(s[2 * L]);
-  float b0 = __uint_as_float(s[3 * L]), b1 = __uint_as_float(s[4 * L]), b2 = __uint_as_float(s[5 * L]);
-  float b3 = __uint_as_float(s[6 * L]), b4 = __uint_as_float(s[7 * L]);
-  float c_freq = __uint_as_float(s[8 * L]), c_res = __uint_as_float(s[9 * L]);
-  const uint32_t* pp = ln.pr + ins.param * L;
-  const float freq = __uint_as_float(pp[0]), res = __uint_as_float(pp[L]), exp_amt = __uint_as_float(pp[2 * L]);
-  const float r = fminf(fmaxf(res, 0.0f), 1.0f);  // :214
-  const float* audio = wire(ln, ins.in[0]);
-  const float* cv = wire(ln, ins.in[1]);
-  float* lowpass = wire(ln, ins.out[0]);
-  float* bandpass = wire(ln, ins.out[1]);
-  float* highpass = wire(ln, ins.out[2]);
-  bool virgin = c_freq == 0.0f && c_res == 0.0f && f == 0.0f;
-  if (!HAS_CV && kk > 0) {  // cutoff is constant over the chunk: one cache check (:61)
-    const float fc = fminf(fmaxf(fadd(freq, fmul(0.0f, exp_amt)), 0.0f), 0.9f);  // :213 with cv = 0.0
-    if (fc != c_freq || r != c_res) {
-      c_freq = fc;
-      c_res = r;
-      moog_coef(fc, r, f, p, q);
-    }
+struct MoogOp {
+  uint32_t* s;
+  float f, p, q, b0, b1, b2, b3, b4, c_freq, c_res;
+  float freq, r, exp_amt;
+
+  __device__ __forceinline__ void load(const Instr& ins, const Lane& ln) {
+    s = ln.st + ins.state * L;
+    f = __uint_as_float(s[0]); p = __uint_as_float(s[L]); q = __uint_as_float(s[2 * L]);
+    b0 = __uint_as_float(s[3 * L]); b1 = __uint_as_float(s[4 * L]); b2 = __uint_as_float(s[5 * L]);
+    b3 = __uint_as_float(s[6 * L]); b4 = __uint_as_float(s[7 * L]);
+    c_freq = __uint_as_float(s[8 * L]); c_res = __uint_as_float(s[9 * L]);
+    const uint32_t* pp = ln.pr + ins.param * L;
+    freq = __uint_as_float(pp[0]);
+    r = fminf(fmaxf(__uint_as_float(pp[L]), 0.0f), 1.0f);  // :214
+    exp_amt = __uint_as_float(pp[2 * L]);
   }
-  for_groups(kk, [&](auto u, int k0) {
-    constexpr int U = decltype(u)::value;
-    float a[U], fj[U], pj[U], qj[U], in_[U], o3[U], o4[U];
+  __device__ __forceinline__ void store() {
+    s[0] = __float_as_uint(f); s[L] = __float_as_uint(p); s[2 * L] = __float_as_uint(q);
+    s[3 * L] = __float_as_uint(b0); s[4 * L] = __float_as_uint(b1); s[5 * L] = __float_as_uint(b2);
+    s[6 * L] = __float_as_uint(b3); s[7 * L] = __float_as_uint(b4);
+    s[8 * L] = __float_as_uint(c_freq); s[9 * L] = __float_as_uint(c_res);
+  }
+
+  template <bool HAS_AUDIO, bool HAS_CV>
+  __device__ __forceinline__ void run_t(const Instr& ins, const Lane& ln, int kk) {
+    const float* audio = wire(ln, ins.in[0]);
+    const float* cv = wire(ln, ins.in[1]);
+    float* lowpass = wire(ln, ins.out[0]);
+    float* bandpass = wire(ln, ins.out[1]);
+    float* highpass = wire(ln, ins.out[2]);
+    bool virgin = (c_freq == 0.0f) & (c_res == 0.0f) & (f == 0.0f);
+    if (!HAS_CV && kk > 0) {  // cutoff is constant over the chunk: one cache check (:61)
+      const float fc = fminf(fmaxf(fadd(freq, fmul(0.0f, exp_amt)), 0.0f), 0.9f);  // :213 with cv = 0.0
+      if (fc != c_freq || r != c_res) {
+        c_freq = fc;
+        c_res = r;
+        moog_coef(fc, r, f, p, q);
+      }
+    }
+    for_groups(kk, [&](auto u, int k0) {
+      constexpr int U = decltype(u)::value;
+      float a[U], fj[U], pj[U], qj[U], in_[U], o3[U], o4[U];
 #pragma unroll
-    for (int j = 0; j < U; ++j) a[j] = HAS_AUDIO ? audio[(k0 + j) * L] : 0.0f;
-    if (HAS_CV) {
-      float fc[U];
+      for (int j = 0; j < U; ++j) a[j] = HAS_AUDIO ? audio[(k0 + j) * L] : 0.0f;
+      if (HAS_CV) {
+        float fc[U];
 #pragma unroll
-      for (int j = 0; j < U; ++j) fc[j] = fminf(fmaxf(fadd(freq, fmul(cv[(k0 + j) * L], exp_amt)), 0.0f), 0.9f);  // :213
+        for (int j = 0; j < U; ++j) fc[j] = fminf(fmaxf(fadd(freq, fmul(cv[(k0 + j) * L], exp_amt)), 0.0f), 0.9f);  // :213
+#pragma unroll
+        for (int j = 0; j < U; ++j) moog_coef(fc[j], r, fj[j], pj[j], qj[j]);
+        if (virgin) {  // only until (fc, r) first leaves (0, 0)
+#pragma unroll
+          for (int j = 0; j < U; ++j) {
+            virgin = virgin & (fc[j] == 0.0f) & (r == 0.0f);
+            if (virgin) { fj[j] = 0.0f; pj[j] = 0.0f; qj[j] = 0.0f; }
+          }
+        }
+        if (!virgin) { c_freq = fc[U - 1]; c_res = r; }
+        f = fj[U - 1]; p = pj[U - 1]; q = qj[U - 1];
+      } else {
+#pragma unroll
+        for (int j = 0; j < U; ++j) { fj[j] = f; pj[j] = p; qj[j] = q; }
+      }
+      // the ladder (:69-82): the only dependent chain
 #pragma unroll
       for (int j = 0; j < U; ++j) {
-        moog_coef(fc[j], r, fj[j], pj[j], qj[j]);
-        virgin = virgin && fc[j] == 0.0f && r == 0.0f;
-        if (virgin) { fj[j] = 0.0f; pj[j] = 0.0f; qj[j] = 0.0f; }
+        const float in = fsub(a[j], fmul(qj[j], b4));
+        float t1 = b1;
+        b1 = fsub(fmul(fadd(in, b0), pj[j]), fmul(b1, fj[j]));
+        const float t2 = b2;
+        b2 = fsub(fmul(fadd(b1, t1), pj[j]), fmul(b2, fj[j]));
+        t1 = b3;
+        b3 = fsub(fmul(fadd(b2, t2), pj[j]), fmul(b3, fj[j]));
+        b4 = fsub(fmul(fadd(b3, t1), pj[j]), fmul(b4, fj[j]));
+        b4 = fsub(b4, fmul(fmul(fmul(b4, b4), b4), 0.166667f));  // powi(3)
+        b0 = clamp1(in);
+        b1 = clamp1(b1); b2 = clamp1(b2); b3 = clamp1(b3); b4 = clamp1(b4);
+        in_[j] = in; o3[j] = b3; o4[j] = b4;
       }
-      if (!virgin) { c_freq = fc[U - 1]; c_res = r; }
-      f = fj[U - 1]; p = pj[U - 1]; q = qj[U - 1];
-    } else {
+      // calc returns (b4, in - b4, 3*(b3-b4)) assigned to (lowpass, highpass, bandpass), :211
+      if (lowpass) {
 #pragma unroll
-      for (int j = 0; j < U; ++j) { fj[j] = f; pj[j] = p; qj[j] = q; }
-    }
-    // the ladder (:69-82): the only dependent chain
+        for (int j = 0; j < U; ++j) lowpass[(k0 + j) * L] = o4[j];
+      }
+      if (highpass) {
 #pragma unroll
-    for (int j = 0; j < U; ++j) {
-      const float in = fsub(a[j], fmul(qj[j], b4));
-      float t1 = b1;
-      b1 = fsub(fmul(fadd(in, b0), pj[j]), fmul(b1, fj[j]));
-      const float t2 = b2;
-      b2 = fsub(fmul(fadd(b1, t1), pj[j]), fmul(b2, fj[j]));
-      t1 = b3;
-      b3 = fsub(fmul(fadd(b2, t2), pj[j]), fmul(b3, fj[j]));
-      b4 = fsub(fmul(fadd(b3, t1), pj[j]), fmul(b4, fj[j]));
-      b4 = fsub(b4, fmul(fmul(fmul(b4, b4), b4), 0.166667f));  // powi(3)
-      b0 = clamp1(in);
-      b1 = clamp1(b1); b2 = clamp1(b2); b3 = clamp1(b3); b4 = clamp1(b4);
-      in_[j] = in; o3[j] = b3; o4[j] = b4;
-    }
-    // calc returns (b4, in - b4, 3*(b3-b4)) assigned to (lowpass, highpass, bandpass), :211
-    if (lowpass) {
+        for (int j = 0; j < U; ++j) highpass[(k0 + j) * L] = fsub(in_[j], o4[j]);
+      }
+      if (bandpass) {
 #pragma unroll
-      for (int j = 0; j < U; ++j) lowpass[(k0 + j) * L] = o4[j];
-    }
-    if (highpass) {
-#pragma unroll
-      for (int j = 0; j < U; ++j) highpass[(k0 + j) * L] = fsub(in_[j], o4[j]);
-    }
-    if (bandpass) {
-#pragma unroll
-      for (int j = 0; j < U; ++j) bandpass[(k0 + j) * L] = fmul(3.0f, fsub(o3[j], o4[j]));
-    }
-  });
-  s[0] = __float_as_uint(f); s[L] = __float_as_uint(p); s[2 * L] = __float_as_uint(q);
-  s[3 * L] = __float_as_uint(b0); s[4 * L] = __float_as_uint(b1); s[5 * L] = __float_as_uint(b2);
-  s[6 * L] = __float_as_uint(b3); s[7 * L] = __float_as_uint(b4);
-  s[8 * L] = __float_as_uint(c_freq); s[9 * L] = __float_as_uint(c_res);
-}
-
-__device__ __forceinline__ void op_moog_dispatch(const Instr& ins, const Lane& ln, int kk) {
-  const bool au = ins.in[0] >= 0, cv = ins.in[1] >= 0;
-  if (au) {
-    if (cv) op_moog<true, true>(ins, ln, kk);
-    else op_moog<true, false>(ins, ln, kk);
-  } else {
-    if (cv) op_moog<false, true>(ins, ln, kk);
-    else op_moog<false, false>(ins, ln, kk);
+        for (int j = 0; j < U; ++j) bandpass[(k0 + j) * L] = fmul(3.0f, fsub(o3[j], o4[j]));
+      }
+    });
   }
-}
+
+  __device__ __forceinline__ void run(const Instr& ins, const Lane& ln, int kk) {
+    const bool au = ins.in[0] >= 0, cv = ins.in[1] >= 0;
+    if (au) {
+      if (cv) run_t<true, true>(ins, ln, kk);
+      else run_t<true, false>(ins, ln, kk);
+    } else {
+      if (cv) run_t<false, true>(ins, ln, kk);
+      else run_t<false, false>(ins, ln, kk);
+    }
+  }
+};
 
 // ---- ADSRModule::calc, src/synth/adsr.rs:134-217 ------------------------------
-__device__ __forceinline__ void op_adsr(const Instr& ins, const Lane& ln, int kk) {
-  uint32_t* s = ln.st + ins.state * L;
-  float phase = __uint_as_float(s[0]), r_val = __uint_as_float(s[L]), from_a_val = __uint_as_float(s[2 * L]);
-  uint32_t mode = s[3 * L] & 0xFFu;
-  bool last = (s[3 * L] >> 8) & 1u;
-  const uint32_t* pp = ln.pr + ins.param * L;
-  const float a_sec = __uint_as_float(pp[0]), d_sec = __uint_as_float(pp[L]);
-  const float s_val = __uint_as_float(pp[2 * L]), r_sec = __uint_as_float(pp[3 * L]);
-  const float sr = ins.imm;
-  // `1.0 / (self.sample_rate * self.x_sec)` is loop invariant: same IEEE value every sample
-  const float inc_a = __fdiv_rn(1.0f, fmul(sr, a_sec));
-  const float inc_d = __fdiv_rn(1.0f, fmul(sr, d_sec));
-  const float inc_r = __fdiv_rn(1.0f, fmul(sr, r_sec));
-  const float one_minus_s = fsub(1.0f, s_val);
-  const float* gate = wire(ln, ins.in[0]);
-  float* out = wire(ln, ins.out[0]);
-  for_groups(kk, [&](auto u, int k0) {
-    constexpr int U = decltype(u)::value;
-    float g[U], o[U];
+struct AdsrOp {
+  uint32_t* s;
+  float phase, r_val, from_a_val;
+  uint32_t mode;
+  bool last;
+  float s_val, inc_a, inc_d, inc_r, one_minus_s;
+
+  __device__ __forceinline__ void load(const Instr& ins, const Lane& ln) {
+    s = ln.st + ins.state * L;
+    phase = __uint_as_float(s[0]); r_val = __uint_as_float(s[L]); from_a_val = __uint_as_float(s[2 * L]);
+    mode = s[3 * L] & 0xFFu;
+    last = (s[3 * L] >> 8) & 1u;
+    const uint32_t* pp = ln.pr + ins.param * L;
+    const float a_sec = __uint_as_float(pp[0]), d_sec = __uint_as_float(pp[L]), r_sec = __uint_as_float(pp[3 * L]);
+    s_val = __uint_as_float(pp[2 * L]);
+    const float sr = ins.imm;
+    // `1.0 / (self.sample_rate * self.x_sec)` is loop invariant: same IEEE value every sample
+    inc_a = __fdiv_rn(1.0f, fmul(sr, a_sec));
+    inc_d = __fdiv_rn(1.0f, fmul(sr, d_sec));
+    inc_r = __fdiv_rn(1.0f, fmul(sr, r_sec));
+    one_minus_s = fsub(1.0f, s_val);
+  }
+  __device__ __forceinline__ void store() {
+    s[0] = __float_as_uint(phase); s[L] = __float_as_uint(r_val); s[2 * L] = __float_as_uint(from_a_val);
+    s[3 * L] = mode | (last ? 1u << 8 : 0u);
+  }
+
+  // The five-arm `match self.mode` (:144-200) as selects: each arm's next (mode, phase, r_val)
+  // is a few compares, and lanes in different modes then cost nothing extra.
+  __device__ __forceinline__ void run(const Instr& ins, const Lane& ln, int kk) {
+    const float* gate = wire(ln, ins.in[0]);
+    float* out = wire(ln, ins.out[0]);
+    const bool has_gate = gate != nullptr;
+    for_groups(kk, [&](auto u, int k0) {
+      constexpr int U = decltype(u)::value;
+      float g[U], o[U];
 #pragma unroll
-    for (int j = 0; j < U; ++j) g[j] = gate ? gate[(k0 + j) * L] : 0.0f;
+      for (int j = 0; j < U; ++j) g[j] = has_gate ? gate[(k0 + j) * L] : 0.0f;
 #pragma unroll
-    for (int j = 0; j < U; ++j) {
-      const bool high = gate && g[j] > 0.0f;   // `gate.is_some() && gate[i] > 0.0`
-      const bool low = !gate || g[j] <= 0.0f;  // `gate.is_none() || gate[i] <= 0.0` (NaN is neither)
-      const bool tr = transition(last, g[j]);  // None => detector sees 0.0
-      if (mode == ADSR_NONE) {
-        if (high) { phase = 0.0f; mode = ADSR_ATTACK; }
-      } else if (mode == ADSR_ATTACK) {
-        phase = fadd(phase, inc_a);
-        if (phase >= 1.0f) { phase = 0.0f; mode = ADSR_DECAY; }
-        else if (tr) { phase = 0.0f; r_val = from_a_val; }
-      } else if (mode == ADSR_DECAY) {
-        phase = fadd(phase, inc_d);
-        if (phase >= 1.0f) { phase = 0.0f; mode = ADSR_SUSTAIN; }
-        if (tr) { phase = 0.0f; mode = ADSR_ATTACK; }
-      } else if (mode == ADSR_SUSTAIN) {
-        if (low) { phase = 0.0f; mode = ADSR_RELEASE; }
-        if (tr) { phase = 0.0f; mode = ADSR_ATTACK; }
-      } else {  // Release
-        if (high) { phase = 0.0f; mode = ADSR_ATTACK; }
-        phase = fadd(phase, inc_r);
-        if (phase >= 1.0f) { phase = 0.0f; r_val = 0.0f; mode = ADSR_NONE; }
+      for (int j = 0; j < U; ++j) {
+        const bool above = g[j] > 0.0f;
+        const bool high = has_gate & above;            // `gate.is_some() && gate[i] > 0.0`
+        const bool low = !has_gate | (g[j] <= 0.0f);   // `gate.is_none() || gate[i] <= 0.0` (NaN is neither)
+        const bool tr = above & !last;                 // TransitionDetector, None => sees 0.0
+        last = above;
+        const bool m_none = mode == ADSR_NONE, m_att = mode == ADSR_ATTACK, m_dec = mode == ADSR_DECAY;
+        const bool m_sus = mode == ADSR_SUSTAIN, m_rel = mode == ADSR_RELEASE;
+        // Release restarts the attack first, then still advances by the release increment (:188-199)
+        const bool rel_retrig = m_rel & high;
+        const float ph0 = rel_retrig ? 0.0f : phase;
+        const float inc = m_att ? inc_a : m_dec ? inc_d : inc_r;
+        const float ph1 = fadd(ph0, inc);
+        const bool ge = ph1 >= 1.0f;
+        // next mode
+        uint32_t nm = mode;
+        nm = (m_none & high) ? ADSR_ATTACK : nm;
+        nm = (m_att & ge) ? ADSR_DECAY : nm;
+        nm = m_dec ? (tr ? ADSR_ATTACK : ge ? ADSR_SUSTAIN : ADSR_DECAY) : nm;
+        nm = m_sus ? (tr ? ADSR_ATTACK : low ? ADSR_RELEASE : ADSR_SUSTAIN) : nm;
+        nm = m_rel ? (ge ? ADSR_NONE : rel_retrig ? ADSR_ATTACK : ADSR_RELEASE) : nm;
+        // next phase (None without a gate and Sustain keep theirs)
+        const bool zero = (m_none & high) | ((m_att | m_dec) & (ge | tr)) | (m_sus & (low | tr)) | (m_rel & ge);
+        const bool advance = m_att | m_dec | m_rel;
+        const float np = zero ? 0.0f : advance ? ph1 : phase;
+        // r_val: a retrigger during attack restarts from where the attack began; release end clears it
+        r_val = (m_att & !ge & tr) ? from_a_val : r_val;
+        r_val = (m_rel & ge) ? 0.0f : r_val;
+        mode = nm;
+        phase = np;
+        const bool n_att = mode == ADSR_ATTACK;
+        const float omp = fsub(1.0f, phase);
+        const float lin = fadd(n_att ? r_val : s_val, fmul(n_att ? fsub(1.0f, r_val) : one_minus_s, n_att ? phase : omp));
+        float v = lin;                                 // Attack / Decay (:203-204)
+        v = mode == ADSR_RELEASE ? fmul(s_val, omp) : v;
+        v = mode == ADSR_SUSTAIN ? s_val : v;
+        v = mode == ADSR_NONE ? 0.0f : v;
+        o[j] = v;
+        r_val = n_att ? r_val : v;
+        from_a_val = n_att ? v : from_a_val;
       }
-      float v;
-      if (mode == ADSR_NONE) v = 0.0f;
-      else if (mode == ADSR_ATTACK) v = fadd(r_val, fmul(fsub(1.0f, r_val), phase));
-      else if (mode == ADSR_DECAY) v = fadd(s_val, fmul(one_minus_s, fsub(1.0f, phase)));
-      else if (mode == ADSR_SUSTAIN) v = s_val;
-      else v = fmul(s_val, fsub(1.0f, phase));
-      o[j] = v;
-      if (mode != ADSR_ATTACK) r_val = v; else from_a_val = v;
-    }
-    if (out) {
+      if (out) {
 #pragma unroll
-      for (int j = 0; j < U; ++j) out[(k0 + j) * L] = o[j];
-    }
-  });
-  s[0] = __float_as_uint(phase); s[L] = __float_as_uint(r_val); s[2 * L] = __float_as_uint(from_a_val);
-  s[3 * L] = mode | (last ? 1u << 8 : 0u);
-}
+        for (int j = 0; j < U; ++j) out[(k0 + j) * L] = o[j];
+      }
+    });
+  }
+};
 
 // ---- VCAModule::calc, src/synth/vca.rs:117-148 ---------------------------------
-__device__ __forceinline__ void op_vca(const Instr& ins, const Lane& ln, int kk) {
-  const float* audio = wire(ln, ins.in[0]);
-  const float* cv = wire(ln, ins.in[1]);
-  float* out = wire(ln, ins.out[0]);
-  if (!out) return;
-  const bool negative = __uint_as_float(ln.pr[ins.param * L]) != 0.0f;
-  if (!(audio && cv)) {  // :143 `_ => output.fill(0.0)`
-    for (int k = 0; k < kk; ++k) out[k * L] = 0.0f;
-    return;
+struct VcaOp {
+  bool negative;
+  __device__ __forceinline__ void load(const Instr& ins, const Lane& ln) {
+    negative = __uint_as_float(ln.pr[ins.param * L]) != 0.0f;
   }
-  for_groups(kk, [&](auto u, int k0) {
-    constexpr int U = decltype(u)::value;
-    float a[U], c[U];
+  __device__ __forceinline__ void store() {}
+  __device__ __forceinline__ void run(const Instr& ins, const Lane& ln, int kk) {
+    const float* audio = wire(ln, ins.in[0]);
+    const float* cv = wire(ln, ins.in[1]);
+    float* out = wire(ln, ins.out[0]);
+    if (!out) return;
+    if (!(audio && cv)) {  // :143 `_ => output.fill(0.0)`
+      for (int k = 0; k < kk; ++k) out[k * L] = 0.0f;
+      return;
+    }
+    for_groups(kk, [&](auto u, int k0) {
+      constexpr int U = decltype(u)::value;
+      float a[U], c[U];
 #pragma unroll
-    for (int j = 0; j < U; ++j) { a[j] = audio[(k0 + j) * L]; c[j] = cv[(k0 + j) * L]; }
+      for (int j = 0; j < U; ++j) { a[j] = audio[(k0 + j) * L]; c[j] = cv[(k0 + j) * L]; }
 #pragma unroll
-    for (int j = 0; j < U; ++j) out[(k0 + j) * L] = (negative || c[j] > 0.0f) ? fmul(a[j], c[j]) : 0.0f;
-  });
-}
+      for (int j = 0; j < U; ++j) out[(k0 + j) * L] = (negative | (c[j] > 0.0f)) ? fmul(a[j], c[j]) : 0.0f;
+    });
+  }
+};
 
 // ---- MonoMixerModule::calc, src/synth/mixer.rs:101-122 -------------------------
-__device__ __forceinline__ void op_mixer(const Instr& ins, const Lane& ln, int kk) {
-  float* out = wire(ln, ins.out[0]);
-  if (!out) return;
-  const uint32_t* pp = ln.pr + ins.param * L;
-  const float* in[4];
+struct MixerOp {
   float gain[4];
+  __device__ __forceinline__ void load(const Instr& ins, const Lane& ln) {
+    const uint32_t* pp = ln.pr + ins.param * L;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    in[j] = wire(ln, ins.in[j]);
-    gain[j] = __uint_as_float(pp[j * L]);
+    for (int j = 0; j < 4; ++j) gain[j] = __uint_as_float(pp[j * L]);
   }
-  for_groups(kk, [&](auto u, int k0) {
-    constexpr int U = decltype(u)::value;
-    float o[U];  // output.fill(0.0) then `*dst += src * gain` per connected input, in order
+  __device__ __forceinline__ void store() {}
+  __device__ __forceinline__ void run(const Instr& ins, const Lane& ln, int kk) {
+    float* out = wire(ln, ins.out[0]);
+    if (!out) return;
+    const float* in0 = wire(ln, ins.in[0]);
+    const float* in1 = wire(ln, ins.in[1]);
+    const float* in2 = wire(ln, ins.in[2]);
+    const float* in3 = wire(ln, ins.in[3]);
+    for_groups(kk, [&](auto u, int k0) {
+      constexpr int U = decltype(u)::value;
+      float o[U];  // output.fill(0.0) then `*dst += src * gain` per connected input, in order
 #pragma unroll
-    for (int j = 0; j < U; ++j) o[j] = 0.0f;
+      for (int j = 0; j < U; ++j) o[j] = 0.0f;
+      if (in0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (in[i]) {
+        for (int j = 0; j < U; ++j) o[j] = fadd(o[j], fmul(in0[(k0 + j) * L], gain[0]));
+      }
+      if (in1) {
 #pragma unroll
-        for (int j = 0; j < U; ++j) o[j] = fadd(o[j], fmul(in[i][(k0 + j) * L], gain[i]));
+        for (int j = 0; j < U; ++j) o[j] = fadd(o[j], fmul(in1[(k0 + j) * L], gain[1]));
+      }
+      if (in2) {
+#pragma unroll
+        for (int j = 0; j < U; ++j) o[j] = fadd(o[j], fmul(in2[(k0 + j) * L], gain[2]));
+      }
+      if (in3) {
+#pragma unroll
+        for (int j = 0; j < U; ++j) o[j] = fadd(o[j], fmul(in3[(k0 + j) * L], gain[3]));
       }
 #pragma unroll
-    for (int j = 0; j < U; ++j) out[(k0 + j) * L] = o[j];
-  });
-}
+      for (int j = 0; j < U; ++j) out[(k0 + j) * L] = o[j];
+    });
+  }
+};
 
 // ---- MathModule / NonLinearModule::calc, src/synth/math.rs:139-160, :292-313 ----
+// math.rs:203-205 `if a > 0.0 { a.powf(b) } else { -(-a).powf(b) }` in f32.  glibc's powf
+// evaluates in f64 and rounds once; f64 pow here then one rounding agrees with it except
+// when the f64 results straddle an f32 rounding boundary.  Out of line: pow() is large.
+__device__ __noinline__ float nonlinear(float a, float b) {
+  return a > 0.0f ? __double2float_rn(pow((double)a, (double)b)) : -__double2float_rn(pow((double)(-a), (double)b));
+}
+
 template <int WHICH>
 __device__ __forceinline__ float math_op(float a, float b) {
   if (WHICH == F_MATH_ADD) return fadd(a, b);
   if (WHICH == F_MATH_SUB) return fsub(a, b);
   if (WHICH == F_MATH_MUL) return fmul(a, b);
-  // math.rs:203-205 `if a > 0.0 { a.powf(b) } else { -(-a).powf(b) }` in f32.  glibc's powf
-  // evaluates in f64 and rounds once; f64 pow here then one rounding agrees with it except
-  // when the f64 results straddle an f32 rounding boundary.
-  return a > 0.0f ? __double2float_rn(pow((double)a, (double)b)) : -__double2float_rn(pow((double)(-a), (double)b));
+  return nonlinear(a, b);
 }
 
-template <int WHICH>
-__device__ __forceinline__ void op_math(const Instr& ins, const Lane& ln, int kk) {
-  float* out = wire(ln, ins.out[0]);
-  if (!out) return;
-  const float constant = __uint_as_float(ln.pr[ins.param * L]);
-  const float* i1 = wire(ln, ins.in[0]);
-  const float* i2 = wire(ln, ins.in[1]);
-  for_groups(kk, [&](auto u, int k0) {
-    constexpr int U = decltype(u)::value;
-    float a[U], b[U];
-#pragma unroll
-    for (int j = 0; j < U; ++j) {
-      a[j] = i1 ? i1[(k0 + j) * L] : 0.0f;      // (None, _) => 0.0
-      b[j] = i2 ? i2[(k0 + j) * L] : constant;  // (_, None) => constant
-    }
-#pragma unroll
-    for (int j = 0; j < U; ++j) out[(k0 + j) * L] = math_op<WHICH>(a[j], b[j]);
-  });
-}
-
-__device__ __forceinline__ void op_math_dispatch(const Instr& ins, const Lane& ln, int kk) {
-  switch (ins.flags) {
-    case F_MATH_ADD: op_math<F_MATH_ADD>(ins, ln, kk); break;
-    case F_MATH_SUB: op_math<F_MATH_SUB>(ins, ln, kk); break;
-    case F_MATH_MUL: op_math<F_MATH_MUL>(ins, ln, kk); break;
-    default: op_math<F_MATH_NONLIN>(ins, ln, kk); break;
+struct MathOp {
+  float constant;
+  __device__ __forceinline__ void load(const Instr& ins, const Lane& ln) {
+    constant = __uint_as_float(ln.pr[ins.param * L]);
   }
-}
+  __device__ __forceinline__ void store() {}
+
+  template <int WHICH>
+  __device__ __forceinline__ void run_t(const Instr& ins, const Lane& ln, int kk) {
+    float* out = wire(ln, ins.out[0]);
+    if (!out) return;
+    const float* i1 = wire(ln, ins.in[0]);
+    const float* i2 = wire(ln, ins.in[1]);
+    for_groups(kk, [&](auto u, int k0) {
+      constexpr int U = decltype(u)::value;
+      float a[U], b[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        a[j] = i1 ? i1[(k0 + j) * L] : 0.0f;      // (None, _) => 0.0
+        b[j] = i2 ? i2[(k0 + j) * L] : constant;  // (_, None) => constant
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j) out[(k0 + j) * L] = math_op<WHICH>(a[j], b[j]);
+    });
+  }
+  __device__ __forceinline__ void run(const Instr& ins, const Lane& ln, int kk) {
+    switch (ins.flags) {
+      case F_MATH_ADD: run_t<F_MATH_ADD>(ins, ln, kk); break;
+      case F_MATH_SUB: run_t<F_MATH_SUB>(ins, ln, kk); break;
+      case F_MATH_MUL: run_t<F_MATH_MUL>(ins, ln, kk); break;
+      default: run_t<F_MATH_NONLIN>(ins, ln, kk); break;
+    }
+  }
+};
 
 }  // namespace dsp
 }  // namespace srk

@@ -45,11 +45,120 @@ struct RenderArgs {
   uint32_t n_samples;
   uint32_t S, P, C, B;
   uint32_t K;             // samples per chunk: power of two <= 32
+  uint32_t log2K;
   uint32_t ring_phase;    // absolute sample index of sample 0, mod B
   uint32_t seed_lo, seed_hi;
 };
 
 constexpr int kMaxThreads = kMaxWarps * 32;
+
+// What the ring and output ops need beyond dsp::Lane.
+struct GroupCtx {
+  const RenderArgs& a;
+  uint32_t v;         // this lane's voice (idle lanes shadow the last voice)
+  uint32_t n_active;  // voices of this group that exist
+  bool active;
+  int lane;
+  bool solo;          // one warp runs the whole program in plan order
+};
+
+// OP_RING_LOAD / OP_RING_STORE: the delayed (feedback) wires, rings f32 [R][B][V] in HBM.
+__device__ __forceinline__ void run_ring_load(const Instr& ins, const dsp::Lane& ln, const GroupCtx& g, uint32_t n0, int kk) {
+  const RenderArgs& a = g.a;
+  const float* ring = a.rings + (size_t)ins.aux * a.B * a.V + g.v;
+  float* out = dsp::wire(ln, ins.out[0]);
+  uint32_t idx = (a.ring_phase + n0) % a.B;
+  for (int k = 0; k < kk; ++k) {
+    out[k * 32] = ring[(size_t)idx * a.V];
+    idx = idx + 1 == a.B ? 0 : idx + 1;
+  }
+}
+
+__device__ __forceinline__ void run_ring_store(const Instr& ins, const dsp::Lane& ln, const GroupCtx& g, uint32_t n0, int kk) {
+  const RenderArgs& a = g.a;
+  float* ring = a.rings + (size_t)ins.aux * a.B * a.V + g.v;
+  const float* in = dsp::wire(ln, ins.in[0]);
+  uint32_t idx = (a.ring_phase + n0) % a.B;
+  for (int k = 0; k < kk; ++k) {
+    if (g.active) ring[(size_t)idx * a.V] = in[k * 32];
+    idx = idx + 1 == a.B ? 0 : idx + 1;
+  }
+}
+
+// OP_OUTPUT: OutputModule::calc, src/synth/output.rs:46-60 (stems), + this group's share of the mix.
+__device__ __forceinline__ void run_output(const Instr& ins, const dsp::Lane& ln, const GroupCtx& g, uint32_t n0, int kk) {
+  const RenderArgs& a = g.a;
+  const uint32_t K = a.K;
+  const int lane = g.lane;
+  if (g.solo) __syncwarp();  // the tile was written by this warp a moment ago
+  float sum = 0.0f;
+  for (int j = 0; j < ins.n_ch; ++j) {
+    const uint32_t c = ins.aux + j;
+    const float* src = dsp::wire(ln, ins.in[j]);
+    if (a.stems && g.active) {
+      float* dst = a.stems + ((size_t)c * a.n_samples + n0) * a.V + g.v;
+      if (src) {
+        dsp::for_groups(kk, [&](auto u, int k0) {
+          constexpr int U = decltype(u)::value;
+          float x[U];
+#pragma unroll
+          for (int q = 0; q < U; ++q) x[q] = src[(k0 + q) * 32];
+#pragma unroll
+          for (int q = 0; q < U; ++q) __stcs(dst + (size_t)(k0 + q) * a.V, x[q]);
+        });
+      } else {
+        for (int k = 0; k < kk; ++k) __stcs(dst + (size_t)k * a.V, 0.0f);
+      }
+    }
+    if (a.partial) {
+      if (!src) {
+        sum = 0.0f;
+      } else if (j == 0 || ins.in[j] != ins.in[j - 1]) {
+        // Transposed read of the [K][32] tile: lane (k, seg) adds K columns of sample row k
+        // (rotated start => 32 lanes on 32 banks), then a butterfly over seg.
+        const uint32_t k = lane & (K - 1), seg = lane >> a.log2K;
+        const float* row = src - lane + k * 32 + seg * K;
+        const uint32_t col0 = seg * K;
+        float acc = 0.0f;
+#pragma unroll 4
+        for (uint32_t q = 0; q < K; ++q) {
+          const uint32_t col = (q + k) & (K - 1);
+          const float x = row[col];
+          acc = dsp::fadd(acc, col0 + col < g.n_active ? x : 0.0f);
+        }
+        for (uint32_t off = K; off < 32; off <<= 1) acc = dsp::fadd(acc, __shfl_xor_sync(0xFFFFFFFFu, acc, off));
+        sum = acc;
+      }  // else: same wire as the previous channel, same sums
+      if (lane < kk) a.partial[((size_t)blockIdx.x * a.C + c) * a.n_samples + n0 + lane] = sum;
+    }
+  }
+}
+
+// A warp that owns ONE instruction keeps the module's state in registers for the whole
+// render: load once, one run() + one block barrier per iteration, store once.
+template <class Op>
+__device__ __forceinline__ void run_resident(const Instr& ins, dsp::Lane& ln, const RenderArgs& a, uint32_t n_chunks,
+                                             uint32_t n_iter) {
+  Op op;
+  op.load(ins, ln);
+  for (uint32_t it = 0; it < n_iter; ++it) {
+    const uint32_t chunk = it - ins.stage;
+    if (chunk < n_chunks) {  // also false while it < stage (wraps)
+      ln.chunk = chunk;
+      op.run(ins, ln, (int)min(a.K, a.n_samples - chunk * a.K));
+    }
+    __syncthreads();
+  }
+  op.store();
+}
+
+template <class Op>
+__device__ __forceinline__ void run_once(const Instr& ins, const dsp::Lane& ln, int kk) {
+  Op op;
+  op.load(ins, ln);
+  op.run(ins, ln, kk);
+  op.store();
+}
 
 __global__ void __launch_bounds__(kMaxThreads, 1) render_voices_kernel(const RenderArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -71,96 +180,50 @@ __global__ void __launch_bounds__(kMaxThreads, 1) render_voices_kernel(const Ren
   for (uint32_t w = wid; w < a.P; w += a.n_warps) pr[w * 32 + lane] = a.params[(size_t)w * a.V + v];
   __syncthreads();
 
-  dsp::Lane ln{st + lane, pr + lane, tiles + lane, wd, a.K * 32, 0};
+  dsp::Lane ln{st + lane, pr + lane, tiles + lane, wd, a.K * 32, 0, a.voice_offset + v, a.seed_lo, a.seed_hi};
   const uint32_t pc0 = warp_begin[wid], pc1 = warp_begin[wid + 1];
   const uint32_t K = a.K;
   const uint32_t n_chunks = (a.n_samples + K - 1) / K;
   const uint32_t n_iter = n_chunks + a.n_stages - 1;
-  const bool solo = a.n_warps == 1;
-  for (uint32_t it = 0; it < n_iter; ++it) {
-    for (uint32_t pc = pc0; pc < pc1; ++pc) {
-      const Instr ins = prog[pc];
-      const uint32_t chunk = it - ins.stage;
-      if (chunk >= n_chunks) continue;  // also catches it < stage (wraps)
-      const uint32_t n0 = chunk * K;
-      const int kk = (int)min(K, a.n_samples - n0);
-      ln.chunk = chunk;
-      switch (ins.op) {
-        case OP_OSC: dsp::op_osc_dispatch(ins, ln, kk); break;
-        case OP_MOOG: dsp::op_moog_dispatch(ins, ln, kk); break;
-        case OP_ADSR: dsp::op_adsr(ins, ln, kk); break;
-        case OP_VCA: dsp::op_vca(ins, ln, kk); break;
-        case OP_MIXER: dsp::op_mixer(ins, ln, kk); break;
-        case OP_MATH: dsp::op_math_dispatch(ins, ln, kk); break;
-        case OP_NOISE: dsp::op_noise(ins, ln, kk, a.voice_offset + v, a.seed_lo, a.seed_hi); break;
-        case OP_RING_LOAD: {
-          const float* ring = a.rings + (size_t)ins.aux * a.B * a.V + v;
-          float* out = dsp::wire(ln, ins.out[0]);
-          uint32_t idx = (a.ring_phase + n0) % a.B;
-          for (int k = 0; k < kk; ++k) {
-            out[k * 32] = ring[(size_t)idx * a.V];
-            idx = idx + 1 == a.B ? 0 : idx + 1;
-          }
-          break;
-        }
-        case OP_RING_STORE: {
-          float* ring = a.rings + (size_t)ins.aux * a.B * a.V + v;
-          const float* in = dsp::wire(ln, ins.in[0]);
-          uint32_t idx = (a.ring_phase + n0) % a.B;
-          for (int k = 0; k < kk; ++k) {
-            if (active) ring[(size_t)idx * a.V] = in[k * 32];
-            idx = idx + 1 == a.B ? 0 : idx + 1;
-          }
-          break;
-        }
-        case OP_OUTPUT: {  // OutputModule::calc, src/synth/output.rs:46-60, + mixdown
-          if (solo) __syncwarp();  // the tile was written by this warp a moment ago
-          float sum = 0.0f;
-          for (int j = 0; j < ins.n_ch; ++j) {
-            const uint32_t c = ins.aux + j;
-            const float* src = dsp::wire(ln, ins.in[j]);
-            if (a.stems && active) {
-              float* dst = a.stems + ((size_t)c * a.n_samples + n0) * a.V + v;
-              if (src) {
-                dsp::for_groups(kk, [&](auto u, int k0) {
-                  constexpr int U = decltype(u)::value;
-                  float x[U];
-#pragma unroll
-                  for (int q = 0; q < U; ++q) x[q] = src[(k0 + q) * 32];
-#pragma unroll
-                  for (int q = 0; q < U; ++q) __stcs(dst + (size_t)(k0 + q) * a.V, x[q]);
-                });
-              } else {
-                for (int k = 0; k < kk; ++k) __stcs(dst + (size_t)k * a.V, 0.0f);
-              }
-            }
-            if (a.partial) {
-              if (!src) {
-                sum = 0.0f;
-              } else if (j == 0 || ins.in[j] != ins.in[j - 1]) {
-                // Transposed read of the [K][32] tile: lane (k, seg) adds K columns of sample
-                // row k (rotated start => 32 lanes on 32 banks), then a butterfly over seg.
-                const uint32_t k = lane & (K - 1), seg = lane / K;
-                const float* row = src - lane + k * 32 + seg * K;
-                const uint32_t col0 = seg * K;
-                float acc = 0.0f;
-                for (uint32_t q = 0; q < K; ++q) {
-                  const uint32_t col = (q + k) & (K - 1);
-                  const float x = row[col];
-                  acc = dsp::fadd(acc, col0 + col < n_active ? x : 0.0f);
-                }
-                for (uint32_t off = K; off < 32; off <<= 1) acc = dsp::fadd(acc, __shfl_xor_sync(0xFFFFFFFFu, acc, off));
-                sum = acc;
-              }  // else: same wire as the previous channel, same sums
-              if (lane < kk) a.partial[((size_t)blockIdx.x * a.C + c) * a.n_samples + n0 + lane] = sum;
-            }
-          }
-          break;
-        }
-        default: break;
-      }
+  const GroupCtx g{a, v, n_active, active, lane, a.n_warps == 1};
+
+  bool resident = false;
+  if (!g.solo && pc1 == pc0 + 1) {
+    const Instr ins = prog[pc0];
+    resident = true;
+    switch (ins.op) {
+      case OP_OSC: run_resident<dsp::OscOp>(ins, ln, a, n_chunks, n_iter); break;
+      case OP_MOOG: run_resident<dsp::MoogOp>(ins, ln, a, n_chunks, n_iter); break;
+      case OP_ADSR: run_resident<dsp::AdsrOp>(ins, ln, a, n_chunks, n_iter); break;
+      case OP_NOISE: run_resident<dsp::NoiseOp>(ins, ln, a, n_chunks, n_iter); break;
+      default: resident = false; break;  // stateless ops: nothing to keep
     }
-    if (solo) __syncwarp(); else __syncthreads();
+  }
+  if (!resident) {
+    for (uint32_t it = 0; it < n_iter; ++it) {
+      for (uint32_t pc = pc0; pc < pc1; ++pc) {
+        const Instr ins = prog[pc];
+        const uint32_t chunk = it - ins.stage;
+        if (chunk >= n_chunks) continue;  // also catches it < stage (wraps)
+        const uint32_t n0 = chunk * K;
+        const int kk = (int)min(K, a.n_samples - n0);
+        ln.chunk = chunk;
+        switch (ins.op) {
+          case OP_OSC: run_once<dsp::OscOp>(ins, ln, kk); break;
+          case OP_MOOG: run_once<dsp::MoogOp>(ins, ln, kk); break;
+          case OP_ADSR: run_once<dsp::AdsrOp>(ins, ln, kk); break;
+          case OP_NOISE: run_once<dsp::NoiseOp>(ins, ln, kk); break;
+          case OP_VCA: run_once<dsp::VcaOp>(ins, ln, kk); break;
+          case OP_MIXER: run_once<dsp::MixerOp>(ins, ln, kk); break;
+          case OP_MATH: run_once<dsp::MathOp>(ins, ln, kk); break;
+          case OP_RING_LOAD: run_ring_load(ins, ln, g, n0, kk); break;
+          case OP_RING_STORE: run_ring_store(ins, ln, g, n0, kk); break;
+          case OP_OUTPUT: run_output(ins, ln, g, n0, kk); break;
+          default: break;
+        }
+      }
+      if (g.solo) __syncwarp(); else __syncthreads();
+    }
   }
   __syncthreads();
   if (active)
@@ -517,6 +580,8 @@ int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t
   a.C = (uint32_t)C;
   a.B = std::max<uint32_t>(prog.ring_len, 1);
   a.K = (uint32_t)K;
+  a.log2K = 0;
+  while ((1u << a.log2K) < a.K) ++a.log2K;
   a.ring_phase = (uint32_t)(e.n_abs % a.B);
   a.seed_lo = (uint32_t)patch->seed;
   a.seed_hi = (uint32_t)(patch->seed >> 32);
