@@ -106,6 +106,21 @@ __device__ __forceinline__ float* wire(const Lane& ln, int slot) {
   return ln.tiles + (size_t)(d.base + (ln.chunk & d.mask)) * ln.tile_elems;
 }
 
+// A wire slot resolved once (at load()): first tile of its ring + ring mask; at() picks
+// the tile of the chunk being worked on.  nullptr base = not connected / nobody reads it.
+struct Port {
+  float* base;
+  uint32_t mask;
+  __device__ __forceinline__ float* at(const Lane& ln) const {
+    return base ? base + (ln.chunk & mask) * ln.tile_elems : nullptr;
+  }
+};
+__device__ __forceinline__ Port port(const Lane& ln, int slot) {
+  if (slot < 0) return Port{nullptr, 0};
+  const WireDesc d = ln.wd[slot];
+  return Port{ln.tiles + d.base * ln.tile_elems, d.mask};
+}
+
 template <int U>
 using UC = std::integral_constant<int, U>;
 
@@ -126,6 +141,7 @@ struct OscOp {
   uint32_t* s;
   double pos, val, delta_const, sr;
   bool last, aa;
+  Port p_cv, p_sync, p_sine, p_square, p_saw;
 
   __device__ __forceinline__ void load(const Instr& ins, const Lane& ln) {
     s = ln.st + ins.state * L;
@@ -136,6 +152,8 @@ struct OscOp {
     delta_const = __hiloint2double((int)p[2 * L], (int)p[L]);
     sr = (double)ins.imm;
     aa = __uint_as_float(p[3 * L]) != 0.0f;
+    p_cv = port(ln, ins.in[0]); p_sync = port(ln, ins.in[1]);
+    p_sine = port(ln, ins.out[0]); p_square = port(ln, ins.out[1]); p_saw = port(ln, ins.out[2]);
   }
   __device__ __forceinline__ void store() {
     s[0] = (uint32_t)__double2loint(pos);
@@ -143,40 +161,46 @@ struct OscOp {
     s[2 * L] = last ? 1u : 0u;
   }
 
-  template <bool HAS_CV, bool HAS_SYNC>
-  __device__ __forceinline__ void run_t(const Instr& ins, const Lane& ln, int kk) {
-    const float* cv = wire(ln, ins.in[0]);
-    const float* sync = wire(ln, ins.in[1]);
-    float* sine = wire(ln, ins.out[0]);
-    float* square = wire(ln, ins.out[1]);
-    float* saw = wire(ln, ins.out[2]);
+  // OUTS: bit 0 sine, bit 1 square, bit 2 saw are read by somebody.  Compile-time, because a
+  // per-group `if (port connected)` costs more than the arithmetic it guards (see header).
+  template <bool HAS_CV, int OUTS>
+  __device__ __forceinline__ void run_t(const Lane& ln, int kk) {
+    constexpr bool SINE = OUTS & 1, SQUARE = OUTS & 2, SAW = OUTS & 4;
+    const float* cv = p_cv.at(ln);
+    const float* sync = p_sync.at(ln);
+    const bool has_sync = sync != nullptr;
+    float* sine = p_sine.at(ln);
+    float* square = p_square.at(ln);
+    float* saw = p_saw.at(ln);
     for_groups(kk, [&](auto u, int k0) {
       constexpr int U = decltype(u)::value;
-      float cvv[U], syv[U];
+      float cvv[U];
+      bool edge[U];  // sync transition on this sample (:125-131)
       double ps[U], dl[U];
       if (HAS_CV) {
 #pragma unroll
         for (int j = 0; j < U; ++j) cvv[j] = cv[(k0 + j) * L];
       }
-      if (HAS_SYNC) {
 #pragma unroll
-        for (int j = 0; j < U; ++j) syv[j] = sync[(k0 + j) * L];
+      for (int j = 0; j < U; ++j) edge[j] = false;
+      if (has_sync) {
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const bool above = sync[(k0 + j) * L] > 0.0f;
+          edge[j] = above & !last;
+          last = above;
+        }
       }
       // get_freq_in_hz (:43-48) then / sample_rate (:132): stateless
 #pragma unroll
       for (int j = 0; j < U; ++j)
         dl[j] = HAS_CV ? __ddiv_rn(dmul(440.0, exp2(dadd((double)cvv[j], val))), sr) : delta_const;
-      // the recurrence: sync reset (:125-131), pos += delta; pos %= 1.0 (:151-152)
+      // the recurrence: sync reset, pos += delta; pos %= 1.0 (:151-152)
       const double pos0 = pos;
-      const bool last0 = last;
       bool odd = false;
 #pragma unroll
       for (int j = 0; j < U; ++j) {
-        if (HAS_SYNC) {
-          const bool above = syv[j] > 0.0f;
-          pos = (above & !last) ? 0.0 : pos;
-          last = above;
-        }
+        pos = edge[j] ? 0.0 : pos;
         ps[j] = pos;
         const double x = dadd(pos, dl[j]);
         odd |= !(x < 2.0);  // NaN, inf or a step of more than one period: exact path below
@@ -184,39 +208,29 @@ struct OscOp {
       }
       if (odd) {
         pos = pos0;
-        last = last0;
 #pragma unroll
         for (int j = 0; j < U; ++j) {
-          if (HAS_SYNC) {
-            const bool above = syv[j] > 0.0f;
-            pos = (above & !last) ? 0.0 : pos;
-            last = above;
-          }
+          pos = edge[j] ? 0.0 : pos;
           ps[j] = pos;
           pos = fmod1_exact(dadd(pos, dl[j]));
         }
       }
-      if (sine) {
+      if (SINE) {
 #pragma unroll
         for (int j = 0; j < U; ++j)
           sine[(k0 + j) * L] = __double2float_rn(sin(dmul(dmul(ps[j], 3.14159265358979323846), 2.0)));
       }
-      if (square || saw) {
-        // polyBLEP corrections (:135-149): zero unless a sample sits within dt of a
-        // discontinuity; one branch per group decides whether the evaluation runs at all
-        double om[U], p2[U], pb0[U], pb1[U];
+      if (SQUARE || SAW) {
+        // polyBLEP corrections (:135-149) are zero unless a sample sits within dt of a
+        // discontinuity: one test per group picks the plain or the corrected write-out.
+        // (x - 0.0f == x bit for bit, so the plain path skips the subtraction.)
+        double om[U], p2[U];
         bool near = false;
 #pragma unroll
         for (int j = 0; j < U; ++j) {
           om[j] = dsub(1.0, dl[j]);
-          pb0[j] = 0.0;
-          pb1[j] = 0.0;
-          p2[j] = 0.0;
           near |= (ps[j] < dl[j]) | (ps[j] > om[j]);
-        }
-        if (square) {
-#pragma unroll
-          for (int j = 0; j < U; ++j) {
+          if (SQUARE) {
             // (pos + 0.5) % 1.0: pos is in [0, 1) or NaN (it is itself the result of `% 1.0`
             // of a non-negative sum), so the sum is in [0.5, 1.5)
             p2[j] = wrap01(dadd(ps[j], 0.5));
@@ -224,40 +238,55 @@ struct OscOp {
           }
         }
         if (aa & near) {
+          double pb0[U];
 #pragma unroll
           for (int j = 0; j < U; ++j) pb0[j] = blep_eval(ps[j], dl[j], om[j]);
-          if (square) {
+          if (SQUARE) {
 #pragma unroll
-            for (int j = 0; j < U; ++j) pb1[j] = blep_eval(p2[j], dl[j], om[j]);
+            for (int j = 0; j < U; ++j) {
+              const float base = ps[j] < 0.5 ? -1.0f : 1.0f;
+              square[(k0 + j) * L] = fsub(base, __double2float_rn(dsub(pb0[j], blep_eval(p2[j], dl[j], om[j]))));
+            }
           }
-        }
-        if (square) {
+          if (SAW) {
 #pragma unroll
-          for (int j = 0; j < U; ++j) {
-            const float base = ps[j] < 0.5 ? -1.0f : 1.0f;
-            square[(k0 + j) * L] = fsub(base, __double2float_rn(dsub(pb0[j], pb1[j])));
+            for (int j = 0; j < U; ++j)
+              saw[(k0 + j) * L] = fsub(fsub(fmul(__double2float_rn(ps[j]), 2.0f), 1.0f), __double2float_rn(pb0[j]));
           }
-        }
-        if (saw) {
+        } else {
+          if (SQUARE) {
 #pragma unroll
-          for (int j = 0; j < U; ++j)
-            saw[(k0 + j) * L] = fsub(fsub(fmul(__double2float_rn(ps[j]), 2.0f), 1.0f), __double2float_rn(pb0[j]));
+            for (int j = 0; j < U; ++j) square[(k0 + j) * L] = ps[j] < 0.5 ? -1.0f : 1.0f;
+          }
+          if (SAW) {
+#pragma unroll
+            for (int j = 0; j < U; ++j) saw[(k0 + j) * L] = fsub(fmul(__double2float_rn(ps[j]), 2.0f), 1.0f);
+          }
         }
       }
     });
     // with no sync input the detector sees 0.0 every sample: `last` just goes false
-    if (!HAS_SYNC && kk > 0) last = false;
+    if (!has_sync && kk > 0) last = false;
   }
 
-  __device__ __forceinline__ void run(const Instr& ins, const Lane& ln, int kk) {
-    const bool cv = ins.in[0] >= 0, sync = ins.in[1] >= 0;
-    if (cv) {
-      if (sync) run_t<true, true>(ins, ln, kk);
-      else run_t<true, false>(ins, ln, kk);
-    } else {
-      if (sync) run_t<false, true>(ins, ln, kk);
-      else run_t<false, false>(ins, ln, kk);
+  template <bool HAS_CV>
+  __device__ __forceinline__ void run_outs(const Lane& ln, int kk) {
+    const int outs = (p_sine.base ? 1 : 0) | (p_square.base ? 2 : 0) | (p_saw.base ? 4 : 0);
+    switch (outs) {
+      case 0: run_t<HAS_CV, 0>(ln, kk); break;
+      case 1: run_t<HAS_CV, 1>(ln, kk); break;
+      case 2: run_t<HAS_CV, 2>(ln, kk); break;
+      case 3: run_t<HAS_CV, 3>(ln, kk); break;
+      case 4: run_t<HAS_CV, 4>(ln, kk); break;
+      case 5: run_t<HAS_CV, 5>(ln, kk); break;
+      case 6: run_t<HAS_CV, 6>(ln, kk); break;
+      default: run_t<HAS_CV, 7>(ln, kk); break;
     }
+  }
+
+  __device__ __forceinline__ void run(const Instr&, const Lane& ln, int kk) {
+    if (p_cv.base) run_outs<true>(ln, kk);
+    else run_outs<false>(ln, kk);
   }
 };
 
@@ -265,17 +294,19 @@ struct OscOp {
 struct NoiseOp {
   uint32_t* s;
   uint64_t n;
+  Port p_out;
 
   __device__ __forceinline__ void load(const Instr& ins, const Lane& ln) {
     s = ln.st + ins.state * L;
     n = ((uint64_t)s[L] << 32) | s[0];
+    p_out = port(ln, ins.out[0]);
   }
   __device__ __forceinline__ void store() {
     s[0] = (uint32_t)n;
     s[L] = (uint32_t)(n >> 32);
   }
   __device__ __forceinline__ void run(const Instr& ins, const Lane& ln, int kk) {
-    float* out = wire(ln, ins.out[0]);
+    float* out = p_out.at(ln);
     if (out) {
       auto draw = [&](uint64_t blk, uint32_t (&c)[4]) {
         c[0] = (uint32_t)blk; c[1] = (uint32_t)(blk >> 32); c[2] = ln.voice; c[3] = ins.aux;
@@ -334,6 +365,7 @@ struct MoogOp {
   uint32_t* s;
   float f, p, q, b0, b1, b2, b3, b4, c_freq, c_res;
   float freq, r, exp_amt;
+  Port p_audio, p_cv, p_lp, p_bp, p_hp;
 
   __device__ __forceinline__ void load(const Instr& ins, const Lane& ln) {
     s = ln.st + ins.state * L;
@@ -345,6 +377,8 @@ struct MoogOp {
     freq = __uint_as_float(pp[0]);
     r = fminf(fmaxf(__uint_as_float(pp[L]), 0.0f), 1.0f);  // :214
     exp_amt = __uint_as_float(pp[2 * L]);
+    p_audio = port(ln, ins.in[0]); p_cv = port(ln, ins.in[1]);
+    p_lp = port(ln, ins.out[0]); p_bp = port(ln, ins.out[1]); p_hp = port(ln, ins.out[2]);
   }
   __device__ __forceinline__ void store() {
     s[0] = __float_as_uint(f); s[L] = __float_as_uint(p); s[2 * L] = __float_as_uint(q);
@@ -353,13 +387,15 @@ struct MoogOp {
     s[8 * L] = __float_as_uint(c_freq); s[9 * L] = __float_as_uint(c_res);
   }
 
-  template <bool HAS_AUDIO, bool HAS_CV>
-  __device__ __forceinline__ void run_t(const Instr& ins, const Lane& ln, int kk) {
-    const float* audio = wire(ln, ins.in[0]);
-    const float* cv = wire(ln, ins.in[1]);
-    float* lowpass = wire(ln, ins.out[0]);
-    float* bandpass = wire(ln, ins.out[1]);
-    float* highpass = wire(ln, ins.out[2]);
+  // OUTS: bit 0 lowpass, bit 1 bandpass, bit 2 highpass are read by somebody (compile-time,
+  // like OscOp's).
+  template <bool HAS_CV, int OUTS>
+  __device__ __forceinline__ void run_t(const Lane& ln, int kk) {
+    const float* audio = p_audio.at(ln);
+    const float* cv = p_cv.at(ln);
+    float* lowpass = p_lp.at(ln);
+    float* bandpass = p_bp.at(ln);
+    float* highpass = p_hp.at(ln);
     bool virgin = (c_freq == 0.0f) & (c_res == 0.0f) & (f == 0.0f);
     if (!HAS_CV && kk > 0) {  // cutoff is constant over the chunk: one cache check (:61)
       const float fc = fminf(fmaxf(fadd(freq, fmul(0.0f, exp_amt)), 0.0f), 0.9f);  // :213 with cv = 0.0
@@ -373,7 +409,11 @@ struct MoogOp {
       constexpr int U = decltype(u)::value;
       float a[U], fj[U], pj[U], qj[U], in_[U], o3[U], o4[U];
 #pragma unroll
-      for (int j = 0; j < U; ++j) a[j] = HAS_AUDIO ? audio[(k0 + j) * L] : 0.0f;
+      for (int j = 0; j < U; ++j) a[j] = 0.0f;
+      if (audio) {
+#pragma unroll
+        for (int j = 0; j < U; ++j) a[j] = audio[(k0 + j) * L];
+      }
       if (HAS_CV) {
         float fc[U];
 #pragma unroll
@@ -410,30 +450,39 @@ struct MoogOp {
         in_[j] = in; o3[j] = b3; o4[j] = b4;
       }
       // calc returns (b4, in - b4, 3*(b3-b4)) assigned to (lowpass, highpass, bandpass), :211
-      if (lowpass) {
+      if (OUTS & 1) {
 #pragma unroll
         for (int j = 0; j < U; ++j) lowpass[(k0 + j) * L] = o4[j];
       }
-      if (highpass) {
+      if (OUTS & 4) {
 #pragma unroll
         for (int j = 0; j < U; ++j) highpass[(k0 + j) * L] = fsub(in_[j], o4[j]);
       }
-      if (bandpass) {
+      if (OUTS & 2) {
 #pragma unroll
         for (int j = 0; j < U; ++j) bandpass[(k0 + j) * L] = fmul(3.0f, fsub(o3[j], o4[j]));
       }
     });
   }
 
-  __device__ __forceinline__ void run(const Instr& ins, const Lane& ln, int kk) {
-    const bool au = ins.in[0] >= 0, cv = ins.in[1] >= 0;
-    if (au) {
-      if (cv) run_t<true, true>(ins, ln, kk);
-      else run_t<true, false>(ins, ln, kk);
-    } else {
-      if (cv) run_t<false, true>(ins, ln, kk);
-      else run_t<false, false>(ins, ln, kk);
+  template <bool HAS_CV>
+  __device__ __forceinline__ void run_outs(const Lane& ln, int kk) {
+    const int outs = (p_lp.base ? 1 : 0) | (p_bp.base ? 2 : 0) | (p_hp.base ? 4 : 0);
+    switch (outs) {
+      case 0: run_t<HAS_CV, 0>(ln, kk); break;
+      case 1: run_t<HAS_CV, 1>(ln, kk); break;
+      case 2: run_t<HAS_CV, 2>(ln, kk); break;
+      case 3: run_t<HAS_CV, 3>(ln, kk); break;
+      case 4: run_t<HAS_CV, 4>(ln, kk); break;
+      case 5: run_t<HAS_CV, 5>(ln, kk); break;
+      case 6: run_t<HAS_CV, 6>(ln, kk); break;
+      default: run_t<HAS_CV, 7>(ln, kk); break;
     }
+  }
+
+  __device__ __forceinline__ void run(const Instr&, const Lane& ln, int kk) {
+    if (p_cv.base) run_outs<true>(ln, kk);
+    else run_outs<false>(ln, kk);
   }
 };
 
@@ -444,6 +493,7 @@ struct AdsrOp {
   uint32_t mode;
   bool last;
   float s_val, inc_a, inc_d, inc_r, one_minus_s;
+  Port p_gate, p_out;
 
   __device__ __forceinline__ void load(const Instr& ins, const Lane& ln) {
     s = ln.st + ins.state * L;
@@ -459,64 +509,128 @@ struct AdsrOp {
     inc_d = __fdiv_rn(1.0f, fmul(sr, d_sec));
     inc_r = __fdiv_rn(1.0f, fmul(sr, r_sec));
     one_minus_s = fsub(1.0f, s_val);
+    p_gate = port(ln, ins.in[0]);
+    p_out = port(ln, ins.out[0]);
   }
   __device__ __forceinline__ void store() {
     s[0] = __float_as_uint(phase); s[L] = __float_as_uint(r_val); s[2 * L] = __float_as_uint(from_a_val);
     s[3 * L] = mode | (last ? 1u << 8 : 0u);
   }
 
-  // The five-arm `match self.mode` (:144-200) as selects: each arm's next (mode, phase, r_val)
-  // is a few compares, and lanes in different modes then cost nothing extra.
+  // One sample of the five-arm `match self.mode` (:144-200) as selects: each arm's next
+  // (mode, phase, r_val) is a few compares, and lanes in different modes cost nothing extra.
+  __device__ __forceinline__ float step(float g, bool has_gate) {
+    const bool above = g > 0.0f;
+    const bool high = has_gate & above;         // `gate.is_some() && gate[i] > 0.0`
+    const bool low = !has_gate | (g <= 0.0f);   // `gate.is_none() || gate[i] <= 0.0` (NaN is neither)
+    const bool tr = above & !last;              // TransitionDetector, None => sees 0.0
+    last = above;
+    const bool m_none = mode == ADSR_NONE, m_att = mode == ADSR_ATTACK, m_dec = mode == ADSR_DECAY;
+    const bool m_sus = mode == ADSR_SUSTAIN, m_rel = mode == ADSR_RELEASE;
+    // Release restarts the attack first, then still advances by the release increment (:188-199)
+    const bool rel_retrig = m_rel & high;
+    const float ph0 = rel_retrig ? 0.0f : phase;
+    const float inc = m_att ? inc_a : m_dec ? inc_d : inc_r;
+    const float ph1 = fadd(ph0, inc);
+    const bool ge = ph1 >= 1.0f;
+    uint32_t nm = mode;
+    nm = (m_none & high) ? ADSR_ATTACK : nm;
+    nm = (m_att & ge) ? ADSR_DECAY : nm;
+    nm = m_dec ? (tr ? ADSR_ATTACK : ge ? ADSR_SUSTAIN : ADSR_DECAY) : nm;
+    nm = m_sus ? (tr ? ADSR_ATTACK : low ? ADSR_RELEASE : ADSR_SUSTAIN) : nm;
+    nm = m_rel ? (ge ? ADSR_NONE : rel_retrig ? ADSR_ATTACK : ADSR_RELEASE) : nm;
+    // next phase (None without a gate and Sustain keep theirs)
+    const bool zero = (m_none & high) | ((m_att | m_dec) & (ge | tr)) | (m_sus & (low | tr)) | (m_rel & ge);
+    const bool advance = m_att | m_dec | m_rel;
+    const float np = zero ? 0.0f : advance ? ph1 : phase;
+    // r_val: a retrigger during attack restarts from where the attack began; release end clears it
+    r_val = (m_att & !ge & tr) ? from_a_val : r_val;
+    r_val = (m_rel & ge) ? 0.0f : r_val;
+    mode = nm;
+    phase = np;
+    const bool n_att = mode == ADSR_ATTACK;
+    const float omp = fsub(1.0f, phase);
+    const float lin = fadd(n_att ? r_val : s_val, fmul(n_att ? fsub(1.0f, r_val) : one_minus_s, n_att ? phase : omp));
+    float v = lin;                              // Attack / Decay (:203-204)
+    v = mode == ADSR_RELEASE ? fmul(s_val, omp) : v;
+    v = mode == ADSR_SUSTAIN ? s_val : v;
+    v = mode == ADSR_NONE ? 0.0f : v;
+    r_val = n_att ? r_val : v;
+    from_a_val = n_att ? v : from_a_val;
+    return v;
+  }
+
+  // A group of samples in which nothing happens to the envelope's mode: no gate edge the
+  // current mode reacts to and no phase wrap.  Then each arm is two or three flops per
+  // sample (the same ones, in the same order, as step()).  Returns false -- with the
+  // state untouched -- when something does happen; the caller then runs step().
+  template <int U>
+  __device__ __forceinline__ bool quiet(const float (&g)[U], bool has_gate, float (&o)[U]) {
+    bool prev = last, any_tr = false, any_high = false, any_low = false;
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const bool above = g[j] > 0.0f;
+      any_tr |= above & !prev;
+      any_high |= has_gate & above;
+      any_low |= !has_gate | (g[j] <= 0.0f);
+      prev = above;
+    }
+    float ph[U];
+    bool ge = false;
+    const float inc = mode == ADSR_ATTACK ? inc_a : mode == ADSR_DECAY ? inc_d : inc_r;
+    float acc = phase;
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      acc = fadd(acc, inc);
+      ph[j] = acc;
+      ge |= acc >= 1.0f;
+    }
+    if (mode == ADSR_SUSTAIN) {
+      if (any_low | any_tr) return false;
+#pragma unroll
+      for (int j = 0; j < U; ++j) o[j] = s_val;
+      r_val = s_val;
+    } else if (mode == ADSR_NONE) {
+      if (any_high) return false;
+#pragma unroll
+      for (int j = 0; j < U; ++j) o[j] = 0.0f;
+      r_val = 0.0f;
+    } else if (mode == ADSR_ATTACK) {
+      if (ge | any_tr) return false;
+      const float span = fsub(1.0f, r_val);
+#pragma unroll
+      for (int j = 0; j < U; ++j) o[j] = fadd(r_val, fmul(span, ph[j]));
+      from_a_val = o[U - 1];
+      phase = acc;
+    } else if (mode == ADSR_DECAY) {
+      if (ge | any_tr) return false;
+#pragma unroll
+      for (int j = 0; j < U; ++j) o[j] = fadd(s_val, fmul(one_minus_s, fsub(1.0f, ph[j])));
+      r_val = o[U - 1];
+      phase = acc;
+    } else {  // Release
+      if (ge | any_high) return false;
+#pragma unroll
+      for (int j = 0; j < U; ++j) o[j] = fmul(s_val, fsub(1.0f, ph[j]));
+      r_val = o[U - 1];
+      phase = acc;
+    }
+    last = prev;
+    return true;
+  }
+
   __device__ __forceinline__ void run(const Instr& ins, const Lane& ln, int kk) {
-    const float* gate = wire(ln, ins.in[0]);
-    float* out = wire(ln, ins.out[0]);
+    const float* gate = p_gate.at(ln);
+    float* out = p_out.at(ln);
     const bool has_gate = gate != nullptr;
     for_groups(kk, [&](auto u, int k0) {
       constexpr int U = decltype(u)::value;
       float g[U], o[U];
 #pragma unroll
       for (int j = 0; j < U; ++j) g[j] = has_gate ? gate[(k0 + j) * L] : 0.0f;
+      if (!quiet<U>(g, has_gate, o)) {
 #pragma unroll
-      for (int j = 0; j < U; ++j) {
-        const bool above = g[j] > 0.0f;
-        const bool high = has_gate & above;            // `gate.is_some() && gate[i] > 0.0`
-        const bool low = !has_gate | (g[j] <= 0.0f);   // `gate.is_none() || gate[i] <= 0.0` (NaN is neither)
-        const bool tr = above & !last;                 // TransitionDetector, None => sees 0.0
-        last = above;
-        const bool m_none = mode == ADSR_NONE, m_att = mode == ADSR_ATTACK, m_dec = mode == ADSR_DECAY;
-        const bool m_sus = mode == ADSR_SUSTAIN, m_rel = mode == ADSR_RELEASE;
-        // Release restarts the attack first, then still advances by the release increment (:188-199)
-        const bool rel_retrig = m_rel & high;
-        const float ph0 = rel_retrig ? 0.0f : phase;
-        const float inc = m_att ? inc_a : m_dec ? inc_d : inc_r;
-        const float ph1 = fadd(ph0, inc);
-        const bool ge = ph1 >= 1.0f;
-        // next mode
-        uint32_t nm = mode;
-        nm = (m_none & high) ? ADSR_ATTACK : nm;
-        nm = (m_att & ge) ? ADSR_DECAY : nm;
-        nm = m_dec ? (tr ? ADSR_ATTACK : ge ? ADSR_SUSTAIN : ADSR_DECAY) : nm;
-        nm = m_sus ? (tr ? ADSR_ATTACK : low ? ADSR_RELEASE : ADSR_SUSTAIN) : nm;
-        nm = m_rel ? (ge ? ADSR_NONE : rel_retrig ? ADSR_ATTACK : ADSR_RELEASE) : nm;
-        // next phase (None without a gate and Sustain keep theirs)
-        const bool zero = (m_none & high) | ((m_att | m_dec) & (ge | tr)) | (m_sus & (low | tr)) | (m_rel & ge);
-        const bool advance = m_att | m_dec | m_rel;
-        const float np = zero ? 0.0f : advance ? ph1 : phase;
-        // r_val: a retrigger during attack restarts from where the attack began; release end clears it
-        r_val = (m_att & !ge & tr) ? from_a_val : r_val;
-        r_val = (m_rel & ge) ? 0.0f : r_val;
-        mode = nm;
-        phase = np;
-        const bool n_att = mode == ADSR_ATTACK;
-        const float omp = fsub(1.0f, phase);
-        const float lin = fadd(n_att ? r_val : s_val, fmul(n_att ? fsub(1.0f, r_val) : one_minus_s, n_att ? phase : omp));
-        float v = lin;                                 // Attack / Decay (:203-204)
-        v = mode == ADSR_RELEASE ? fmul(s_val, omp) : v;
-        v = mode == ADSR_SUSTAIN ? s_val : v;
-        v = mode == ADSR_NONE ? 0.0f : v;
-        o[j] = v;
-        r_val = n_att ? r_val : v;
-        from_a_val = n_att ? v : from_a_val;
+        for (int j = 0; j < U; ++j) o[j] = step(g[j], has_gate);
       }
       if (out) {
 #pragma unroll
@@ -529,14 +643,16 @@ struct AdsrOp {
 // ---- VCAModule::calc, src/synth/vca.rs:117-148 ---------------------------------
 struct VcaOp {
   bool negative;
+  Port p_audio, p_cv, p_out;
   __device__ __forceinline__ void load(const Instr& ins, const Lane& ln) {
     negative = __uint_as_float(ln.pr[ins.param * L]) != 0.0f;
+    p_audio = port(ln, ins.in[0]); p_cv = port(ln, ins.in[1]); p_out = port(ln, ins.out[0]);
   }
   __device__ __forceinline__ void store() {}
   __device__ __forceinline__ void run(const Instr& ins, const Lane& ln, int kk) {
-    const float* audio = wire(ln, ins.in[0]);
-    const float* cv = wire(ln, ins.in[1]);
-    float* out = wire(ln, ins.out[0]);
+    const float* audio = p_audio.at(ln);
+    const float* cv = p_cv.at(ln);
+    float* out = p_out.at(ln);
     if (!out) return;
     if (!(audio && cv)) {  // :143 `_ => output.fill(0.0)`
       for (int k = 0; k < kk; ++k) out[k * L] = 0.0f;
@@ -556,19 +672,24 @@ struct VcaOp {
 // ---- MonoMixerModule::calc, src/synth/mixer.rs:101-122 -------------------------
 struct MixerOp {
   float gain[4];
+  Port p_in[4], p_out;
   __device__ __forceinline__ void load(const Instr& ins, const Lane& ln) {
     const uint32_t* pp = ln.pr + ins.param * L;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) gain[j] = __uint_as_float(pp[j * L]);
+    for (int j = 0; j < 4; ++j) {
+      gain[j] = __uint_as_float(pp[j * L]);
+      p_in[j] = port(ln, ins.in[j]);
+    }
+    p_out = port(ln, ins.out[0]);
   }
   __device__ __forceinline__ void store() {}
   __device__ __forceinline__ void run(const Instr& ins, const Lane& ln, int kk) {
-    float* out = wire(ln, ins.out[0]);
+    float* out = p_out.at(ln);
     if (!out) return;
-    const float* in0 = wire(ln, ins.in[0]);
-    const float* in1 = wire(ln, ins.in[1]);
-    const float* in2 = wire(ln, ins.in[2]);
-    const float* in3 = wire(ln, ins.in[3]);
+    const float* in0 = p_in[0].at(ln);
+    const float* in1 = p_in[1].at(ln);
+    const float* in2 = p_in[2].at(ln);
+    const float* in3 = p_in[3].at(ln);
     for_groups(kk, [&](auto u, int k0) {
       constexpr int U = decltype(u)::value;
       float o[U];  // output.fill(0.0) then `*dst += src * gain` per connected input, in order
@@ -614,17 +735,19 @@ __device__ __forceinline__ float math_op(float a, float b) {
 
 struct MathOp {
   float constant;
+  Port p_a, p_b, p_out;
   __device__ __forceinline__ void load(const Instr& ins, const Lane& ln) {
     constant = __uint_as_float(ln.pr[ins.param * L]);
+    p_a = port(ln, ins.in[0]); p_b = port(ln, ins.in[1]); p_out = port(ln, ins.out[0]);
   }
   __device__ __forceinline__ void store() {}
 
   template <int WHICH>
   __device__ __forceinline__ void run_t(const Instr& ins, const Lane& ln, int kk) {
-    float* out = wire(ln, ins.out[0]);
+    float* out = p_out.at(ln);
     if (!out) return;
-    const float* i1 = wire(ln, ins.in[0]);
-    const float* i2 = wire(ln, ins.in[1]);
+    const float* i1 = p_a.at(ln);
+    const float* i2 = p_b.at(ln);
     for_groups(kk, [&](auto u, int k0) {
       constexpr int U = decltype(u)::value;
       float a[U], b[U];

@@ -85,53 +85,75 @@ __device__ __forceinline__ void run_ring_store(const Instr& ins, const dsp::Lane
   }
 }
 
-// OP_OUTPUT: OutputModule::calc, src/synth/output.rs:46-60 (stems), + this group's share of the mix.
+// OP_OUTPUT: OutputModule::calc, src/synth/output.rs:46-60 -- bufs[c] = input c or zeros, for
+// up to 4 channels; `bufs` here is the stems array [C][N][V] in HBM (one 128-byte line per
+// warp, sample and channel; streaming stores).  Channels fed by the same wire load it once.
 __device__ __forceinline__ void run_output(const Instr& ins, const dsp::Lane& ln, const GroupCtx& g, uint32_t n0, int kk) {
   const RenderArgs& a = g.a;
+  if (!a.stems || !g.active) return;
+  const float* src[kOutputChannelsPerInstr];
+  float* dst[kOutputChannelsPerInstr];
+#pragma unroll
+  for (int j = 0; j < kOutputChannelsPerInstr; ++j) {
+    src[j] = j < ins.n_ch ? dsp::wire(ln, ins.in[j]) : nullptr;
+    dst[j] = a.stems + ((size_t)(ins.aux + j) * a.n_samples + n0) * a.V + g.v;
+  }
+  const uint32_t V = a.V;  // offsets inside one chunk fit 32 bits: K * V <= 32 * 2^32 / 2^5
+  dsp::for_groups(kk, [&](auto u, int k0) {
+    constexpr int U = decltype(u)::value;
+    float x[U];
+#pragma unroll
+    for (int j = 0; j < kOutputChannelsPerInstr; ++j) {
+      if (j >= ins.n_ch) break;
+      if (j == 0 || ins.in[j] != ins.in[j - 1]) {
+#pragma unroll
+        for (int q = 0; q < U; ++q) x[q] = src[j] ? src[j][(k0 + q) * 32] : 0.0f;
+      }
+#pragma unroll
+      for (int q = 0; q < U; ++q) __stcs(dst[j] + (uint32_t)(k0 + q) * V, x[q]);
+    }
+  });
+}
+
+// OP_MIX: this group's share of the mixdown, partial[group][c][n] = sum over the group's voices.
+// Transposed read of the [K][32] tile: lane (k, seg) adds K columns of sample row k (rotated
+// start => 32 lanes on 32 banks), then a butterfly over seg.  Fixed order => reproducible bits.
+__device__ __forceinline__ void run_mix(const Instr& ins, const dsp::Lane& ln, const GroupCtx& g, uint32_t n0, int kk) {
+  const RenderArgs& a = g.a;
+  if (!a.partial) return;
   const uint32_t K = a.K;
   const int lane = g.lane;
   if (g.solo) __syncwarp();  // the tile was written by this warp a moment ago
+  const uint32_t k = lane & (K - 1), seg = lane >> a.log2K;
   float sum = 0.0f;
   for (int j = 0; j < ins.n_ch; ++j) {
-    const uint32_t c = ins.aux + j;
     const float* src = dsp::wire(ln, ins.in[j]);
-    if (a.stems && g.active) {
-      float* dst = a.stems + ((size_t)c * a.n_samples + n0) * a.V + g.v;
-      if (src) {
-        dsp::for_groups(kk, [&](auto u, int k0) {
-          constexpr int U = decltype(u)::value;
-          float x[U];
-#pragma unroll
-          for (int q = 0; q < U; ++q) x[q] = src[(k0 + q) * 32];
-#pragma unroll
-          for (int q = 0; q < U; ++q) __stcs(dst + (size_t)(k0 + q) * a.V, x[q]);
-        });
+    if (!src) {
+      sum = 0.0f;
+    } else if (j == 0 || ins.in[j] != ins.in[j - 1]) {
+      const float* row = src - lane + k * 32 + seg * K;  // K columns [seg*K, seg*K + K) of sample row k
+      float acc = 0.0f;
+      if (g.n_active == 32) {
+        uint32_t col = k;
+#pragma unroll 8
+        for (uint32_t q = 0; q < K; ++q) {
+          acc = dsp::fadd(acc, row[col]);
+          col = (col + 1) & (K - 1);
+        }
       } else {
-        for (int k = 0; k < kk; ++k) __stcs(dst + (size_t)k * a.V, 0.0f);
-      }
-    }
-    if (a.partial) {
-      if (!src) {
-        sum = 0.0f;
-      } else if (j == 0 || ins.in[j] != ins.in[j - 1]) {
-        // Transposed read of the [K][32] tile: lane (k, seg) adds K columns of sample row k
-        // (rotated start => 32 lanes on 32 banks), then a butterfly over seg.
-        const uint32_t k = lane & (K - 1), seg = lane >> a.log2K;
-        const float* row = src - lane + k * 32 + seg * K;
         const uint32_t col0 = seg * K;
-        float acc = 0.0f;
-#pragma unroll 4
         for (uint32_t q = 0; q < K; ++q) {
           const uint32_t col = (q + k) & (K - 1);
           const float x = row[col];
           acc = dsp::fadd(acc, col0 + col < g.n_active ? x : 0.0f);
         }
-        for (uint32_t off = K; off < 32; off <<= 1) acc = dsp::fadd(acc, __shfl_xor_sync(0xFFFFFFFFu, acc, off));
-        sum = acc;
-      }  // else: same wire as the previous channel, same sums
-      if (lane < kk) a.partial[((size_t)blockIdx.x * a.C + c) * a.n_samples + n0 + lane] = sum;
-    }
+      }
+      for (uint32_t off = K; off < 32; off <<= 1) acc = dsp::fadd(acc, __shfl_xor_sync(0xFFFFFFFFu, acc, off));
+      sum = acc;
+    }  // else: same wire as the previous channel, same sums
+    if (lane < kk) a.partial[((size_t)blockIdx.x * a.C + ins.aux + j) * a.n_samples + n0 + lane] = sum;
   }
+  if (g.solo) __syncwarp();
 }
 
 // A warp that owns ONE instruction keeps the module's state in registers for the whole
@@ -219,6 +241,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) render_voices_kernel(const Ren
           case OP_RING_LOAD: run_ring_load(ins, ln, g, n0, kk); break;
           case OP_RING_STORE: run_ring_store(ins, ln, g, n0, kk); break;
           case OP_OUTPUT: run_output(ins, ln, g, n0, kk); break;
+          case OP_MIX: run_mix(ins, ln, g, n0, kk); break;
           default: break;
         }
       }

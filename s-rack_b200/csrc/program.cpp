@@ -36,7 +36,8 @@ int op_cost(const Pending& p) {
                         (p.in_vw[0] >= 0 ? 90 : 0);
     case OP_ADSR: return 40;
     case OP_NOISE: return 25;
-    case OP_OUTPUT: return 12;
+    case OP_OUTPUT: return 10;
+    case OP_MIX: return 8;
     case OP_MIXER: return 10;
     case OP_MATH: return p.ins.flags == F_MATH_NONLIN ? 150 : 4;
     default: return 4;
@@ -191,6 +192,8 @@ int compile_program(const srk_patch& patch, int max_warps, Program& prog, std::s
           q.ins.aux = (uint16_t)c0;
           q.ins.n_ch = (uint8_t)std::min<size_t>(kOutputChannelsPerInstr, mod->inputs.size() - c0);
           for (int j = 0; j < q.ins.n_ch; ++j) q.in_vw[j] = in_wire[m][c0 + j];
+          code.push_back(q);
+          q.ins.op = OP_MIX;  // same wires, summed over the group's voices
           code.push_back(q);
         }
         continue;

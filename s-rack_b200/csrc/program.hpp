@@ -28,7 +28,8 @@ enum Op : uint8_t {
   OP_VCA,
   OP_MIXER,
   OP_MATH,
-  OP_OUTPUT,      // channels aux .. aux+3 <- in[0..3]; stems + per-group mix partial
+  OP_OUTPUT,      // channels aux .. aux+3 <- in[0..3]: per-voice stems
+  OP_MIX,         // channels aux .. aux+3: this voice group's share of the mixdown
 };
 
 // Instr::flags
@@ -52,7 +53,7 @@ struct alignas(16) Instr {
   uint8_t warp;     // warp of the group that executes this instruction
   uint8_t stage;    // pipeline delay in chunks
   float imm;        // oscillator / ADSR sample rate
-  uint8_t n_ch;     // OUTPUT: channels covered by this instruction (1..4)
+  uint8_t n_ch;     // OUTPUT / MIX: channels covered by this instruction (1..4)
   uint8_t pad[3];
 };
 static_assert(sizeof(Instr) == 32, "Instr must stay 32 bytes (staged to shared memory as uint4 pairs)");

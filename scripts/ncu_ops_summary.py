@@ -11,7 +11,7 @@ dsp = sys.argv[2] if len(sys.argv) > 2 else os.path.join(os.path.dirname(__file_
 # function ranges in dsp.cuh: "__device__ ... name(" starts a range
 starts = []
 for i, line in enumerate(open(dsp), 1):
-    m = re.search(r"__device__ __forceinline__ \S+ (\w+)\(", line)
+    m = re.match(r"struct (\w+Op) \{", line) or re.match(r"__device__ \S+ \S+ (\w+)\(", line)
     if m:
         starts.append((i, m.group(1)))
 def fn_of(line_no):
@@ -45,8 +45,8 @@ for r in rows:
     except ValueError:
         pass
 insts.sort()
-LEAF = {"fadd", "fsub", "fmul", "dadd", "dsub", "dmul", "fmod1", "transition", "poly_blep", "philox4x32_10", "wire",
-        "for_groups", "clamp1", "moog_coef", "math_op", "?"}
+LEAF = {"fadd", "fsub", "fmul", "dadd", "dsub", "dmul", "fmod1_exact", "wrap01", "blep_eval", "philox4x32_10", "wire",
+        "for_groups", "clamp1", "moog_coef", "math_op", "nonlinear", "?"}
 agg = collections.OrderedDict()
 region = "prologue"
 for addr, f, line, sass, samp, bar, ex in insts:
