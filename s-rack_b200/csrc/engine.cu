@@ -63,7 +63,8 @@ struct GroupCtx {
 };
 
 // OP_RING_LOAD / OP_RING_STORE: the delayed (feedback) wires, rings f32 [R][B][V] in HBM.
-__device__ __forceinline__ void run_ring_load(const Instr& ins, const dsp::Lane& ln, const GroupCtx& g, uint32_t n0, int kk) {
+__device__ __forceinline__ void run_ring_load(const Instr& ins, const dsp::Lane& ln, const GroupCtx& g, int kk) {
+  const uint32_t n0 = ln.chunk * g.a.K;
   const RenderArgs& a = g.a;
   const float* ring = a.rings + (size_t)ins.aux * a.B * a.V + g.v;
   float* out = dsp::wire(ln, ins.out[0]);
@@ -74,7 +75,8 @@ __device__ __forceinline__ void run_ring_load(const Instr& ins, const dsp::Lane&
   }
 }
 
-__device__ __forceinline__ void run_ring_store(const Instr& ins, const dsp::Lane& ln, const GroupCtx& g, uint32_t n0, int kk) {
+__device__ __forceinline__ void run_ring_store(const Instr& ins, const dsp::Lane& ln, const GroupCtx& g, int kk) {
+  const uint32_t n0 = ln.chunk * g.a.K;
   const RenderArgs& a = g.a;
   float* ring = a.rings + (size_t)ins.aux * a.B * a.V + g.v;
   const float* in = dsp::wire(ln, ins.in[0]);
@@ -88,8 +90,9 @@ __device__ __forceinline__ void run_ring_store(const Instr& ins, const dsp::Lane
 // OP_OUTPUT: OutputModule::calc, src/synth/output.rs:46-60 -- bufs[c] = input c or zeros, for
 // up to 4 channels; `bufs` here is the stems array [C][N][V] in HBM (one 128-byte line per
 // warp, sample and channel; streaming stores).  Channels fed by the same wire load it once.
-__device__ __forceinline__ void run_output(const Instr& ins, const dsp::Lane& ln, const GroupCtx& g, uint32_t n0, int kk) {
+__device__ __forceinline__ void run_output(const Instr& ins, const dsp::Lane& ln, const GroupCtx& g, int kk) {
   const RenderArgs& a = g.a;
+  const uint32_t n0 = ln.chunk * a.K;
   if (!a.stems || !g.active) return;
   const float* src[kOutputChannelsPerInstr];
   float* dst[kOutputChannelsPerInstr];
@@ -118,8 +121,9 @@ __device__ __forceinline__ void run_output(const Instr& ins, const dsp::Lane& ln
 // OP_MIX: this group's share of the mixdown, partial[group][c][n] = sum over the group's voices.
 // Transposed read of the [K][32] tile: lane (k, seg) adds K columns of sample row k (rotated
 // start => 32 lanes on 32 banks), then a butterfly over seg.  Fixed order => reproducible bits.
-__device__ __forceinline__ void run_mix(const Instr& ins, const dsp::Lane& ln, const GroupCtx& g, uint32_t n0, int kk) {
+__device__ __forceinline__ void run_mix(const Instr& ins, const dsp::Lane& ln, const GroupCtx& g, int kk) {
   const RenderArgs& a = g.a;
+  const uint32_t n0 = ln.chunk * a.K;
   if (!a.partial) return;
   const uint32_t K = a.K;
   const int lane = g.lane;
@@ -156,21 +160,30 @@ __device__ __forceinline__ void run_mix(const Instr& ins, const dsp::Lane& ln, c
   if (g.solo) __syncwarp();
 }
 
-// A warp that owns ONE instruction keeps the module's state in registers for the whole
-// render: load once, one run() + one block barrier per iteration, store once.
+// A warp that owns ONE instruction never goes back to the interpreter: it loads the module's
+// state into registers once, then loops run() + one block barrier per iteration, and stores
+// the state at the end.  (Besides keeping state in registers this keeps each warp inside one
+// contiguous piece of code: the interpreter's dispatch hops across all inlined op bodies and
+// measured ~100 cycles of instruction fetch per hop, profiles/r01g_k8.)
+template <class Body>
+__device__ __forceinline__ void resident_loop(const Instr& ins, dsp::Lane& ln, const RenderArgs& a, uint32_t n_chunks,
+                                              uint32_t n_iter, Body&& body) {
+  for (uint32_t it = 0; it < n_iter; ++it) {
+    const uint32_t chunk = it - ins.stage;
+    if (chunk < n_chunks) {  // also false while it < stage (wraps)
+      ln.chunk = chunk;
+      body((int)min(a.K, a.n_samples - chunk * a.K));
+    }
+    __syncthreads();
+  }
+}
+
 template <class Op>
 __device__ __forceinline__ void run_resident(const Instr& ins, dsp::Lane& ln, const RenderArgs& a, uint32_t n_chunks,
                                              uint32_t n_iter) {
   Op op;
   op.load(ins, ln);
-  for (uint32_t it = 0; it < n_iter; ++it) {
-    const uint32_t chunk = it - ins.stage;
-    if (chunk < n_chunks) {  // also false while it < stage (wraps)
-      ln.chunk = chunk;
-      op.run(ins, ln, (int)min(a.K, a.n_samples - chunk * a.K));
-    }
-    __syncthreads();
-  }
+  resident_loop(ins, ln, a, n_chunks, n_iter, [&](int kk) { op.run(ins, ln, kk); });
   op.store();
 }
 
@@ -209,26 +222,29 @@ __global__ void __launch_bounds__(kMaxThreads, 1) render_voices_kernel(const Ren
   const uint32_t n_iter = n_chunks + a.n_stages - 1;
   const GroupCtx g{a, v, n_active, active, lane, a.n_warps == 1};
 
-  bool resident = false;
   if (!g.solo && pc1 == pc0 + 1) {
     const Instr ins = prog[pc0];
-    resident = true;
     switch (ins.op) {
       case OP_OSC: run_resident<dsp::OscOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_MOOG: run_resident<dsp::MoogOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_ADSR: run_resident<dsp::AdsrOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_NOISE: run_resident<dsp::NoiseOp>(ins, ln, a, n_chunks, n_iter); break;
-      default: resident = false; break;  // stateless ops: nothing to keep
+      case OP_VCA: run_resident<dsp::VcaOp>(ins, ln, a, n_chunks, n_iter); break;
+      case OP_MIXER: run_resident<dsp::MixerOp>(ins, ln, a, n_chunks, n_iter); break;
+      case OP_MATH: run_resident<dsp::MathOp>(ins, ln, a, n_chunks, n_iter); break;
+      case OP_OUTPUT: resident_loop(ins, ln, a, n_chunks, n_iter, [&](int kk) { run_output(ins, ln, g, kk); }); break;
+      case OP_MIX: resident_loop(ins, ln, a, n_chunks, n_iter, [&](int kk) { run_mix(ins, ln, g, kk); }); break;
+      case OP_RING_LOAD: resident_loop(ins, ln, a, n_chunks, n_iter, [&](int kk) { run_ring_load(ins, ln, g, kk); }); break;
+      case OP_RING_STORE: resident_loop(ins, ln, a, n_chunks, n_iter, [&](int kk) { run_ring_store(ins, ln, g, kk); }); break;
+      default: resident_loop(ins, ln, a, n_chunks, n_iter, [](int) {}); break;
     }
-  }
-  if (!resident) {
+  } else {
     for (uint32_t it = 0; it < n_iter; ++it) {
       for (uint32_t pc = pc0; pc < pc1; ++pc) {
         const Instr ins = prog[pc];
         const uint32_t chunk = it - ins.stage;
         if (chunk >= n_chunks) continue;  // also catches it < stage (wraps)
-        const uint32_t n0 = chunk * K;
-        const int kk = (int)min(K, a.n_samples - n0);
+        const int kk = (int)min(K, a.n_samples - chunk * K);
         ln.chunk = chunk;
         switch (ins.op) {
           case OP_OSC: run_once<dsp::OscOp>(ins, ln, kk); break;
@@ -238,10 +254,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) render_voices_kernel(const Ren
           case OP_VCA: run_once<dsp::VcaOp>(ins, ln, kk); break;
           case OP_MIXER: run_once<dsp::MixerOp>(ins, ln, kk); break;
           case OP_MATH: run_once<dsp::MathOp>(ins, ln, kk); break;
-          case OP_RING_LOAD: run_ring_load(ins, ln, g, n0, kk); break;
-          case OP_RING_STORE: run_ring_store(ins, ln, g, n0, kk); break;
-          case OP_OUTPUT: run_output(ins, ln, g, n0, kk); break;
-          case OP_MIX: run_mix(ins, ln, g, n0, kk); break;
+          case OP_RING_LOAD: run_ring_load(ins, ln, g, kk); break;
+          case OP_RING_STORE: run_ring_store(ins, ln, g, kk); break;
+          case OP_OUTPUT: run_output(ins, ln, g, kk); break;
+          case OP_MIX: run_mix(ins, ln, g, kk); break;
           default: break;
         }
       }
