@@ -126,14 +126,17 @@ using UC = std::integral_constant<int, U>;
 
 constexpr int kGroup = 4;
 
-// Runs body(UC<kGroup>, k0) over full groups of samples, body(UC<1>, k) over the tail.
+// Runs body(UC<kGroup>, k) over full groups of samples in [k0, k1), body(UC<1>, k) over the tail.
+template <class Body>
+__device__ __forceinline__ void for_groups(int k0, int k1, Body&& body) {
+#pragma unroll 1
+  for (; k0 + kGroup <= k1; k0 += kGroup) body(UC<kGroup>(), k0);
+#pragma unroll 1
+  for (; k0 < k1; ++k0) body(UC<1>(), k0);
+}
 template <class Body>
 __device__ __forceinline__ void for_groups(int kk, Body&& body) {
-  int k0 = 0;
-#pragma unroll 1
-  for (; k0 + kGroup <= kk; k0 += kGroup) body(UC<kGroup>(), k0);
-#pragma unroll 1
-  for (; k0 < kk; ++k0) body(UC<1>(), k0);
+  for_groups(0, kk, body);
 }
 
 // ---- OscillatorModule::calc, src/synth/oscillator.rs:108-158 ----------------
@@ -164,7 +167,7 @@ struct OscOp {
   // OUTS: bit 0 sine, bit 1 square, bit 2 saw are read by somebody.  Compile-time, because a
   // per-group `if (port connected)` costs more than the arithmetic it guards (see header).
   template <bool HAS_CV, int OUTS>
-  __device__ __forceinline__ void run_t(const Lane& ln, int kk) {
+  __device__ __forceinline__ void run_t(const Lane& ln, int kb, int ke) {
     constexpr bool SINE = OUTS & 1, SQUARE = OUTS & 2, SAW = OUTS & 4;
     const float* cv = p_cv.at(ln);
     const float* sync = p_sync.at(ln);
@@ -172,7 +175,7 @@ struct OscOp {
     float* sine = p_sine.at(ln);
     float* square = p_square.at(ln);
     float* saw = p_saw.at(ln);
-    for_groups(kk, [&](auto u, int k0) {
+    for_groups(kb, ke, [&](auto u, int k0) {
       constexpr int U = decltype(u)::value;
       float cvv[U];
       bool edge[U];  // sync transition on this sample (:125-131)
@@ -266,28 +269,41 @@ struct OscOp {
       }
     });
     // with no sync input the detector sees 0.0 every sample: `last` just goes false
-    if (!has_sync && kk > 0) last = false;
+    if (!has_sync && ke > kb) last = false;
   }
 
   template <bool HAS_CV>
-  __device__ __forceinline__ void run_outs(const Lane& ln, int kk) {
+  __device__ __forceinline__ void run_outs(const Lane& ln, int kb, int ke) {
     const int outs = (p_sine.base ? 1 : 0) | (p_square.base ? 2 : 0) | (p_saw.base ? 4 : 0);
     switch (outs) {
-      case 0: run_t<HAS_CV, 0>(ln, kk); break;
-      case 1: run_t<HAS_CV, 1>(ln, kk); break;
-      case 2: run_t<HAS_CV, 2>(ln, kk); break;
-      case 3: run_t<HAS_CV, 3>(ln, kk); break;
-      case 4: run_t<HAS_CV, 4>(ln, kk); break;
-      case 5: run_t<HAS_CV, 5>(ln, kk); break;
-      case 6: run_t<HAS_CV, 6>(ln, kk); break;
-      default: run_t<HAS_CV, 7>(ln, kk); break;
+      case 0: run_t<HAS_CV, 0>(ln, kb, ke); break;
+      case 1: run_t<HAS_CV, 1>(ln, kb, ke); break;
+      case 2: run_t<HAS_CV, 2>(ln, kb, ke); break;
+      case 3: run_t<HAS_CV, 3>(ln, kb, ke); break;
+      case 4: run_t<HAS_CV, 4>(ln, kb, ke); break;
+      case 5: run_t<HAS_CV, 5>(ln, kb, ke); break;
+      case 6: run_t<HAS_CV, 6>(ln, kb, ke); break;
+      default: run_t<HAS_CV, 7>(ln, kb, ke); break;
     }
   }
 
-  __device__ __forceinline__ void run(const Instr&, const Lane& ln, int kk) {
-    if (p_cv.base) run_outs<true>(ln, kk);
-    else run_outs<false>(ln, kk);
+  // flags = (n << 4) | i for a time-split copy (program.cpp): every copy advances the phase
+  // through the whole chunk, copy i shapes the outputs of the i-th n-th of every chunk (so
+  // within one barrier interval each copy does phase(K) + shape(K / n)).
+  __device__ __forceinline__ void run(const Instr& ins, const Lane& ln, int kk) {
+    const uint32_t n = ins.flags >> 4;
+    if (n > 1) {  // only CV-less oscillators are split
+      const int span = (int)(ln.tile_elems / L / n);
+      const int lo = min(kk, (int)(ins.flags & 15u) * span), hi = min(kk, lo + span);
+      run_t<false, 0>(ln, 0, lo);
+      run_outs<false>(ln, lo, hi);
+      run_t<false, 0>(ln, hi, kk);
+      return;
+    }
+    if (p_cv.base) run_outs<true>(ln, 0, kk);
+    else run_outs<false>(ln, 0, kk);
   }
+  __device__ __forceinline__ bool owns_state(const Instr& ins) const { return (ins.flags & 15u) == 0; }
 };
 
 // ---- NoiseModule::calc, src/synth/oscillator.rs:381-388 (seeded generator) ----

@@ -44,7 +44,7 @@ struct RenderArgs {
   uint32_t voice_offset;  // global index of voice 0 (noise key)
   uint32_t n_samples;
   uint32_t S, P, C, B;
-  uint32_t K;             // samples per chunk: power of two <= 32
+  uint32_t K;             // samples per chunk: power of two <= 128
   uint32_t log2K;
   uint32_t ring_phase;    // absolute sample index of sample 0, mod B
   uint32_t seed_lo, seed_hi;
@@ -101,7 +101,7 @@ __device__ __forceinline__ void run_output(const Instr& ins, const dsp::Lane& ln
     src[j] = j < ins.n_ch ? dsp::wire(ln, ins.in[j]) : nullptr;
     dst[j] = a.stems + ((size_t)(ins.aux + j) * a.n_samples + n0) * a.V + g.v;
   }
-  const uint32_t V = a.V;  // offsets inside one chunk fit 32 bits: K * V <= 32 * 2^32 / 2^5
+  const uint32_t V = a.V;  // offsets inside one chunk fit 32 bits as long as K * V < 2^32 (checked at launch)
   dsp::for_groups(kk, [&](auto u, int k0) {
     constexpr int U = decltype(u)::value;
     float x[U];
@@ -119,43 +119,46 @@ __device__ __forceinline__ void run_output(const Instr& ins, const dsp::Lane& ln
 }
 
 // OP_MIX: this group's share of the mixdown, partial[group][c][n] = sum over the group's voices.
-// Transposed read of the [K][32] tile: lane (k, seg) adds K columns of sample row k (rotated
-// start => 32 lanes on 32 banks), then a butterfly over seg.  Fixed order => reproducible bits.
+// Transposed read of the [K][32] tile, R = min(K, 32) sample rows at a time: lane (k, seg) adds
+// R columns of sample row k (rotated start => 32 lanes on 32 banks), then a butterfly over seg.
+// Fixed order => reproducible bits.
 __device__ __forceinline__ void run_mix(const Instr& ins, const dsp::Lane& ln, const GroupCtx& g, int kk) {
   const RenderArgs& a = g.a;
   const uint32_t n0 = ln.chunk * a.K;
   if (!a.partial) return;
-  const uint32_t K = a.K;
+  const uint32_t R = min(a.K, 32u), log2R = min(a.log2K, 5u);
   const int lane = g.lane;
   if (g.solo) __syncwarp();  // the tile was written by this warp a moment ago
-  const uint32_t k = lane & (K - 1), seg = lane >> a.log2K;
-  float sum = 0.0f;
-  for (int j = 0; j < ins.n_ch; ++j) {
-    const float* src = dsp::wire(ln, ins.in[j]);
-    if (!src) {
-      sum = 0.0f;
-    } else if (j == 0 || ins.in[j] != ins.in[j - 1]) {
-      const float* row = src - lane + k * 32 + seg * K;  // K columns [seg*K, seg*K + K) of sample row k
-      float acc = 0.0f;
-      if (g.n_active == 32) {
-        uint32_t col = k;
+  const uint32_t k = lane & (R - 1), seg = lane >> log2R;
+  for (int kb = 0; kb < kk; kb += 32) {
+    float sum = 0.0f;
+    for (int j = 0; j < ins.n_ch; ++j) {
+      const float* src = dsp::wire(ln, ins.in[j]);
+      if (!src) {
+        sum = 0.0f;
+      } else if (j == 0 || ins.in[j] != ins.in[j - 1]) {
+        const float* row = src - lane + (kb + k) * 32 + seg * R;  // R columns [seg*R, seg*R + R) of row kb + k
+        float acc = 0.0f;
+        if (g.n_active == 32) {
+          uint32_t col = k;
 #pragma unroll 8
-        for (uint32_t q = 0; q < K; ++q) {
-          acc = dsp::fadd(acc, row[col]);
-          col = (col + 1) & (K - 1);
+          for (uint32_t q = 0; q < R; ++q) {
+            acc = dsp::fadd(acc, row[col]);
+            col = (col + 1) & (R - 1);
+          }
+        } else {
+          const uint32_t col0 = seg * R;
+          for (uint32_t q = 0; q < R; ++q) {
+            const uint32_t col = (q + k) & (R - 1);
+            const float x = row[col];
+            acc = dsp::fadd(acc, col0 + col < g.n_active ? x : 0.0f);
+          }
         }
-      } else {
-        const uint32_t col0 = seg * K;
-        for (uint32_t q = 0; q < K; ++q) {
-          const uint32_t col = (q + k) & (K - 1);
-          const float x = row[col];
-          acc = dsp::fadd(acc, col0 + col < g.n_active ? x : 0.0f);
-        }
-      }
-      for (uint32_t off = K; off < 32; off <<= 1) acc = dsp::fadd(acc, __shfl_xor_sync(0xFFFFFFFFu, acc, off));
-      sum = acc;
-    }  // else: same wire as the previous channel, same sums
-    if (lane < kk) a.partial[((size_t)blockIdx.x * a.C + ins.aux + j) * a.n_samples + n0 + lane] = sum;
+        for (uint32_t off = R; off < 32; off <<= 1) acc = dsp::fadd(acc, __shfl_xor_sync(0xFFFFFFFFu, acc, off));
+        sum = acc;
+      }  // else: same wire as the previous channel, same sums
+      if (kb + lane < kk) a.partial[((size_t)blockIdx.x * a.C + ins.aux + j) * a.n_samples + n0 + kb + lane] = sum;
+    }
   }
   if (g.solo) __syncwarp();
 }
@@ -225,7 +228,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) render_voices_kernel(const Ren
   if (!g.solo && pc1 == pc0 + 1) {
     const Instr ins = prog[pc0];
     switch (ins.op) {
-      case OP_OSC: run_resident<dsp::OscOp>(ins, ln, a, n_chunks, n_iter); break;
+      case OP_OSC: {
+        dsp::OscOp op;
+        op.load(ins, ln);
+        resident_loop(ins, ln, a, n_chunks, n_iter, [&](int kk) { op.run(ins, ln, kk); });
+        if (op.owns_state(ins)) op.store();
+        break;
+      }
       case OP_MOOG: run_resident<dsp::MoogOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_ADSR: run_resident<dsp::AdsrOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_NOISE: run_resident<dsp::NoiseOp>(ins, ln, a, n_chunks, n_iter); break;
@@ -335,7 +344,7 @@ struct Engine {
   uint32_t* h_params = nullptr;  // pinned staging
   size_t h_params_bytes = 0;
   uint64_t launches = 0;
-  int smem_optin = 0, n_sm = 0;
+  int smem_optin = 0, smem_sm = 0, n_sm = 0;
   // geometry of the last launch
   int block_threads = 0, step = 0, n_warps = 0, n_stages = 0;
   size_t smem_bytes = 0;
@@ -381,6 +390,7 @@ static int engine_open(srk_patch* patch) {
   for (auto& ev : eng->ev) SRK_CUDA(cudaEventCreate(&ev));
   SRK_CUDA(cudaDeviceGetAttribute(&eng->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   SRK_CUDA(cudaDeviceGetAttribute(&eng->n_sm, cudaDevAttrMultiProcessorCount, dev));
+  SRK_CUDA(cudaDeviceGetAttribute(&eng->smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
   patch->engine = std::move(eng);
   return SRK_OK;
 }
@@ -407,10 +417,9 @@ static int choose_max_warps(const Engine& e, size_t V) {
   if (forced > 0) return std::min(forced, (int)kMaxWarps);
   const size_t groups = (V + kVoicesPerGroup - 1) / kVoicesPerGroup;
   const size_t per_sm = (groups + std::max(e.n_sm, 1) - 1) / std::max(e.n_sm, 1);
-  if (per_sm <= 2) return kMaxWarps;
-  if (per_sm <= 4) return 8;
-  if (per_sm <= 8) return 4;
-  return 1;
+  // measured on B200 (profiles/r01j sweep): with 3+ groups per SM the one-warp schedule wins
+  // (cfg2 at 14 groups/SM: 42 ms vs 54 ms pipelined; cfg4 at 7 groups/SM: 78 ms vs 100 ms)
+  return per_sm <= 2 ? kMaxWarps : 1;
 }
 
 static size_t smem_bytes_for(const Program& prog, size_t blob_vec, int K) {
@@ -418,24 +427,36 @@ static size_t smem_bytes_for(const Program& prog, size_t blob_vec, int K) {
                              kVoicesPerGroup * sizeof(uint32_t);
 }
 
-// Samples per chunk (a power of two <= 32) for this program; 0 when it cannot fit.
-static int choose_chunk(const Engine& e, const Program& prog, size_t blob_vec) {
-  int K = env_int("SRK_STEP", prog.n_warps > 1 ? 32 : 8);
+// Samples per chunk (a power of two) for this program and render length; 0 when it cannot fit.
+// Pipelined groups want long chunks: every iteration costs a block barrier plus ~1.5k cycles of
+// instruction-cache refill for the code outside the sample loops (profiles/r01i_k8), and only
+// pays (stages - 1) chunks of fill/drain per render.
+constexpr int kMaxChunk = 128;
+static int choose_chunk(const Engine& e, const Program& prog, size_t blob_vec, size_t n_samples, size_t V) {
+  const bool pipelined = prog.n_warps > 1;
+  // shared memory one block may take so that every group of this launch is resident at once
+  const size_t groups = (V + kVoicesPerGroup - 1) / kVoicesPerGroup;
+  const size_t per_sm = std::max<size_t>((groups + std::max(e.n_sm, 1) - 1) / std::max(e.n_sm, 1), 1);
+  const size_t smem_cap = pipelined && per_sm <= 4 ? std::min<size_t>(e.smem_optin, (size_t)(e.smem_sm / per_sm) - 1024)
+                                                   : (size_t)e.smem_optin;
+  int K = env_int("SRK_STEP", pipelined ? kMaxChunk : 16);
   if (K < 1) K = 1;
-  if (K > 32) K = 32;
+  if (K > kMaxChunk) K = kMaxChunk;
   while (K & (K - 1)) K &= K - 1;  // power of two
+  if (pipelined)  // keep fill/drain under ~1/8 of the render
+    while (K > 8 && (size_t)K * (prog.n_stages - 1) * 8 > std::max<size_t>(n_samples, 1)) K /= 2;
   if (prog.n_rings) {
     // a delayed wire's sample n - B must have been stored in an EARLIER iteration than the one
     // that loads sample n: K <= B when one warp runs everything in order, K * (stage + 2) <= B
     // when the store runs `stage` iterations behind the load.
     const size_t B = std::max<uint32_t>(prog.ring_len, 1);
-    const size_t lim = prog.n_warps > 1 ? B / (prog.max_ring_store_stage + 2) : B;
+    const size_t lim = pipelined ? B / (prog.max_ring_store_stage + 2) : B;
     while (K > 1 && (size_t)K > lim) K /= 2;
     if ((size_t)K > lim) return 0;
   }
-  while (K > 1 && smem_bytes_for(prog, blob_vec, K) > (size_t)e.smem_optin) K /= 2;
-  if (smem_bytes_for(prog, blob_vec, K) > (size_t)e.smem_optin) return 0;
-  if (prog.n_warps > 1 && K < 8) return 0;  // a barrier every few samples: not worth pipelining
+  while (K > 1 && smem_bytes_for(prog, blob_vec, K) > smem_cap) K /= 2;
+  if (smem_bytes_for(prog, blob_vec, K) > smem_cap) return 0;
+  if (pipelined && K < 8) return 0;  // a barrier every few samples: not worth pipelining
   return K;
 }
 
@@ -518,12 +539,12 @@ static int engine_prepare(srk_patch* patch, size_t n_voices, size_t voice_offset
     int rc = compile_program(*patch, want_warps, e.prog, err);
     if (rc != SRK_OK) { patch->last_error = err; return rc; }
     build_blob(e.prog, e.blob);
-    e.chunk = choose_chunk(e, e.prog, e.blob.size());
+    e.chunk = choose_chunk(e, e.prog, e.blob.size(), 1u << 30, n_voices);
     if (e.chunk == 0 && e.prog.n_warps > 1) {  // does not fit as a pipeline: one warp, plan order
       rc = compile_program(*patch, 1, e.prog, err);
       if (rc != SRK_OK) { patch->last_error = err; return rc; }
       build_blob(e.prog, e.blob);
-      e.chunk = choose_chunk(e, e.prog, e.blob.size());
+      e.chunk = choose_chunk(e, e.prog, e.blob.size(), 1u << 30, n_voices);
     }
     if (e.chunk == 0) { patch->last_error = "patch needs more shared memory than one block can have"; return SRK_ERR_LIMIT; }
     SRK_CUDA(e.d_prog.ensure(e.blob.size() * sizeof(uint4)));
@@ -559,7 +580,7 @@ static int engine_prepare(srk_patch* patch, size_t n_voices, size_t voice_offset
 int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t n_samples, unsigned flags,
                   float* stems, float* mix, void* user_stream, bool use_user_stream) {
   if (!patch->planned) { patch->last_error = "srk_plan() has not been called since the last wiring change"; return SRK_ERR_NOT_PLANNED; }
-  if (n_voices > 0xFFFFFFFFull || n_samples > 0xFFFFFFFFull) { patch->last_error = "n_voices / n_samples exceed 2^32-1"; return SRK_ERR_ARG; }
+  if (n_voices > (0xFFFFFFFFull / kMaxChunk) || n_samples > 0xFFFFFFFFull) { patch->last_error = "n_voices exceeds 2^25-1 or n_samples 2^32-1"; return SRK_ERR_ARG; }
   if ((flags & SRK_RENDER_ASYNC) && !(flags & SRK_RENDER_DEVICE_OUT)) { patch->last_error = "SRK_RENDER_ASYNC needs SRK_RENDER_DEVICE_OUT"; return SRK_ERR_ARG; }
   int rc = engine_open(patch);
   if (rc != SRK_OK) return rc;
@@ -580,7 +601,7 @@ int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t
 
   const Program& prog = e.prog;
   const size_t C = prog.channels;
-  const int K = e.chunk;
+  const int K = choose_chunk(e, prog, e.blob.size(), n_samples, n_voices);  // <= e.chunk, which fitted
   const int T = (int)prog.n_warps * 32;
   const size_t smem = smem_bytes_for(prog, e.blob.size(), K);
   const unsigned grid = (unsigned)((n_voices + kVoicesPerGroup - 1) / kVoicesPerGroup);
@@ -690,18 +711,19 @@ int engine_program_info(srk_patch* patch, size_t n_voices, srk_program_info* out
   Engine probe;  // geometry without a device: assume the sm_100 limits
   probe.smem_optin = patch->engine ? patch->engine->smem_optin : 227 * 1024;
   probe.n_sm = patch->engine ? patch->engine->n_sm : 148;
+  probe.smem_sm = patch->engine ? patch->engine->smem_sm : 228 * 1024;
   Program prog;
   std::string err;
   std::vector<uint4> blob;
   int rc = compile_program(*patch, choose_max_warps(probe, n_voices), prog, err);
   if (rc != SRK_OK) { patch->last_error = err; return rc; }
   build_blob(prog, blob);
-  int K = choose_chunk(probe, prog, blob.size());
+  int K = choose_chunk(probe, prog, blob.size(), 1u << 30, n_voices);
   if (K == 0 && prog.n_warps > 1) {
     rc = compile_program(*patch, 1, prog, err);
     if (rc != SRK_OK) { patch->last_error = err; return rc; }
     build_blob(prog, blob);
-    K = choose_chunk(probe, prog, blob.size());
+    K = choose_chunk(probe, prog, blob.size(), 1u << 30, n_voices);
   }
   if (K == 0) { patch->last_error = "patch needs more shared memory than one block can have"; return SRK_ERR_LIMIT; }
   out->n_instr = (uint32_t)prog.code.size();

@@ -28,13 +28,22 @@ struct Pending {
   int cost;
 };
 
-// Rough issue cost per sample, only used to balance warps over the 4 SM sub-partitions.
+// Rough cycles per sample of a warp that runs only this instruction (measured on B200,
+// profiles/r01j): used to balance warps over the 4 SM sub-partitions and to decide
+// which oscillators to time-split.
+int osc_phase_cost(const Pending& p) { return 25 + (p.in_vw[0] >= 0 ? 100 : 0); }  // recurrence (+ 2^cv / sr)
+int osc_shape_cost(const Pending& p) {
+  return (p.out_vw[0] >= 0 ? 90 : 0) + (p.out_vw[1] >= 0 ? 90 : 0) + (p.out_vw[2] >= 0 ? 100 : 0);
+}
+
 int op_cost(const Pending& p) {
   switch (p.ins.op) {
-    case OP_MOOG: return 100;
-    case OP_OSC: return 30 + (p.out_vw[0] >= 0 ? 60 : 0) + (p.out_vw[1] >= 0 ? 20 : 0) + (p.out_vw[2] >= 0 ? 10 : 0) +
-                        (p.in_vw[0] >= 0 ? 90 : 0);
-    case OP_ADSR: return 40;
+    case OP_MOOG: return 115;
+    case OP_OSC: {
+      const int n = std::max(1, p.ins.flags >> 4);  // time-split copies share the shaping work
+      return osc_phase_cost(p) + osc_shape_cost(p) / n;
+    }
+    case OP_ADSR: return 60;
     case OP_NOISE: return 25;
     case OP_OUTPUT: return 10;
     case OP_MIX: return 8;
@@ -219,21 +228,45 @@ int compile_program(const srk_patch& patch, int max_warps, Program& prog, std::s
   }
 
   // ---- liveness: drop output ports nobody reads --------------------------------
-  const int nc = (int)code.size();
-  for (int i = 0; i < nc; ++i) {
-    for (int k = 0; k < 3; ++k)
-      if (code[i].out_vw[k] >= 0) vw[code[i].out_vw[k]].def = i;
+  for (size_t i = 0; i < code.size(); ++i)
     for (int k = 0; k < 4; ++k)
-      if (code[i].in_vw[k] >= 0) vw[code[i].in_vw[k]].last_use = std::max(vw[code[i].in_vw[k]].last_use, i);
-  }
-  for (int i = 0; i < nc; ++i)
+      if (code[i].in_vw[k] >= 0) vw[code[i].in_vw[k]].last_use = std::max(vw[code[i].in_vw[k]].last_use, (int)i);
+  for (size_t i = 0; i < code.size(); ++i)
     for (int k = 0; k < 3; ++k) {
       int w = code[i].out_vw[k];
       if (w >= 0 && vw[w].last_use < 0) code[i].out_vw[k] = -1;
     }
+  const bool pipelined = max_warps > 1 && code.size() > 1;
+  if (pipelined) {
+    // Time-split heavy oscillators.  An oscillator without a CV input spends ~25 cycles per
+    // sample on its phase recurrence and 4x that on shaping the outputs (sin, polyBLEP with an
+    // f64 division); the shaping is stateless.  n copies of the instruction on n warps all run
+    // the recurrence (identical state, bit for bit) and copy i shapes only chunks with
+    // chunk % n == i, so the slowest pipeline stage shrinks from phase + shape to
+    // phase + shape / n.  Copy 0 alone stores the state back.
+    std::vector<Pending> split;
+    int spare = std::min(max_warps, kMaxWarps) - (int)code.size();
+    for (const Pending& p : code) {
+      int n = 1;
+      if (p.ins.op == OP_OSC && p.in_vw[0] < 0) {
+        const int phase = osc_phase_cost(p), shape = osc_shape_cost(p);
+        while (n < 4 && phase + shape / n > 100 && spare >= n) n *= 2;  // n -> 2n adds n warps
+        if (n > 1) spare -= n - 1;
+      }
+      for (int i = 0; i < n; ++i) {
+        Pending q = p;
+        if (n > 1) q.ins.flags = (uint8_t)((n << 4) | i);
+        split.push_back(q);
+      }
+    }
+    code.swap(split);
+  }
+  const int nc = (int)code.size();
+  for (int i = 0; i < nc; ++i)
+    for (int k = 0; k < 3; ++k)
+      if (code[i].out_vw[k] >= 0) vw[code[i].out_vw[k]].def = i;
   for (auto& p : code) p.cost = op_cost(p);
 
-  const bool pipelined = max_warps > 1 && nc > 1;
   std::vector<int> stage(nc, 0), warp(nc, 0);
   if (!pipelined) {
     // One warp, plan order, physical tiles shared by liveness (no in-place reuse inside one instr).
@@ -284,7 +317,7 @@ int compile_program(const srk_patch& patch, int max_warps, Program& prog, std::s
     for (int i = 0; i < nc; ++i)
       for (int k = 0; k < 3; ++k) {
         int w = code[i].out_vw[k];
-        if (w < 0) continue;
+        if (w < 0 || vw[w].slot >= 0) continue;  // (time-split copies write the same wire)
         int max_delta = 1;
         for (int j = 0; j < nc; ++j)
           for (int q = 0; q < 4; ++q)
