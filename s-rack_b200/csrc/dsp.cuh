@@ -381,7 +381,8 @@ struct MoogOp {
   uint32_t* s;
   float f, p, q, b0, b1, b2, b3, b4, c_freq, c_res;
   float freq, r, exp_amt;
-  Port p_audio, p_cv, p_lp, p_bp, p_hp;
+  bool ext;  // coefficients arrive on three wires from a MoogCoefOp, which then owns f, p, q and the cache
+  Port p_audio, p_cv, p_lp, p_bp, p_hp, p_f, p_p, p_q;
 
   __device__ __forceinline__ void load(const Instr& ins, const Lane& ln) {
     s = ln.st + ins.state * L;
@@ -393,27 +394,36 @@ struct MoogOp {
     freq = __uint_as_float(pp[0]);
     r = fminf(fmaxf(__uint_as_float(pp[L]), 0.0f), 1.0f);  // :214
     exp_amt = __uint_as_float(pp[2 * L]);
-    p_audio = port(ln, ins.in[0]); p_cv = port(ln, ins.in[1]);
+    ext = ins.flags & F_MOOG_EXT_COEF;
+    p_audio = port(ln, ins.in[0]);
+    p_cv = ext ? Port{nullptr, 0} : port(ln, ins.in[1]);
+    p_f = port(ln, ext ? ins.in[1] : -1); p_p = port(ln, ext ? ins.in[2] : -1); p_q = port(ln, ext ? ins.in[3] : -1);
     p_lp = port(ln, ins.out[0]); p_bp = port(ln, ins.out[1]); p_hp = port(ln, ins.out[2]);
   }
   __device__ __forceinline__ void store() {
-    s[0] = __float_as_uint(f); s[L] = __float_as_uint(p); s[2 * L] = __float_as_uint(q);
     s[3 * L] = __float_as_uint(b0); s[4 * L] = __float_as_uint(b1); s[5 * L] = __float_as_uint(b2);
     s[6 * L] = __float_as_uint(b3); s[7 * L] = __float_as_uint(b4);
+    if (ext) return;
+    s[0] = __float_as_uint(f); s[L] = __float_as_uint(p); s[2 * L] = __float_as_uint(q);
     s[8 * L] = __float_as_uint(c_freq); s[9 * L] = __float_as_uint(c_res);
   }
 
-  // OUTS: bit 0 lowpass, bit 1 bandpass, bit 2 highpass are read by somebody (compile-time,
-  // like OscOp's).
-  template <bool HAS_CV, int OUTS>
+  // COEF: 0 = no CV (constant cutoff), 1 = CV, coefficients computed here, 2 = coefficients
+  // from a MoogCoefOp.  OUTS: bit 0 lowpass, bit 1 bandpass, bit 2 highpass are read by
+  // somebody (compile-time, like OscOp's).
+  template <int COEF, int OUTS>
   __device__ __forceinline__ void run_t(const Lane& ln, int kk) {
+    constexpr bool HAS_CV = COEF == 1;
     const float* audio = p_audio.at(ln);
     const float* cv = p_cv.at(ln);
+    const float* wf = p_f.at(ln);
+    const float* wp = p_p.at(ln);
+    const float* wq = p_q.at(ln);
     float* lowpass = p_lp.at(ln);
     float* bandpass = p_bp.at(ln);
     float* highpass = p_hp.at(ln);
     bool virgin = (c_freq == 0.0f) & (c_res == 0.0f) & (f == 0.0f);
-    if (!HAS_CV && kk > 0) {  // cutoff is constant over the chunk: one cache check (:61)
+    if (COEF == 0 && kk > 0) {  // cutoff is constant over the chunk: one cache check (:61)
       const float fc = fminf(fmaxf(fadd(freq, fmul(0.0f, exp_amt)), 0.0f), 0.9f);  // :213 with cv = 0.0
       if (fc != c_freq || r != c_res) {
         c_freq = fc;
@@ -445,6 +455,9 @@ struct MoogOp {
         }
         if (!virgin) { c_freq = fc[U - 1]; c_res = r; }
         f = fj[U - 1]; p = pj[U - 1]; q = qj[U - 1];
+      } else if (COEF == 2) {
+#pragma unroll
+        for (int j = 0; j < U; ++j) { fj[j] = wf[(k0 + j) * L]; pj[j] = wp[(k0 + j) * L]; qj[j] = wq[(k0 + j) * L]; }
       } else {
 #pragma unroll
         for (int j = 0; j < U; ++j) { fj[j] = f; pj[j] = p; qj[j] = q; }
@@ -481,24 +494,76 @@ struct MoogOp {
     });
   }
 
-  template <bool HAS_CV>
+  template <int COEF>
   __device__ __forceinline__ void run_outs(const Lane& ln, int kk) {
     const int outs = (p_lp.base ? 1 : 0) | (p_bp.base ? 2 : 0) | (p_hp.base ? 4 : 0);
     switch (outs) {
-      case 0: run_t<HAS_CV, 0>(ln, kk); break;
-      case 1: run_t<HAS_CV, 1>(ln, kk); break;
-      case 2: run_t<HAS_CV, 2>(ln, kk); break;
-      case 3: run_t<HAS_CV, 3>(ln, kk); break;
-      case 4: run_t<HAS_CV, 4>(ln, kk); break;
-      case 5: run_t<HAS_CV, 5>(ln, kk); break;
-      case 6: run_t<HAS_CV, 6>(ln, kk); break;
-      default: run_t<HAS_CV, 7>(ln, kk); break;
+      case 0: run_t<COEF, 0>(ln, kk); break;
+      case 1: run_t<COEF, 1>(ln, kk); break;
+      case 2: run_t<COEF, 2>(ln, kk); break;
+      case 3: run_t<COEF, 3>(ln, kk); break;
+      case 4: run_t<COEF, 4>(ln, kk); break;
+      case 5: run_t<COEF, 5>(ln, kk); break;
+      case 6: run_t<COEF, 6>(ln, kk); break;
+      default: run_t<COEF, 7>(ln, kk); break;
     }
   }
 
   __device__ __forceinline__ void run(const Instr&, const Lane& ln, int kk) {
-    if (p_cv.base) run_outs<true>(ln, kk);
-    else run_outs<false>(ln, kk);
+    if (ext) run_outs<2>(ln, kk);
+    else if (p_cv.base) run_outs<1>(ln, kk);
+    else run_outs<0>(ln, kk);
+  }
+};
+
+// The coefficient half of a CV-driven filter on its own warp (program.cpp splits it off when
+// warps are spare): same arithmetic and cache semantics as MoogOp's COEF == 1 path; owns the
+// state words f, p, q, freq, res and writes (f, p, q) per sample to three wires.
+struct MoogCoefOp {
+  uint32_t* s;
+  float f, p, q, c_freq, c_res, freq, r, exp_amt;
+  Port p_cv, p_f, p_p, p_q;
+
+  __device__ __forceinline__ void load(const Instr& ins, const Lane& ln) {
+    s = ln.st + ins.state * L;
+    f = __uint_as_float(s[0]); p = __uint_as_float(s[L]); q = __uint_as_float(s[2 * L]);
+    c_freq = __uint_as_float(s[8 * L]); c_res = __uint_as_float(s[9 * L]);
+    const uint32_t* pp = ln.pr + ins.param * L;
+    freq = __uint_as_float(pp[0]);
+    r = fminf(fmaxf(__uint_as_float(pp[L]), 0.0f), 1.0f);  // :214
+    exp_amt = __uint_as_float(pp[2 * L]);
+    p_cv = port(ln, ins.in[0]);
+    p_f = port(ln, ins.out[0]); p_p = port(ln, ins.out[1]); p_q = port(ln, ins.out[2]);
+  }
+  __device__ __forceinline__ void store() {
+    s[0] = __float_as_uint(f); s[L] = __float_as_uint(p); s[2 * L] = __float_as_uint(q);
+    s[8 * L] = __float_as_uint(c_freq); s[9 * L] = __float_as_uint(c_res);
+  }
+  __device__ __forceinline__ void run(const Instr&, const Lane& ln, int kk) {
+    const float* cv = p_cv.at(ln);
+    float* wf = p_f.at(ln);
+    float* wp = p_p.at(ln);
+    float* wq = p_q.at(ln);
+    bool virgin = (c_freq == 0.0f) & (c_res == 0.0f) & (f == 0.0f);
+    for_groups(kk, [&](auto u, int k0) {
+      constexpr int U = decltype(u)::value;
+      float fc[U], fj[U], pj[U], qj[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) fc[j] = fminf(fmaxf(fadd(freq, fmul(cv[(k0 + j) * L], exp_amt)), 0.0f), 0.9f);  // :213
+#pragma unroll
+      for (int j = 0; j < U; ++j) moog_coef(fc[j], r, fj[j], pj[j], qj[j]);
+      if (virgin) {  // only until (fc, r) first leaves (0, 0)
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          virgin = virgin & (fc[j] == 0.0f) & (r == 0.0f);
+          if (virgin) { fj[j] = 0.0f; pj[j] = 0.0f; qj[j] = 0.0f; }
+        }
+      }
+      if (!virgin) { c_freq = fc[U - 1]; c_res = r; }
+      f = fj[U - 1]; p = pj[U - 1]; q = qj[U - 1];
+#pragma unroll
+      for (int j = 0; j < U; ++j) { wf[(k0 + j) * L] = fj[j]; wp[(k0 + j) * L] = pj[j]; wq[(k0 + j) * L] = qj[j]; }
+    });
   }
 };
 

@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) render_voices_kernel(const Ren
         break;
       }
       case OP_MOOG: run_resident<dsp::MoogOp>(ins, ln, a, n_chunks, n_iter); break;
+      case OP_MOOG_COEF: run_resident<dsp::MoogCoefOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_ADSR: run_resident<dsp::AdsrOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_NOISE: run_resident<dsp::NoiseOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_VCA: run_resident<dsp::VcaOp>(ins, ln, a, n_chunks, n_iter); break;
@@ -258,6 +259,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) render_voices_kernel(const Ren
         switch (ins.op) {
           case OP_OSC: run_once<dsp::OscOp>(ins, ln, kk); break;
           case OP_MOOG: run_once<dsp::MoogOp>(ins, ln, kk); break;
+          case OP_MOOG_COEF: run_once<dsp::MoogCoefOp>(ins, ln, kk); break;
           case OP_ADSR: run_once<dsp::AdsrOp>(ins, ln, kk); break;
           case OP_NOISE: run_once<dsp::NoiseOp>(ins, ln, kk); break;
           case OP_VCA: run_once<dsp::VcaOp>(ins, ln, kk); break;

@@ -13,6 +13,7 @@
 #include "program.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 
 #include "patch.hpp"
@@ -38,7 +39,8 @@ int osc_shape_cost(const Pending& p) {
 
 int op_cost(const Pending& p) {
   switch (p.ins.op) {
-    case OP_MOOG: return 115;
+    case OP_MOOG: return p.ins.flags & F_MOOG_EXT_COEF ? 95 : 115;
+    case OP_MOOG_COEF: return 45;
     case OP_OSC: {
       const int n = std::max(1, p.ins.flags >> 4);  // time-split copies share the shaping work
       return osc_phase_cost(p) + osc_shape_cost(p) / n;
@@ -244,21 +246,52 @@ int compile_program(const srk_patch& patch, int max_warps, Program& prog, std::s
     // the recurrence (identical state, bit for bit) and copy i shapes only chunks with
     // chunk % n == i, so the slowest pipeline stage shrinks from phase + shape to
     // phase + shape / n.  Copy 0 alone stores the state back.
-    std::vector<Pending> split;
+    std::vector<int> copies(code.size(), 1);
     int spare = std::min(max_warps, kMaxWarps) - (int)code.size();
-    for (const Pending& p : code) {
-      int n = 1;
-      if (p.ins.op == OP_OSC && p.in_vw[0] < 0) {
-        const int phase = osc_phase_cost(p), shape = osc_shape_cost(p);
-        while (n < 4 && phase + shape / n > 100 && spare >= n) n *= 2;  // n -> 2n adds n warps
-        if (n > 1) spare -= n - 1;
+    for (;;) {  // double the copies of the currently slowest splittable oscillator while warps last
+      int best = -1, best_cost = 60;  // per-copy cost under which splitting further is pointless
+      for (size_t i = 0; i < code.size(); ++i) {
+        const Pending& p = code[i];
+        if (p.ins.op != OP_OSC || p.in_vw[0] >= 0 || copies[i] >= 4 || spare < copies[i]) continue;
+        const int c = osc_phase_cost(p) + osc_shape_cost(p) / copies[i];
+        if (c > best_cost) { best = (int)i; best_cost = c; }
       }
-      for (int i = 0; i < n; ++i) {
-        Pending q = p;
-        if (n > 1) q.ins.flags = (uint8_t)((n << 4) | i);
+      if (best < 0) break;
+      spare -= copies[best];  // n -> 2n adds n warps
+      copies[best] *= 2;
+    }
+    // Split CV-driven ladder filters: the coefficient block (filter.rs:61-68) is a pure function
+    // of the CV sample, ~20 of the filter's ~75 instructions per sample and off the ladder's
+    // dependency chain -- it moves to its own warp and feeds (f, p, q) through three wires.
+    // Measured on B200 (profiles/r01o): 4.09 ms vs 4.13 ms per step at equal chunk length -- the
+    // ladder is bound by its dependency chain, not by issue slots -- and the three extra wires
+    // halve the chunk that fits in shared memory, so it is off unless SRK_MOOG_SPLIT=1.
+    const char* split_env = std::getenv("SRK_MOOG_SPLIT");
+    const bool split_coef = split_env && split_env[0] == '1';
+    std::vector<int> coef_of(code.size(), 0);
+    for (size_t i = 0; split_coef && i < code.size() && spare > 0; ++i)
+      if (code[i].ins.op == OP_MOOG && code[i].in_vw[1] >= 0) { coef_of[i] = 1; --spare; }
+    std::vector<Pending> split;
+    for (size_t i = 0; i < code.size(); ++i)
+      for (int c = 0; c < copies[i]; ++c) {
+        if (coef_of[i]) {
+          Pending k = code[i];
+          k.ins.op = OP_MOOG_COEF;
+          for (int j = 1; j < 4; ++j) k.in_vw[j] = -1;
+          k.in_vw[0] = code[i].in_vw[1];
+          for (int j = 0; j < 3; ++j) {
+            vw.push_back(VWire());
+            vw.back().last_use = 0;  // read by the ladder below
+            k.out_vw[j] = (int)vw.size() - 1;
+            code[i].in_vw[1 + j] = k.out_vw[j];
+          }
+          code[i].ins.flags |= F_MOOG_EXT_COEF;
+          split.push_back(k);
+        }
+        Pending q = code[i];
+        if (copies[i] > 1) q.ins.flags = (uint8_t)((copies[i] << 4) | c);
         split.push_back(q);
       }
-    }
     code.swap(split);
   }
   const int nc = (int)code.size();
@@ -337,12 +370,19 @@ int compile_program(const srk_patch& patch, int max_warps, Program& prog, std::s
     int load[4] = {0, 0, 0, 0}, count[4] = {0, 0, 0, 0};
     std::vector<int> warp_load(cap, 0);
     int n_warps = 1;
+    // The slowest instruction (the pipeline's critical stage, normally the ladder filter's
+    // dependent chain) gets sub-partition 0 to itself when the other three have warps enough
+    // for everything else: co-resident warps steal its issue slots.
+    const bool isolate = nc >= 2 && nc - 1 <= 3 * (cap / 4);
+    bool first = true;
     for (int idx : order) {
       int best = -1;
       for (int s = 0; s < 4; ++s) {
         if (s + 4 * count[s] >= cap) continue;  // no free warp left on this sub-partition
+        if (isolate && !first && s == 0) continue;
         if (best < 0 || load[s] < load[best]) best = s;
       }
+      first = false;
       int w;
       if (best >= 0) {
         w = best + 4 * count[best]++;

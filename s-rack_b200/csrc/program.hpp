@@ -30,10 +30,12 @@ enum Op : uint8_t {
   OP_MATH,
   OP_OUTPUT,      // channels aux .. aux+3 <- in[0..3]: per-voice stems
   OP_MIX,         // channels aux .. aux+3: this voice group's share of the mixdown
+  OP_MOOG_COEF,   // out[0..2] <- ladder coefficients (f, p, q) of a filter's CV input in[0]
 };
 
 // Instr::flags
 enum : uint8_t { F_MATH_ADD = 0, F_MATH_SUB = 1, F_MATH_MUL = 2, F_MATH_NONLIN = 3 };
+enum : uint8_t { F_MOOG_EXT_COEF = 1 };  // OP_MOOG: in[1..3] carry (f, p, q) from an OP_MOOG_COEF instead of the CV
 
 // ADSR mode encoding in the state word (adsr.rs:26-33 order)
 enum : uint32_t { ADSR_ATTACK = 0, ADSR_DECAY = 1, ADSR_SUSTAIN = 2, ADSR_RELEASE = 3, ADSR_NONE = 4 };
