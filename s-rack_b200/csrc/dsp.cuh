@@ -431,9 +431,11 @@ struct MoogOp {
         moog_coef(fc, r, f, p, q);
       }
     }
-    for_groups(kk, [&](auto u, int k0) {
+    // prep(): everything that does not depend on the ladder state -- input loads and the
+    // coefficient block, in sample order (the cache key and the `virgin` flag are sequential
+    // but cheap).  ladder(): the dependent chain (:69-82) and the write-out.
+    auto prep = [&](auto u, int k0, float* a, float* fj, float* pj, float* qj) {
       constexpr int U = decltype(u)::value;
-      float a[U], fj[U], pj[U], qj[U], in_[U], o3[U], o4[U];
 #pragma unroll
       for (int j = 0; j < U; ++j) a[j] = 0.0f;
       if (audio) {
@@ -462,7 +464,10 @@ struct MoogOp {
 #pragma unroll
         for (int j = 0; j < U; ++j) { fj[j] = f; pj[j] = p; qj[j] = q; }
       }
-      // the ladder (:69-82): the only dependent chain
+    };
+    auto ladder = [&](auto u, int k0, const float* a, const float* fj, const float* pj, const float* qj) {
+      constexpr int U = decltype(u)::value;
+      float in_[U], o3[U], o4[U];
 #pragma unroll
       for (int j = 0; j < U; ++j) {
         const float in = fsub(a[j], fmul(qj[j], b4));
@@ -491,7 +496,33 @@ struct MoogOp {
 #pragma unroll
         for (int j = 0; j < U; ++j) bandpass[(k0 + j) * L] = fmul(3.0f, fsub(o3[j], o4[j]));
       }
-    });
+    };
+    // Software pipeline over groups: group g+1's prep sits in the same basic block as group
+    // g's ladder, so its loads and ~20 flops per sample fill the chain's latency bubbles.
+    constexpr int G = kGroup;
+    const int n_full = kk / G;
+    int k0 = 0;
+    if (n_full > 0) {
+      float a0[G], f0[G], p0[G], q0[G];
+      prep(UC<G>(), 0, a0, f0, p0, q0);
+#pragma unroll 1
+      for (int g = 1; g < n_full; ++g) {
+        float a1[G], f1[G], p1[G], q1[G];
+        prep(UC<G>(), k0 + G, a1, f1, p1, q1);
+        ladder(UC<G>(), k0, a0, f0, p0, q0);
+#pragma unroll
+        for (int j = 0; j < G; ++j) { a0[j] = a1[j]; f0[j] = f1[j]; p0[j] = p1[j]; q0[j] = q1[j]; }
+        k0 += G;
+      }
+      ladder(UC<G>(), k0, a0, f0, p0, q0);
+      k0 += G;
+    }
+#pragma unroll 1
+    for (; k0 < kk; ++k0) {
+      float a1[1], f1[1], p1[1], q1[1];
+      prep(UC<1>(), k0, a1, f1, p1, q1);
+      ladder(UC<1>(), k0, a1, f1, p1, q1);
+    }
   }
 
   template <int COEF>

@@ -102,9 +102,14 @@ __device__ __forceinline__ void run_output(const Instr& ins, const dsp::Lane& ln
     dst[j] = a.stems + ((size_t)(ins.aux + j) * a.n_samples + n0) * a.V + g.v;
   }
   const uint32_t V = a.V;  // offsets inside one chunk fit 32 bits as long as K * V < 2^32 (checked at launch)
+  uint32_t row = 0;        // k0 * V, carried instead of recomputed
   dsp::for_groups(kk, [&](auto u, int k0) {
     constexpr int U = decltype(u)::value;
     float x[U];
+    uint32_t off[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) off[q] = row + q * V;
+    row += U * V;
 #pragma unroll
     for (int j = 0; j < kOutputChannelsPerInstr; ++j) {
       if (j >= ins.n_ch) break;
@@ -113,7 +118,7 @@ __device__ __forceinline__ void run_output(const Instr& ins, const dsp::Lane& ln
         for (int q = 0; q < U; ++q) x[q] = src[j] ? src[j][(k0 + q) * 32] : 0.0f;
       }
 #pragma unroll
-      for (int q = 0; q < U; ++q) __stcs(dst[j] + (uint32_t)(k0 + q) * V, x[q]);
+      for (int q = 0; q < U; ++q) __stcs(dst[j] + off[q], x[q]);
     }
   });
 }
@@ -251,7 +256,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) render_voices_kernel(const Ren
   } else {
     for (uint32_t it = 0; it < n_iter; ++it) {
       for (uint32_t pc = pc0; pc < pc1; ++pc) {
-        const Instr ins = prog[pc];
+        const Instr& ins = prog[pc];  // stays in shared memory: fields are read where they are used
         const uint32_t chunk = it - ins.stage;
         if (chunk >= n_chunks) continue;  // also catches it < stage (wraps)
         const int kk = (int)min(K, a.n_samples - chunk * K);
