@@ -166,12 +166,12 @@ struct OscOp {
 
   // OUTS: bit 0 sine, bit 1 square, bit 2 saw are read by somebody.  Compile-time, because a
   // per-group `if (port connected)` costs more than the arithmetic it guards (see header).
-  template <bool HAS_CV, int OUTS>
+  template <bool HAS_CV, bool HAS_SYNC, int OUTS>
   __device__ __forceinline__ void run_t(const Lane& ln, int kb, int ke) {
     constexpr bool SINE = OUTS & 1, SQUARE = OUTS & 2, SAW = OUTS & 4;
     const float* cv = p_cv.at(ln);
     const float* sync = p_sync.at(ln);
-    const bool has_sync = sync != nullptr;
+    constexpr bool has_sync = HAS_SYNC;
     float* sine = p_sine.at(ln);
     float* square = p_square.at(ln);
     float* saw = p_saw.at(ln);
@@ -203,7 +203,7 @@ struct OscOp {
       bool odd = false;
 #pragma unroll
       for (int j = 0; j < U; ++j) {
-        pos = edge[j] ? 0.0 : pos;
+        if (HAS_SYNC) pos = edge[j] ? 0.0 : pos;
         ps[j] = pos;
         const double x = dadd(pos, dl[j]);
         odd |= !(x < 2.0);  // NaN, inf or a step of more than one period: exact path below
@@ -213,7 +213,7 @@ struct OscOp {
         pos = pos0;
 #pragma unroll
         for (int j = 0; j < U; ++j) {
-          pos = edge[j] ? 0.0 : pos;
+          if (HAS_SYNC) pos = edge[j] ? 0.0 : pos;
           ps[j] = pos;
           pos = fmod1_exact(dadd(pos, dl[j]));
         }
@@ -272,19 +272,49 @@ struct OscOp {
     if (!has_sync && ke > kb) last = false;
   }
 
-  template <bool HAS_CV>
+  template <bool HAS_CV, bool HAS_SYNC>
   __device__ __forceinline__ void run_outs(const Lane& ln, int kb, int ke) {
     const int outs = (p_sine.base ? 1 : 0) | (p_square.base ? 2 : 0) | (p_saw.base ? 4 : 0);
     switch (outs) {
-      case 0: run_t<HAS_CV, 0>(ln, kb, ke); break;
-      case 1: run_t<HAS_CV, 1>(ln, kb, ke); break;
-      case 2: run_t<HAS_CV, 2>(ln, kb, ke); break;
-      case 3: run_t<HAS_CV, 3>(ln, kb, ke); break;
-      case 4: run_t<HAS_CV, 4>(ln, kb, ke); break;
-      case 5: run_t<HAS_CV, 5>(ln, kb, ke); break;
-      case 6: run_t<HAS_CV, 6>(ln, kb, ke); break;
-      default: run_t<HAS_CV, 7>(ln, kb, ke); break;
+      case 0: run_t<HAS_CV, HAS_SYNC, 0>(ln, kb, ke); break;
+      case 1: run_t<HAS_CV, HAS_SYNC, 1>(ln, kb, ke); break;
+      case 2: run_t<HAS_CV, HAS_SYNC, 2>(ln, kb, ke); break;
+      case 3: run_t<HAS_CV, HAS_SYNC, 3>(ln, kb, ke); break;
+      case 4: run_t<HAS_CV, HAS_SYNC, 4>(ln, kb, ke); break;
+      case 5: run_t<HAS_CV, HAS_SYNC, 5>(ln, kb, ke); break;
+      case 6: run_t<HAS_CV, HAS_SYNC, 6>(ln, kb, ke); break;
+      default: run_t<HAS_CV, HAS_SYNC, 7>(ln, kb, ke); break;
     }
+  }
+
+  // The phase recurrence alone over [kb, ke) for an oscillator with neither CV nor sync
+  // (what a time-split copy runs outside its own share): DADD, DADD, compare, select per
+  // sample, 8 samples per loop trip, the odd-step test once per trip.
+  __device__ __forceinline__ void advance(int kb, int ke) {
+    const double dl = delta_const;
+    int k = kb;
+#pragma unroll 1
+    for (; k + 8 <= ke; k += 8) {
+      const double pos0 = pos;
+      bool odd = false;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const double x = dadd(pos, dl);
+        odd |= !(x < 2.0);
+        pos = wrap01(x);
+      }
+      if (odd) {
+        pos = pos0;
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) pos = fmod1_exact(dadd(pos, dl));
+      }
+    }
+#pragma unroll 1
+    for (; k < ke; ++k) {
+      const double x = dadd(pos, dl);
+      pos = x < 2.0 ? wrap01(x) : fmod1_exact(x);
+    }
+    if (ke > kb) last = false;
   }
 
   // flags = (n << 4) | i for a time-split copy (program.cpp): every copy advances the phase
@@ -292,16 +322,30 @@ struct OscOp {
   // within one barrier interval each copy does phase(K) + shape(K / n)).
   __device__ __forceinline__ void run(const Instr& ins, const Lane& ln, int kk) {
     const uint32_t n = ins.flags >> 4;
-    if (n > 1) {  // only CV-less oscillators are split
+    const bool cv = p_cv.base != nullptr, sync = p_sync.base != nullptr;
+    if (n > 1 && !cv && !sync) {
       const int span = (int)(ln.tile_elems / L / n);
       const int lo = min(kk, (int)(ins.flags & 15u) * span), hi = min(kk, lo + span);
-      run_t<false, 0>(ln, 0, lo);
-      run_outs<false>(ln, lo, hi);
-      run_t<false, 0>(ln, hi, kk);
+      advance(0, lo);
+      run_outs<false, false>(ln, lo, hi);
+      advance(hi, kk);
       return;
     }
-    if (p_cv.base) run_outs<true>(ln, 0, kk);
-    else run_outs<false>(ln, 0, kk);
+    if (n > 1) {  // (a split copy with a sync input: same ranges through the general body)
+      const int span = (int)(ln.tile_elems / L / n);
+      const int lo = min(kk, (int)(ins.flags & 15u) * span), hi = min(kk, lo + span);
+      run_t<false, true, 0>(ln, 0, lo);
+      run_outs<false, true>(ln, lo, hi);
+      run_t<false, true, 0>(ln, hi, kk);
+      return;
+    }
+    if (cv) {
+      if (sync) run_outs<true, true>(ln, 0, kk);
+      else run_outs<true, false>(ln, 0, kk);
+    } else {
+      if (sync) run_outs<false, true>(ln, 0, kk);
+      else run_outs<false, false>(ln, 0, kk);
+    }
   }
   __device__ __forceinline__ bool owns_state(const Instr& ins) const { return (ins.flags & 15u) == 0; }
 };

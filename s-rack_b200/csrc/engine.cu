@@ -203,7 +203,12 @@ __device__ __forceinline__ void run_once(const Instr& ins, const dsp::Lane& ln, 
   op.store();
 }
 
-__global__ void __launch_bounds__(kMaxThreads, 1) render_voices_kernel(const RenderArgs a) {
+// Two instantiations, two separate pieces of code: SOLO (one warp per voice group runs the whole
+// program chunk by chunk; the throughput shape) carries only the interpreter, PIPELINED adds the
+// resident single-instruction loops.  Keeping them apart keeps each one's hot code close together
+// (the one-warp schedule lost 14 % when the resident variants grew the shared kernel, r01s).
+template <bool SOLO>
+__global__ void __launch_bounds__(SOLO ? 32 : kMaxThreads, 1) render_voices_kernel(const RenderArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const Instr* prog = reinterpret_cast<const Instr*>(smem_raw);
@@ -228,9 +233,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) render_voices_kernel(const Ren
   const uint32_t K = a.K;
   const uint32_t n_chunks = (a.n_samples + K - 1) / K;
   const uint32_t n_iter = n_chunks + a.n_stages - 1;
-  const GroupCtx g{a, v, n_active, active, lane, a.n_warps == 1};
+  const GroupCtx g{a, v, n_active, active, lane, SOLO};
 
-  if (!g.solo && pc1 == pc0 + 1) {
+  if (!SOLO && pc1 == pc0 + 1) {
     const Instr ins = prog[pc0];
     switch (ins.op) {
       case OP_OSC: {
@@ -277,7 +282,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) render_voices_kernel(const Ren
           default: break;
         }
       }
-      if (g.solo) __syncwarp(); else __syncthreads();
+      if (SOLO) __syncwarp(); else __syncthreads();
     }
   }
   __syncthreads();
@@ -654,8 +659,13 @@ int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t
   a.seed_hi = (uint32_t)(patch->seed >> 32);
 
   SRK_CUDA(cudaEventRecord(e.ev[1], work));
-  SRK_CUDA(cudaFuncSetAttribute(render_voices_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  render_voices_kernel<<<grid, T, smem, work>>>(a);
+  if (prog.n_warps == 1) {
+    SRK_CUDA(cudaFuncSetAttribute(render_voices_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    render_voices_kernel<true><<<grid, T, smem, work>>>(a);
+  } else {
+    SRK_CUDA(cudaFuncSetAttribute(render_voices_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    render_voices_kernel<false><<<grid, T, smem, work>>>(a);
+  }
   SRK_CUDA(cudaGetLastError());
   ++e.launches;
   SRK_CUDA(cudaEventRecord(e.ev[2], work));
