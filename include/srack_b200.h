@@ -222,6 +222,29 @@ typedef struct srk_program_info {
   uint32_t n_warps, n_stages, n_tiles, reserved;
 } srk_program_info;
 SRK_API int srk_get_program_info(srk_patch* patch, size_t n_voices, srk_program_info* out);
+/* The compiled, scheduled device program itself (what execute() becomes for n_voices voices):
+ * one entry per instruction -- the modules of the plan in plan order (src/synth.rs:97-101), plus
+ * ring loads/stores for the wires the cycle breaker cut (synth.rs:168-192), the stems / mixdown
+ * instructions of the Output, time-split oscillator copies -- sorted by the warp that runs it,
+ * terminated by an op-0 entry; and one entry per wire slot.  For inspection and tests: the
+ * schedule is checked on the CPU without a device (tests/test_program.py). */
+typedef struct srk_instr_info {
+  uint8_t op;      /* 0 end, 1 ring load, 2 ring store, 3 oscillator, 4 noise, 5 moog, 6 adsr, 7 vca,
+                      8 mixer, 9 math, 10 output (stems), 11 mix, 12 moog coefficients */
+  uint8_t flags;   /* math: operation; oscillator: (copies << 4) | copy index when time-split */
+  uint8_t warp;    /* warp of the 32-voice group that executes it */
+  uint8_t stage;   /* works on chunk (iteration - stage) */
+  int16_t in[4];   /* wire slot per input, -1 = not connected */
+  int16_t out[3];  /* wire slot per output port, -1 = nobody reads it */
+  uint8_t n_ch;    /* output / mix: channels covered */
+  uint8_t reserved;
+  uint16_t state, param, aux; /* first state word, first parameter word, ring / channel / module index */
+} srk_instr_info;
+typedef struct srk_wire_info {
+  uint16_t first_tile, n_tiles; /* ring of n_tiles [chunk][32 voices] tiles; chunk c lives in tile c % n_tiles */
+} srk_wire_info;
+SRK_API int srk_get_program(srk_patch* patch, size_t n_voices, srk_instr_info* instrs, size_t instr_cap,
+                            size_t* n_instr, srk_wire_info* wires, size_t wire_cap, size_t* n_wires);
 
 #ifdef __cplusplus
 }

@@ -22,6 +22,19 @@ class srk_program_info(C.Structure):
                                           "n_warps", "n_stages", "n_tiles", "reserved")]
 
 
+class srk_instr_info(C.Structure):
+    _fields_ = [("op", C.c_uint8), ("flags", C.c_uint8), ("warp", C.c_uint8), ("stage", C.c_uint8),
+                ("in_", C.c_int16 * 4), ("out", C.c_int16 * 3), ("n_ch", C.c_uint8), ("reserved", C.c_uint8),
+                ("state", C.c_uint16), ("param", C.c_uint16), ("aux", C.c_uint16)]
+
+
+class srk_wire_info(C.Structure):
+    _fields_ = [("first_tile", C.c_uint16), ("n_tiles", C.c_uint16)]
+
+
+OPS = ["END", "RING_LOAD", "RING_STORE", "OSC", "NOISE", "MOOG", "ADSR", "VCA", "MIXER", "MATH", "OUTPUT", "MIX",
+       "MOOG_COEF"]
+
 # status codes / kinds / params / flags: keep in sync with include/srack_b200.h
 # (tests/test_abi.py parses the header and compares)
 STATUS = dict(OK=0, ERR_ARG=1, ERR_PORT=2, ERR_KIND=3, ERR_UNSUPPORTED=4, ERR_PARAM=5, ERR_SELF_LOOP=6,
@@ -78,6 +91,8 @@ _SIGNATURES = {
     "srk_last_render_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "srk_launch_count": (C.c_uint64, [_P]),
     "srk_get_program_info": (C.c_int, [_P, C.c_size_t, C.POINTER(srk_program_info)]),
+    "srk_get_program": (C.c_int, [_P, C.c_size_t, C.POINTER(srk_instr_info), C.c_size_t, C.POINTER(C.c_size_t),
+                                  C.POINTER(srk_wire_info), C.c_size_t, C.POINTER(C.c_size_t)]),
 }
 
 

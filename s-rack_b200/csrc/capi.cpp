@@ -319,4 +319,10 @@ int srk_get_program_info(srk_patch* p, size_t n_voices, srk_program_info* out) {
   return srk::engine_program_info(p, n_voices, out);
 }
 
+int srk_get_program(srk_patch* p, size_t n_voices, srk_instr_info* instrs, size_t instr_cap, size_t* n_instr,
+                    srk_wire_info* wires, size_t wire_cap, size_t* n_wires) {
+  if (!p) return SRK_ERR_ARG;
+  return srk::engine_program_dump(p, n_voices, instrs, instr_cap, n_instr, wires, wire_cap, n_wires);
+}
+
 }  // extern "C"

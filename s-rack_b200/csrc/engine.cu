@@ -723,19 +723,19 @@ int engine_last_ms(srk_patch* patch, float* kernel_ms, float* total_ms) {
 
 uint64_t engine_launches(const srk_patch* patch) { return patch->engine ? patch->engine->launches : 0; }
 
-int engine_program_info(srk_patch* patch, size_t n_voices, srk_program_info* out) {
+// Compiles the planned patch the way a render of n_voices would (no device needed: the sm_100
+// limits are assumed when the patch has no engine yet).
+static int probe_program(srk_patch* patch, size_t n_voices, Program& prog, std::vector<uint4>& blob, int& K) {
   if (!patch->planned) { patch->last_error = "not planned"; return SRK_ERR_NOT_PLANNED; }
-  Engine probe;  // geometry without a device: assume the sm_100 limits
+  Engine probe;
   probe.smem_optin = patch->engine ? patch->engine->smem_optin : 227 * 1024;
   probe.n_sm = patch->engine ? patch->engine->n_sm : 148;
   probe.smem_sm = patch->engine ? patch->engine->smem_sm : 228 * 1024;
-  Program prog;
   std::string err;
-  std::vector<uint4> blob;
   int rc = compile_program(*patch, choose_max_warps(probe, n_voices), prog, err);
   if (rc != SRK_OK) { patch->last_error = err; return rc; }
   build_blob(prog, blob);
-  int K = choose_chunk(probe, prog, blob.size(), 1u << 30, n_voices);
+  K = choose_chunk(probe, prog, blob.size(), 1u << 30, n_voices);
   if (K == 0 && prog.n_warps > 1) {
     rc = compile_program(*patch, 1, prog, err);
     if (rc != SRK_OK) { patch->last_error = err; return rc; }
@@ -743,6 +743,15 @@ int engine_program_info(srk_patch* patch, size_t n_voices, srk_program_info* out
     K = choose_chunk(probe, prog, blob.size(), 1u << 30, n_voices);
   }
   if (K == 0) { patch->last_error = "patch needs more shared memory than one block can have"; return SRK_ERR_LIMIT; }
+  return SRK_OK;
+}
+
+int engine_program_info(srk_patch* patch, size_t n_voices, srk_program_info* out) {
+  Program prog;
+  std::vector<uint4> blob;
+  int K = 0;
+  int rc = probe_program(patch, n_voices, prog, blob, K);
+  if (rc != SRK_OK) return rc;
   out->n_instr = (uint32_t)prog.code.size();
   out->step_samples = (uint32_t)K;
   out->block_threads = prog.n_warps * 32;
@@ -754,6 +763,32 @@ int engine_program_info(srk_patch* patch, size_t n_voices, srk_program_info* out
   out->n_warps = prog.n_warps;
   out->n_stages = prog.n_stages;
   out->n_tiles = prog.n_tiles;
+  out->reserved = 0;
+  return SRK_OK;
+}
+
+int engine_program_dump(srk_patch* patch, size_t n_voices, srk_instr_info* instrs, size_t instr_cap, size_t* n_instr,
+                        srk_wire_info* wires, size_t wire_cap, size_t* n_wires) {
+  Program prog;
+  std::vector<uint4> blob;
+  int K = 0;
+  int rc = probe_program(patch, n_voices, prog, blob, K);
+  if (rc != SRK_OK) return rc;
+  if (n_instr) *n_instr = prog.code.size();
+  if (n_wires) *n_wires = prog.wires.size();
+  for (size_t i = 0; instrs && i < prog.code.size() && i < instr_cap; ++i) {
+    const Instr& c = prog.code[i];
+    srk_instr_info& o = instrs[i];
+    o.op = c.op; o.flags = c.flags; o.warp = c.warp; o.stage = c.stage;
+    for (int k = 0; k < 4; ++k) o.in[k] = c.in[k];
+    for (int k = 0; k < 3; ++k) o.out[k] = c.out[k];
+    o.n_ch = c.n_ch;
+    o.state = c.state; o.param = c.param; o.aux = c.aux;
+  }
+  for (size_t i = 0; wires && i < prog.wires.size() && i < wire_cap; ++i) {
+    wires[i].first_tile = prog.wires[i].base;
+    wires[i].n_tiles = (uint16_t)(prog.wires[i].mask + 1);
+  }
   return SRK_OK;
 }
 

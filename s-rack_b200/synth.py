@@ -244,6 +244,18 @@ class Patch:
         self._check(lib.srk_get_program_info(self._h, n_voices, C.byref(info)))
         return {f: getattr(info, f) for f, _ in info._fields_}
 
+    def program(self, n_voices=0):
+        """The compiled, scheduled device program for n_voices voices -> (instrs, wires): lists of
+        dicts (op name, flags, warp, stage, in/out wire slots, ...) and (first_tile, n_tiles)."""
+        ni, nw = C.c_size_t(0), C.c_size_t(0)
+        self._check(lib.srk_get_program(self._h, n_voices, None, 0, C.byref(ni), None, 0, C.byref(nw)))
+        instrs = (_ffi.srk_instr_info * max(ni.value, 1))()
+        wires = (_ffi.srk_wire_info * max(nw.value, 1))()
+        self._check(lib.srk_get_program(self._h, n_voices, instrs, ni.value, C.byref(ni), wires, nw.value, C.byref(nw)))
+        out = [dict(op=_ffi.OPS[i.op], flags=i.flags, warp=i.warp, stage=i.stage, ins=list(i.in_), outs=list(i.out),
+                    n_ch=i.n_ch, state=i.state, param=i.param, aux=i.aux) for i in instrs[:ni.value]]
+        return out, [(w.first_tile, w.n_tiles) for w in wires[:nw.value]]
+
     # -- rendering -----------------------------------------------------------
     def render(self, n_voices, n_samples, voice_offset=0, stems=False, mix=True):
         """Render to freshly allocated host arrays -> (stems [C][N][V] or None, mix [C][N] or None)."""
