@@ -52,6 +52,7 @@ extern "C" {
     fn srk_get_input(sink: *const srk_module, input_idx: u8, src: *mut *mut srk_module, port: *mut u8) -> c_int;
     fn srk_set_param_f32(m: *mut srk_module, param_id: c_int, value: f32) -> c_int;
     fn srk_set_param_f32_per_voice(m: *mut srk_module, param_id: c_int, values: *const f32, n: usize) -> c_int;
+    fn srk_set_sequence(m: *mut srk_module, cells: *const i32, n_steps: usize) -> c_int;
     fn srk_plan(patch: *mut srk_patch) -> c_int;
     fn srk_plan_get(patch: *const srk_patch, out: *mut *mut srk_module, cap: usize, n: *mut usize) -> c_int;
     fn srk_render(patch: *mut srk_patch, n_voices: usize, voice_offset: usize, n_samples: usize,
@@ -112,6 +113,10 @@ impl Module {
     /// Struct fields the reference mutates from `ui()` (ids: `enum srk_param`).
     pub fn set_param(&self, param_id: i32, value: f32) -> Result<(), Error> {
         self.check(unsafe { srk_set_param_f32(self.h, param_id, value) })
+    }
+    /// A sequencer's step table (`sequencer.rs:18,341`): `n_steps` cells (grid) or 8 rows x `n_steps` (pattern).
+    pub fn set_sequence(&self, cells: &[i32], n_steps: usize) -> Result<(), Error> {
+        self.check(unsafe { srk_set_sequence(self.h, cells.as_ptr(), n_steps) })
     }
     pub fn set_param_per_voice(&self, param_id: i32, values: &[f32]) -> Result<(), Error> {
         self.check(unsafe { srk_set_param_f32_per_voice(self.h, param_id, values.as_ptr(), values.len()) })

@@ -69,7 +69,9 @@ enum srk_kind {
   SRK_KIND_SUBTRACT = 8,    /* src/synth/math.rs        "Subtract"    */
   SRK_KIND_MULTIPLY = 9,    /* src/synth/math.rs        "Multiply"    */
   SRK_KIND_NON_LINEAR = 10, /* src/synth/math.rs        "Non-Linear"  */
-  SRK_KIND_COUNT = 11
+  SRK_KIND_GRID_SEQUENCER = 11,    /* src/synth/sequencer.rs  "Grid Sequencer"    */
+  SRK_KIND_PATTERN_SEQUENCER = 12, /* src/synth/sequencer.rs  "Pattern Sequencer" */
+  SRK_KIND_COUNT = 13
 };
 
 /* ---- parameter ids (the reference mutates struct fields from ui(); there
@@ -95,8 +97,18 @@ enum srk_param {
   SRK_MIXER_GAIN2 = 2,
   SRK_MIXER_GAIN3 = 3,
   /* Add/Subtract/Multiply/Non-Linear: math.rs:21,184 */
-  SRK_MATH_CONSTANT = 0
+  SRK_MATH_CONSTANT = 0,
+  /* Grid sequencer: sequencer.rs:20 steps_per_octave (u16, default 12 at :44), uniform only */
+  SRK_GRIDSEQ_STEPS_PER_OCTAVE = 0
 };
+
+/* Sequence cells (srk_set_sequence).  Grid sequencer, sequencer.rs:18 `Vec<Option<(u16, bool)>>`:
+ * SRK_SEQ_NONE, or SRK_GRID_CELL(val, hold).  Pattern sequencer, sequencer.rs:341
+ * `Vec<Vec<Option<bool>>>`: SRK_SEQ_NONE, 0 (Some(false): pass the clock) or 1 (Some(true): hold). */
+#define SRK_SEQ_NONE (-1)
+#define SRK_GRID_CELL(val, hold) ((int32_t)(((val) & 0xFFFF) | ((hold) ? 0x10000 : 0)))
+#define SRK_SEQ_MAX_STEPS 64
+#define SRK_PATTERN_ROWS 8
 
 /* ---- render flags ------------------------------------------------------- */
 enum srk_render_flags {
@@ -123,8 +135,7 @@ SRK_API const char* srk_status_string(int status);
 SRK_API int srk_catalog_size(void);
 /* Name of entry i, e.g. "Oscillator"; NULL when i is out of range. */
 SRK_API const char* srk_catalog_name(int i);
-/* srk_kind of entry i, or -1 for entries outside the hot path
- * ("Grid Sequencer", "Pattern Sequencer", "Sample", "Freeverb"). */
+/* srk_kind of entry i, or -1 for entries outside the hot path ("Sample", "Freeverb"). */
 SRK_API int srk_catalog_kind(int i);
 
 /* ---- patch lifetime ----------------------------------------------------- */
@@ -178,6 +189,14 @@ SRK_API int srk_get_param_f32(const srk_module* m, int param_id, float* value);
 /* New axis: one value per voice (global voice index), e.g. detune.  The array is copied. */
 SRK_API int srk_set_param_f32_per_voice(srk_module* m, int param_id, const float* values, size_t n_voices);
 
+/* The step table a sequencer's ui() edits (sequencer.rs:98-188 grid, :388-470 pattern), the same for
+ * every voice.  Grid sequencer: `cells[n_steps]`; pattern sequencer: `cells[8][n_steps]` row major;
+ * 1 <= n_steps <= 64 (the reference's UI limits).  Default: 64 steps of None.  Voice state is kept
+ * (the reference edits the table under the module lock while the audio thread keeps running). */
+SRK_API int srk_set_sequence(srk_module* m, const int32_t* cells, size_t n_steps);
+/* *n_steps receives the current length; up to `cap` cells are copied out (rows x steps for the pattern). */
+SRK_API int srk_get_sequence(const srk_module* m, int32_t* cells, size_t cap, size_t* n_steps);
+
 /* ---- planning: plan_execution(output, &all_modules, &mut plan), src/synth.rs:128-212,
  *      called as in ui.rs:63-82 (output = first Output in the module list) -------- */
 SRK_API int srk_plan(srk_patch* patch);
@@ -230,7 +249,8 @@ SRK_API int srk_get_program_info(srk_patch* patch, size_t n_voices, srk_program_
  * schedule is checked on the CPU without a device (tests/test_program.py). */
 typedef struct srk_instr_info {
   uint8_t op;      /* 0 end, 1 ring load, 2 ring store, 3 oscillator, 4 noise, 5 moog, 6 adsr, 7 vca,
-                      8 mixer, 9 math, 10 output (stems), 11 mix, 12 moog coefficients */
+                      8 mixer, 9 math, 10 output (stems), 11 mix, 12 moog coefficients,
+                      13 grid sequencer, 14 pattern sequencer (three output ports per instruction) */
   uint8_t flags;   /* math: operation; oscillator: (copies << 4) | copy index when time-split */
   uint8_t warp;    /* warp of the 32-voice group that executes it */
   uint8_t stage;   /* works on chunk (iteration - stage) */

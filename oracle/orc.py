@@ -15,7 +15,7 @@ _SO = os.path.join(_HERE, "_build", "libsrack_oracle.so")
 
 # numeric ids, equal to include/srack_b200.h (tests/test_abi.py checks that)
 KIND = dict(OUTPUT=0, OSCILLATOR=1, NOISE=2, ADSR=3, VCA=4, MOOG_FILTER=5, MONO_MIXER=6,
-            ADD=7, SUBTRACT=8, MULTIPLY=9, NON_LINEAR=10)
+            ADD=7, SUBTRACT=8, MULTIPLY=9, NON_LINEAR=10, GRID_SEQUENCER=11, PATTERN_SEQUENCER=12)
 
 
 def build(force=False):
@@ -46,6 +46,7 @@ def lib():
         L.orc_set_param.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float]
         L.orc_set_param_per_voice.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
         L.orc_set_module_order.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_set_sequence.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
         L.orc_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_reset.argtypes = [C.c_void_p]
         L.orc_render.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
@@ -110,6 +111,13 @@ class OraclePatch:
         rc = lib().orc_set_param_per_voice(self._h, module, pid, v.ctypes.data, v.size)
         if rc:
             raise ValueError(f"set_param_per_voice failed rc={rc}")
+
+    def set_sequence(self, module, cells):
+        """Grid sequencer: cells[n_steps]; pattern sequencer: cells[8][n_steps] (int32, see srack_b200.h)."""
+        c = np.ascontiguousarray(cells, dtype=np.int32)
+        rc = lib().orc_set_sequence(self._h, module, c.ctypes.data, c.shape[-1])
+        if rc:
+            raise ValueError(f"set_sequence failed rc={rc}")
 
     def set_module_order(self, order):
         o = np.ascontiguousarray(order, dtype=np.int32)

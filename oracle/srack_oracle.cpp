@@ -51,7 +51,7 @@ namespace {
 // ---- kinds / params: numeric ids deliberately equal to include/srack_b200.h
 enum Kind {
   K_OUTPUT = 0, K_OSC = 1, K_NOISE = 2, K_ADSR = 3, K_VCA = 4, K_MOOG = 5,
-  K_MIXER = 6, K_ADD = 7, K_SUB = 8, K_MUL = 9, K_NONLIN = 10, K_COUNT
+  K_MIXER = 6, K_ADD = 7, K_SUB = 8, K_MUL = 9, K_NONLIN = 10, K_GRIDSEQ = 11, K_PATSEQ = 12, K_COUNT
 };
 
 // src/synth.rs:20-25
@@ -375,6 +375,78 @@ struct Math : Module {
   }
 };
 
+// ---- src/synth/sequencer.rs:12-61 (struct, defaults), :190-246 (calc).
+// Inputs 0 = Step (clock), 1 = Sync; outputs 0 = CV, 1 = Gate, 2 = Sync (:262-307).
+// A cell is Option<(u16 val, bool hold)>; here -1 = None, else val | hold << 16.
+struct GridSequencer : Module {
+  std::vector<int32_t> sequence = std::vector<int32_t>(64, -1);  // vec![None; 64] (:40)
+  uint16_t steps_per_octave = 12;                                  // (:44)
+  uint16_t current_step = 0;
+  TransitionDetector det, sync_det;
+  float last = 0.0f;
+  GridSequencer(const AudioConfig& c) : Module(K_GRIDSEQ, 2, 3, c.buffer_size) {}
+  void reset() override {
+    current_step = 0; det = TransitionDetector(); sync_det = TransitionDetector(); last = 0.0f;
+    for (auto& o : outs) std::fill(o.begin(), o.end(), 0.0f);
+  }
+  bool set_param(int pid, float v) override { if (pid == 0) { steps_per_octave = (uint16_t)v; return true; } return false; }
+  void calc() override {
+    const float* step_buf = resolve(0);
+    const float* sync_buf = resolve(1);
+    float* cv_out = outs[0].data(); float* gate_out = outs[1].data(); float* sync_out = outs[2].data();
+    for (size_t idx = 0; idx < outs[0].size(); ++idx) {
+      const float step_in = step_buf ? step_buf[idx] : 0.0f;
+      const float sync_in = sync_buf ? sync_buf[idx] : 0.0f;
+      if (det.is_transition(step_in)) current_step += 1;
+      if (sync_det.is_transition(sync_in)) current_step = 0;
+      size_t cur = current_step;
+      if (cur >= sequence.size()) { current_step = 0; cur = 0; }
+      const int32_t cell = sequence[cur];
+      if (cell >= 0) {
+        cv_out[idx] = (float)(uint16_t)(cell & 0xFFFF) * (1.0f / (float)steps_per_octave);
+        gate_out[idx] = (cell >> 16) & 1 ? 1.0f : step_in;
+      } else {
+        cv_out[idx] = last;
+        gate_out[idx] = 0.0f;
+      }
+      sync_out[idx] = cur == 0 ? 1.0f : 0.0f;
+      last = cv_out[idx];
+    }
+  }
+};
+
+// ---- src/synth/sequencer.rs:336-366 (struct, defaults), :482-533 (calc).
+// Inputs 0 = Step, 1 = Sync; outputs 0..7 = gate rows, 8 = Sync (:577-596).
+// A cell is Option<bool>; here -1 = None, 0 = Some(false), 1 = Some(true); rows x steps.
+struct PatternSequencer : Module {
+  std::vector<std::vector<int32_t>> sequence = std::vector<std::vector<int32_t>>(8, std::vector<int32_t>(64, -1));
+  uint16_t current_step = 0;
+  TransitionDetector det, sync_det;
+  PatternSequencer(const AudioConfig& c) : Module(K_PATSEQ, 2, 9, c.buffer_size) {}
+  void reset() override {
+    current_step = 0; det = TransitionDetector(); sync_det = TransitionDetector();
+    for (auto& o : outs) std::fill(o.begin(), o.end(), 0.0f);
+  }
+  bool set_param(int, float) override { return false; }
+  void calc() override {
+    const float* step_buf = resolve(0);
+    const float* sync_buf = resolve(1);
+    for (size_t idx = 0; idx < outs[0].size(); ++idx) {
+      const float step_in = step_buf ? step_buf[idx] : 0.0f;
+      const float sync_in = sync_buf ? sync_buf[idx] : 0.0f;
+      if (det.is_transition(step_in)) current_step += 1;
+      if (sync_det.is_transition(sync_in)) current_step = 0;
+      size_t cur = current_step;
+      if (cur >= sequence[0].size()) { current_step = 0; cur = 0; }
+      for (size_t row = 0; row < 8; ++row) {
+        const int32_t cell = sequence[row][cur];
+        outs[row][idx] = cell < 0 ? 0.0f : (cell ? 1.0f : step_in);
+      }
+      outs[8][idx] = cur == 0 ? 1.0f : 0.0f;
+    }
+  }
+};
+
 // ---- src/synth/output.rs:46-60.  `bufs` are kept as outs[] so they can be read.
 struct Output : Module {
   Output(const AudioConfig& c) : Module(K_OUTPUT, c.channels, c.channels, c.buffer_size) {}
@@ -394,6 +466,8 @@ int kind_num_outputs(int kind) {
     case K_OUTPUT: return 0;  // get_num_outputs() == 0 (output.rs:62)
     case K_OSC: return 3;
     case K_MOOG: return 3;
+    case K_GRIDSEQ: return 3;
+    case K_PATSEQ: return 9;
     default: return 1;
   }
 }
@@ -408,6 +482,8 @@ std::unique_ptr<Module> make_module(int kind, const AudioConfig& cfg) {
     case K_MOOG: return std::make_unique<MoogFilter>(cfg);
     case K_MIXER: return std::make_unique<MonoMixer>(cfg);
     case K_ADD: case K_SUB: case K_MUL: case K_NONLIN: return std::make_unique<Math>(cfg, kind);
+    case K_GRIDSEQ: return std::make_unique<GridSequencer>(cfg);
+    case K_PATSEQ: return std::make_unique<PatternSequencer>(cfg);
   }
   return nullptr;
 }
@@ -510,6 +586,7 @@ struct Patch {
   std::vector<int> kinds;
   std::vector<std::vector<std::optional<std::pair<int, int>>>> wiring;  // [module][input] -> (src, port)
   std::vector<ParamSetting> params;  // applied in order
+  std::unordered_map<int, std::vector<int32_t>> sequences;  // module -> cells (rows x steps for the pattern sequencer)
   std::vector<int> order;            // all_modules order (module indices); empty = creation order
   // voice bank
   std::vector<Instance> voices;
@@ -520,6 +597,7 @@ struct Patch {
     switch (kinds[m]) {
       case K_OUTPUT: return cfg.channels;
       case K_OSC: case K_VCA: case K_MOOG: case K_ADD: case K_SUB: case K_MUL: case K_NONLIN: return 2;
+      case K_GRIDSEQ: case K_PATSEQ: return 2;
       case K_NOISE: return 0;
       case K_ADSR: return 1;
       case K_MIXER: return 4;
@@ -560,6 +638,17 @@ struct Patch {
     for (const auto& p : params) {
       float v = p.per_voice ? p.values[voice] : p.value;
       inst.modules[p.module]->set_param(p.pid, v);
+    }
+    for (const auto& kv : sequences) {
+      Module* m = inst.modules[kv.first].get();
+      if (m->kind == K_GRIDSEQ) {
+        static_cast<GridSequencer*>(m)->sequence = kv.second;
+      } else if (m->kind == K_PATSEQ) {
+        auto* ps = static_cast<PatternSequencer*>(m);
+        const size_t steps = kv.second.size() / 8;
+        for (size_t row = 0; row < 8; ++row)
+          ps->sequence[row].assign(kv.second.begin() + row * steps, kv.second.begin() + (row + 1) * steps);
+      }
     }
   }
 };
@@ -638,6 +727,21 @@ int orc_set_param_per_voice(void* h, int module, int pid, const float* values, s
   p->params.push_back(ParamSetting{module, pid, true, 0.0f, std::vector<float>(values, values + n)});
   for (size_t v = 0; v < p->voices.size(); ++v)
     if (p->bank_offset + v < n) p->voices[v].modules[module]->set_param(pid, values[p->bank_offset + v]);
+  return 0;
+}
+
+// The sequence table a sequencer's ui() edits (sequencer.rs:98-188, :388-470): n_steps cells for the
+// grid sequencer, 8 x n_steps (row major) for the pattern sequencer; 1 <= n_steps <= 64.
+int orc_set_sequence(void* h, int module, const int32_t* cells, size_t n_steps) {
+  auto* p = static_cast<Patch*>(h);
+  if (module < 0 || module >= (int)p->kinds.size()) return 1;
+  const int kind = p->kinds[module];
+  if (kind != K_GRIDSEQ && kind != K_PATSEQ) return 2;
+  if (n_steps < 1 || n_steps > 64) return 3;
+  const size_t n = kind == K_GRIDSEQ ? n_steps : 8 * n_steps;
+  p->sequences[module] = std::vector<int32_t>(cells, cells + n);
+  // like the reference's ui(): the table changes under the running module, state is kept
+  for (size_t v = 0; v < p->voices.size(); ++v) p->apply_params(p->voices[v], p->bank_offset + v);
   return 0;
 }
 

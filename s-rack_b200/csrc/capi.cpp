@@ -14,7 +14,7 @@ namespace {
 struct CatalogEntry { const char* name; int kind; };
 const CatalogEntry kCatalog[] = {
     {"Oscillator", SRK_KIND_OSCILLATOR}, {"Noise", SRK_KIND_NOISE},
-    {"Grid Sequencer", -1},              {"Pattern Sequencer", -1},
+    {"Grid Sequencer", SRK_KIND_GRID_SEQUENCER}, {"Pattern Sequencer", SRK_KIND_PATTERN_SEQUENCER},
     {"ADSR", SRK_KIND_ADSR},             {"VCA", SRK_KIND_VCA},
     {"Moog Filter", SRK_KIND_MOOG_FILTER}, {"Mono Mixer", SRK_KIND_MONO_MIXER},
     {"Sample", -1},                      {"Add", SRK_KIND_ADD},
@@ -127,6 +127,10 @@ int srk_module_create(srk_patch* p, int kind, srk_module** out) {
   for (int i = 0; i < ki.n_params; ++i) m->param[i] = ki.param_default[i];
   m->osc_sample_rate = p->cfg.sample_rate;
   m->adsr_sample_rate = (float)p->cfg.sample_rate;
+  if (kind == SRK_KIND_GRID_SEQUENCER || kind == SRK_KIND_PATTERN_SEQUENCER) {  // vec![None; 64] (sequencer.rs:40,360)
+    m->seq_steps = SRK_SEQ_MAX_STEPS;
+    m->sequence.assign((kind == SRK_KIND_PATTERN_SEQUENCER ? SRK_PATTERN_ROWS : 1) * m->seq_steps, SRK_SEQ_NONE);
+  }
   *out = m.get();
   p->modules.push_back(m.get());
   p->owned.push_back(std::move(m));
@@ -239,6 +243,31 @@ int srk_set_param_f32_per_voice(srk_module* m, int pid, const float* values, siz
   if (ki.param_uniform_only[pid]) return fail(m->patch, SRK_ERR_PARAM, "parameter is uniform-only");
   m->param_pv[pid].assign(values, values + n);
   ++m->patch->param_epoch;
+  return SRK_OK;
+}
+
+int srk_set_sequence(srk_module* m, const int32_t* cells, size_t n_steps) {
+  if (!m || !cells) return SRK_ERR_ARG;
+  const bool grid = m->kind == SRK_KIND_GRID_SEQUENCER, pattern = m->kind == SRK_KIND_PATTERN_SEQUENCER;
+  if (!grid && !pattern) return fail(m->patch, SRK_ERR_KIND, "module has no sequence table");
+  if (n_steps < 1 || n_steps > SRK_SEQ_MAX_STEPS) return fail(m->patch, SRK_ERR_ARG, "sequence length must be 1..64");
+  const size_t n = (pattern ? SRK_PATTERN_ROWS : 1) * n_steps;
+  for (size_t i = 0; i < n; ++i) {
+    const int32_t c = cells[i];
+    const bool ok = c == SRK_SEQ_NONE || (grid ? (c >= 0 && c <= 0x1FFFF) : (c == 0 || c == 1));
+    if (!ok) return fail(m->patch, SRK_ERR_ARG, "bad sequence cell");
+  }
+  m->sequence.assign(cells, cells + n);
+  m->seq_steps = n_steps;
+  ++m->patch->table_epoch;
+  return SRK_OK;
+}
+
+int srk_get_sequence(const srk_module* m, int32_t* cells, size_t cap, size_t* n_steps) {
+  if (!m) return SRK_ERR_ARG;
+  if (m->kind != SRK_KIND_GRID_SEQUENCER && m->kind != SRK_KIND_PATTERN_SEQUENCER) return SRK_ERR_KIND;
+  if (n_steps) *n_steps = m->seq_steps;
+  for (size_t i = 0; cells && i < cap && i < m->sequence.size(); ++i) cells[i] = m->sequence[i];
   return SRK_OK;
 }
 

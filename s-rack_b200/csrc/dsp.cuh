@@ -98,6 +98,7 @@ struct Lane {
   uint32_t chunk;      // chunk the current instruction works on
   uint32_t voice;      // global voice index (noise key)
   uint32_t seed_lo, seed_hi;
+  const int32_t* tables;  // sequencer step tables (shared memory, uniform over voices)
 };
 
 __device__ __forceinline__ float* wire(const Lane& ln, int slot) {
@@ -922,6 +923,121 @@ struct MathOp {
       case F_MATH_SUB: run_t<F_MATH_SUB>(ins, ln, kk); break;
       case F_MATH_MUL: run_t<F_MATH_MUL>(ins, ln, kk); break;
       default: run_t<F_MATH_NONLIN>(ins, ln, kk); break;
+    }
+  }
+};
+
+// ---- GridSequencerModule::calc, src/synth/sequencer.rs:190-246 --------------------------
+// Inputs step (clock), sync; outputs cv, gate, sync.  The step table (Option<(u16, bool)> per
+// step: -1 = None, else val | hold << 16) is the same for every voice and sits in shared memory;
+// each voice has its own step counter, detectors and held CV.
+struct GridSeqOp {
+  uint32_t* s;
+  uint32_t step;
+  bool last_step, last_sync;
+  float last_cv, inv_steps;
+  const int32_t* table;
+  uint32_t n_steps;
+  Port p_step, p_sync, p_cv, p_gate, p_syncout;
+
+  __device__ __forceinline__ void load(const Instr& ins, const Lane& ln) {
+    s = ln.st + ins.state * L;
+    step = s[0] & 0xFFFFu;
+    last_step = (s[0] >> 16) & 1u;
+    last_sync = (s[0] >> 17) & 1u;
+    last_cv = __uint_as_float(s[L]);
+    inv_steps = ins.imm;
+    table = ln.tables + ins.aux;
+    n_steps = ins.n_ch;
+    p_step = port(ln, ins.in[0]); p_sync = port(ln, ins.in[1]);
+    p_cv = port(ln, ins.out[0]); p_gate = port(ln, ins.out[1]); p_syncout = port(ln, ins.out[2]);
+  }
+  __device__ __forceinline__ void store() {
+    s[0] = step | (last_step ? 1u << 16 : 0u) | (last_sync ? 1u << 17 : 0u);
+    s[L] = __float_as_uint(last_cv);
+  }
+  __device__ __forceinline__ void run(const Instr&, const Lane& ln, int kk) {
+    const float* step_in = p_step.at(ln);
+    const float* sync_in = p_sync.at(ln);
+    float* cv = p_cv.at(ln);
+    float* gate = p_gate.at(ln);
+    float* sync_out = p_syncout.at(ln);
+#pragma unroll 2
+    for (int k = 0; k < kk; ++k) {
+      const float st = step_in ? step_in[k * L] : 0.0f;
+      const float sy = sync_in ? sync_in[k * L] : 0.0f;
+      const bool a_step = st > 0.0f, a_sync = sy > 0.0f;
+      step += (a_step & !last_step) ? 1u : 0u;     // :220-223
+      step = (a_sync & !last_sync) ? 0u : step;    // :224-226
+      last_step = a_step;
+      last_sync = a_sync;
+      step = step >= n_steps ? 0u : step;          // :227-230
+      const int32_t cell = table[step];
+      const bool some = cell >= 0;
+      const float c = some ? fmul((float)(cell & 0xFFFF), inv_steps) : last_cv;  // :231-239
+      const float g = some ? ((cell >> 16) & 1 ? 1.0f : st) : 0.0f;
+      last_cv = c;
+      if (cv) cv[k * L] = c;
+      if (gate) gate[k * L] = g;
+      if (sync_out) sync_out[k * L] = step == 0u ? 1.0f : 0.0f;
+    }
+  }
+};
+
+// ---- PatternSequencerModule::calc, src/synth/sequencer.rs:482-533 -----------------------
+// 8 gate rows + sync = 9 output ports; one instruction covers ports first..first+2
+// (ins.flags = first) and keeps its own copy of the step counter.  Table: rows x steps,
+// -1 = None, 0 = Some(false) (pass the clock), 1 = Some(true) (hold).
+struct PatSeqOp {
+  uint32_t* s;
+  uint32_t step;
+  bool last_step, last_sync;
+  const int32_t* table;
+  uint32_t n_steps, first;
+  Port p_step, p_sync, p_out[3];
+
+  __device__ __forceinline__ void load(const Instr& ins, const Lane& ln) {
+    s = ln.st + ins.state * L;
+    step = s[0] & 0xFFFFu;
+    last_step = (s[0] >> 16) & 1u;
+    last_sync = (s[0] >> 17) & 1u;
+    table = ln.tables + ins.aux;
+    n_steps = ins.n_ch;
+    first = ins.flags;
+    p_step = port(ln, ins.in[0]); p_sync = port(ln, ins.in[1]);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) p_out[j] = port(ln, ins.out[j]);
+  }
+  __device__ __forceinline__ void store() {
+    s[0] = step | (last_step ? 1u << 16 : 0u) | (last_sync ? 1u << 17 : 0u);
+  }
+  __device__ __forceinline__ void run(const Instr&, const Lane& ln, int kk) {
+    const float* step_in = p_step.at(ln);
+    const float* sync_in = p_sync.at(ln);
+    float* out[3] = {p_out[0].at(ln), p_out[1].at(ln), p_out[2].at(ln)};
+#pragma unroll 2
+    for (int k = 0; k < kk; ++k) {
+      const float st = step_in ? step_in[k * L] : 0.0f;
+      const float sy = sync_in ? sync_in[k * L] : 0.0f;
+      const bool a_step = st > 0.0f, a_sync = sy > 0.0f;
+      step += (a_step & !last_step) ? 1u : 0u;
+      step = (a_sync & !last_sync) ? 0u : step;
+      last_step = a_step;
+      last_sync = a_sync;
+      step = step >= n_steps ? 0u : step;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        if (!out[j]) continue;
+        const uint32_t portno = first + j;
+        float v;
+        if (portno == 8u) {
+          v = step == 0u ? 1.0f : 0.0f;              // sync_out (:526)
+        } else {
+          const int32_t cell = table[portno * n_steps + step];
+          v = cell < 0 ? 0.0f : (cell ? 1.0f : st);  // :515-524
+        }
+        out[j][k * L] = v;
+      }
     }
   }
 };

@@ -32,13 +32,14 @@
 namespace srk {
 
 struct RenderArgs {
-  const uint4* blob;      // [Instr x n_instr][WireDesc x n_wires][u16 warp_begin x (n_warps + 1)]
+  const uint4* blob;      // [Instr x n_instr][WireDesc x n_wires][u16 warp_begin x (n_warps + 1)][pad][i32 tables]
   uint32_t* state;
   const uint32_t* params;
   float* rings;
   float* stems;
   float* partial;
   uint32_t blob_vec;      // blob size in uint4
+  uint32_t table_off;     // byte offset of the sequencer tables inside the blob
   uint32_t n_instr, n_wires, n_warps, n_stages, n_tiles;
   uint32_t V;             // voices rendered by this launch
   uint32_t voice_offset;  // global index of voice 0 (noise key)
@@ -228,7 +229,8 @@ __global__ void __launch_bounds__(SOLO ? 32 : kMaxThreads, 1) render_voices_kern
   for (uint32_t w = wid; w < a.P; w += a.n_warps) pr[w * 32 + lane] = a.params[(size_t)w * a.V + v];
   __syncthreads();
 
-  dsp::Lane ln{st + lane, pr + lane, tiles + lane, wd, a.K * 32, 0, a.voice_offset + v, a.seed_lo, a.seed_hi};
+  dsp::Lane ln{st + lane, pr + lane, tiles + lane, wd, a.K * 32, 0, a.voice_offset + v, a.seed_lo, a.seed_hi,
+               reinterpret_cast<const int32_t*>(smem_raw + a.table_off)};
   const uint32_t pc0 = warp_begin[wid], pc1 = warp_begin[wid + 1];
   const uint32_t K = a.K;
   const uint32_t n_chunks = (a.n_samples + K - 1) / K;
@@ -247,6 +249,8 @@ __global__ void __launch_bounds__(SOLO ? 32 : kMaxThreads, 1) render_voices_kern
       }
       case OP_MOOG: run_resident<dsp::MoogOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_MOOG_COEF: run_resident<dsp::MoogCoefOp>(ins, ln, a, n_chunks, n_iter); break;
+      case OP_GRIDSEQ: run_resident<dsp::GridSeqOp>(ins, ln, a, n_chunks, n_iter); break;
+      case OP_PATSEQ: run_resident<dsp::PatSeqOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_ADSR: run_resident<dsp::AdsrOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_NOISE: run_resident<dsp::NoiseOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_VCA: run_resident<dsp::VcaOp>(ins, ln, a, n_chunks, n_iter); break;
@@ -270,6 +274,8 @@ __global__ void __launch_bounds__(SOLO ? 32 : kMaxThreads, 1) render_voices_kern
           case OP_OSC: run_once<dsp::OscOp>(ins, ln, kk); break;
           case OP_MOOG: run_once<dsp::MoogOp>(ins, ln, kk); break;
           case OP_MOOG_COEF: run_once<dsp::MoogCoefOp>(ins, ln, kk); break;
+          case OP_GRIDSEQ: run_once<dsp::GridSeqOp>(ins, ln, kk); break;
+          case OP_PATSEQ: run_once<dsp::PatSeqOp>(ins, ln, kk); break;
           case OP_ADSR: run_once<dsp::AdsrOp>(ins, ln, kk); break;
           case OP_NOISE: run_once<dsp::NoiseOp>(ins, ln, kk); break;
           case OP_VCA: run_once<dsp::VcaOp>(ins, ln, kk); break;
@@ -345,7 +351,7 @@ struct Engine {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // call start, kernel start, kernel end, call end
   bool timed = false;
   Program prog;
-  uint64_t compiled_epoch = 0, uploaded_param_epoch = 0;
+  uint64_t compiled_epoch = 0, uploaded_param_epoch = 0, compiled_table_epoch = 0;
   int compiled_max_warps = 0;       // schedule the program was compiled for
   int chunk = 0;                    // samples per chunk (K) for the compiled program
   std::vector<uint4> blob;          // device image of the program (see RenderArgs::blob)
@@ -408,9 +414,14 @@ static int engine_open(srk_patch* patch) {
 }
 
 // Device image of a compiled program: instructions, wire table, per-warp ranges.
+static size_t blob_table_offset(const Program& prog) {
+  const size_t head = prog.code.size() * sizeof(Instr) + prog.wires.size() * sizeof(WireDesc) +
+                      prog.warp_begin.size() * sizeof(uint16_t);
+  return (head + 3) / 4 * 4;
+}
+
 static void build_blob(const Program& prog, std::vector<uint4>& blob) {
-  const size_t bytes = prog.code.size() * sizeof(Instr) + prog.wires.size() * sizeof(WireDesc) +
-                       prog.warp_begin.size() * sizeof(uint16_t);
+  const size_t bytes = blob_table_offset(prog) + prog.tables.size() * sizeof(int32_t);
   blob.assign((bytes + 15) / 16, uint4{0, 0, 0, 0});
   unsigned char* p = reinterpret_cast<unsigned char*>(blob.data());
   std::memcpy(p, prog.code.data(), prog.code.size() * sizeof(Instr));
@@ -418,6 +429,9 @@ static void build_blob(const Program& prog, std::vector<uint4>& blob) {
   if (!prog.wires.empty()) std::memcpy(p, prog.wires.data(), prog.wires.size() * sizeof(WireDesc));
   p += prog.wires.size() * sizeof(WireDesc);
   std::memcpy(p, prog.warp_begin.data(), prog.warp_begin.size() * sizeof(uint16_t));
+  if (!prog.tables.empty())
+    std::memcpy(reinterpret_cast<unsigned char*>(blob.data()) + blob_table_offset(prog), prog.tables.data(),
+                prog.tables.size() * sizeof(int32_t));
 }
 
 // How many warps may share one 32-voice group for V voices: with few groups per SM the
@@ -546,7 +560,10 @@ static int engine_prepare(srk_patch* patch, size_t n_voices, size_t voice_offset
   Engine& e = *patch->engine;
   bool fresh = false;
   const int want_warps = choose_max_warps(e, n_voices);
-  if (e.compiled_epoch != patch->wiring_epoch || e.compiled_max_warps != want_warps) {
+  const bool rewired = e.compiled_epoch != patch->wiring_epoch || e.compiled_max_warps != want_warps;
+  if (rewired || e.compiled_table_epoch != patch->table_epoch) {
+    // (a sequence-table edit alone rebuilds the program image but keeps the voice state: the state
+    // layout depends on the wiring only)
     std::string err;
     int rc = compile_program(*patch, want_warps, e.prog, err);
     if (rc != SRK_OK) { patch->last_error = err; return rc; }
@@ -569,7 +586,8 @@ static int engine_prepare(srk_patch* patch, size_t n_voices, size_t voice_offset
     SRK_CUDA(cudaStreamSynchronize(e.stream));
     e.compiled_epoch = patch->wiring_epoch;
     e.compiled_max_warps = want_warps;
-    fresh = true;
+    e.compiled_table_epoch = patch->table_epoch;
+    fresh = rewired;
   }
   if (fresh || e.V != n_voices || e.voice_offset != voice_offset || !e.state_valid) {
     e.V = n_voices;
@@ -639,6 +657,7 @@ int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t
   a.stems = d_stems;
   a.partial = mix ? (float*)e.d_partial.p : nullptr;
   a.blob_vec = (uint32_t)e.blob.size();
+  a.table_off = (uint32_t)blob_table_offset(prog);
   a.n_instr = (uint32_t)prog.code.size();
   a.n_wires = (uint32_t)prog.wires.size();
   a.n_warps = prog.n_warps;

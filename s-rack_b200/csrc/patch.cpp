@@ -29,6 +29,10 @@ const KindInfo kKinds[SRK_KIND_COUNT] = {
   {"Multiply",     2, 1, {"In1", "In2", nullptr, nullptr}, {nullptr, nullptr, nullptr}, 1, {0.0f, 0, 0, 0}, {false, false, false, false}},
   // Non-Linear: math.rs:266-290, constant 1.0 (:194)
   {"Non-Linear",   2, 1, {"In1", "In2", nullptr, nullptr}, {nullptr, nullptr, nullptr}, 1, {1.0f, 0, 0, 0}, {false, false, false, false}},
+  // Grid sequencer: sequencer.rs:262-307 (labels), steps_per_octave 12 (:44)
+  {"Grid Sequencer", 2, 3, {"Step", "Sync", nullptr, nullptr}, {"CV", "Gate", "Sync"}, 1, {12.0f, 0, 0, 0}, {true, false, false, false}},
+  // Pattern sequencer: sequencer.rs:551-596: 8 gate rows labelled "0".."7", then "Sync"
+  {"Pattern Sequencer", 2, 9, {"Step", "Sync", nullptr, nullptr}, {"0", "1", "2", "3", "4", "5", "6", "7", "Sync"}, 0, {0, 0, 0, 0}, {false, false, false, false}},
 };
 // clang-format on
 }  // namespace

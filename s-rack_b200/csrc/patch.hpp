@@ -22,7 +22,7 @@ struct KindInfo {
   int n_inputs;   // -1: `channels` (Output)
   int n_outputs;
   const char* in_labels[4];   // nullptr = the reference's Ok(None)
-  const char* out_labels[3];
+  const char* out_labels[9];
   int n_params;
   float param_default[kMaxParams];
   bool param_uniform_only[kMaxParams];
@@ -42,6 +42,9 @@ struct srk_module {
   std::vector<std::pair<srk_module*, uint8_t>> inputs;
   float param[srk::kMaxParams] = {0, 0, 0, 0};
   std::vector<float> param_pv[srk::kMaxParams];  // per-voice override (global voice index) or empty
+  // Sequencers: the step table (sequencer.rs:18,341), -1 = None; rows x seq_steps for the pattern
+  std::vector<int32_t> sequence;
+  size_t seq_steps = 0;
   uint16_t osc_sample_rate = 0;  // Oscillator: follows set_audio_config (oscillator.rs:83-84)
   float adsr_sample_rate = 0;    // ADSR: fixed at construction (adsr.rs:47,69-71)
   int n_outputs() const;
@@ -59,6 +62,7 @@ struct srk_patch {
   std::vector<std::pair<srk_module*, srk_module*>> cuts;  // (reader, writer)
   uint64_t wiring_epoch = 1;  // bumped by every wiring / list change
   uint64_t param_epoch = 1;   // bumped by every parameter change
+  uint64_t table_epoch = 1;   // bumped by every sequence-table change (program image, not state)
   std::string last_error;
   std::unique_ptr<srk::Engine, void (*)(srk::Engine*)> engine{nullptr, nullptr};
 

@@ -41,6 +41,7 @@ int op_cost(const Pending& p) {
   switch (p.ins.op) {
     case OP_MOOG: return p.ins.flags & F_MOOG_EXT_COEF ? 95 : 115;
     case OP_MOOG_COEF: return 45;
+    case OP_GRIDSEQ: case OP_PATSEQ: return 20;
     case OP_OSC: {
       const int n = std::max(1, p.ins.flags >> 4);  // time-split copies share the shaping work
       return osc_phase_cost(p) + osc_shape_cost(p) / n;
@@ -155,7 +156,7 @@ int compile_program(const srk_patch& patch, int max_warps, Program& prog, std::s
     const int m = patch.index_of(mod);
     Pending p = blank();
     for (size_t i = 0; i < mod->inputs.size() && i < 4; ++i) p.in_vw[i] = in_wire[m][i];
-    for (int port = 0; port < mod->n_outputs(); ++port) {
+    for (int port = 0; port < mod->n_outputs() && port < 3; ++port) {
       auto it = port_wire.find({m, port});
       if (it != port_wire.end()) p.out_vw[port] = it->second;
     }
@@ -195,6 +196,47 @@ int compile_program(const srk_patch& patch, int max_warps, Program& prog, std::s
         p.ins.flags = (uint8_t)(mod->kind - SRK_KIND_ADD);
         p.ins.param = alloc_params(m, {SRK_MATH_CONSTANT});
         break;
+      case SRK_KIND_GRID_SEQUENCER:
+        p.ins.op = OP_GRIDSEQ;
+        p.ins.state = alloc_state(kStateGridSeq, {(1u << 16) | (1u << 17), 0u});  // step 0, both detectors last = true
+        p.ins.aux = (uint16_t)prog.tables.size();
+        p.ins.n_ch = (uint8_t)mod->seq_steps;
+        // `val as f32 * (1.0 / self.steps_per_octave as f32)` (sequencer.rs:233-234): the f32 reciprocal
+        p.ins.imm = 1.0f / (float)(uint16_t)mod->param[SRK_GRIDSEQ_STEPS_PER_OCTAVE];
+        prog.tables.insert(prog.tables.end(), mod->sequence.begin(), mod->sequence.end());
+        break;
+      case SRK_KIND_PATTERN_SEQUENCER: {
+        // 9 output ports, 3 per instruction; every instruction keeps its own copy of the step
+        // counter (identical evolution), triples nobody reads are not emitted
+        const uint16_t table = (uint16_t)prog.tables.size();
+        prog.tables.insert(prog.tables.end(), mod->sequence.begin(), mod->sequence.end());
+        for (int first = 0; first < 9; first += 3) {
+          Pending q = p;
+          bool any = false;
+          for (int k = 0; k < 3; ++k) {
+            auto it = port_wire.find({m, first + k});
+            q.out_vw[k] = it != port_wire.end() ? it->second : -1;
+            any |= q.out_vw[k] >= 0;
+          }
+          if (!any) continue;
+          q.ins.op = OP_PATSEQ;
+          q.ins.flags = (uint8_t)first;
+          q.ins.state = alloc_state(kStatePatSeq, {(1u << 16) | (1u << 17)});
+          q.ins.aux = table;
+          q.ins.n_ch = (uint8_t)mod->seq_steps;
+          code.push_back(q);
+        }
+        for (int port = 0; port < mod->n_outputs(); ++port) {
+          auto it = ring_of.find({m, port});
+          if (it == ring_of.end()) continue;
+          Pending st = blank();
+          st.ins.op = OP_RING_STORE;
+          st.ins.aux = (uint16_t)it->second;
+          st.in_vw[0] = port_wire.at({m, port});
+          code.push_back(st);
+        }
+        continue;
+      }
       case SRK_KIND_OUTPUT: {
         if (mod != output) continue;  // only the first Output's bufs are ever read (ui.rs:84-96, main.rs:66)
         for (size_t c0 = 0; c0 < mod->inputs.size(); c0 += kOutputChannelsPerInstr) {

@@ -31,6 +31,8 @@ enum Op : uint8_t {
   OP_OUTPUT,      // channels aux .. aux+3 <- in[0..3]: per-voice stems
   OP_MIX,         // channels aux .. aux+3: this voice group's share of the mixdown
   OP_MOOG_COEF,   // out[0..2] <- ladder coefficients (f, p, q) of a filter's CV input in[0]
+  OP_GRIDSEQ,     // grid sequencer: in step, sync; out cv, gate, sync; table at aux, n_ch steps
+  OP_PATSEQ,      // pattern sequencer: in step, sync; out ports flags..flags+2 of its 9; table at aux
 };
 
 // Instr::flags
@@ -51,11 +53,11 @@ struct alignas(16) Instr {
   int16_t out[3];   // wire slot per output port, -1 = nobody reads it (not materialised)
   uint16_t state;   // first per-voice state word
   uint16_t param;   // first per-voice parameter word
-  uint16_t aux;     // ring id / module index (noise key) / first channel (output)
+  uint16_t aux;     // ring id / module index (noise key) / first channel (output) / table offset (sequencers)
   uint8_t warp;     // warp of the group that executes this instruction
   uint8_t stage;    // pipeline delay in chunks
   float imm;        // oscillator / ADSR sample rate
-  uint8_t n_ch;     // OUTPUT / MIX: channels covered by this instruction (1..4)
+  uint8_t n_ch;     // OUTPUT / MIX: channels covered by this instruction (1..4); sequencers: steps (1..64)
   uint8_t pad[3];
 };
 static_assert(sizeof(Instr) == 32, "Instr must stay 32 bytes (staged to shared memory as uint4 pairs)");
@@ -71,7 +73,9 @@ struct WireDesc {
 //   NOISE : sample counter (u64, 2 words)
 //   MOOG  : f, p, q, b[0..4], freq, res                            filter.rs:48-56
 //   ADSR  : phase, r_val, from_a_val, mode | gate_last << 8        adsr.rs:14-21
-constexpr int kStateOsc = 3, kStateNoise = 2, kStateMoog = 10, kStateAdsr = 4;
+//   GRIDSEQ : current_step | step_last << 16 | sync_last << 17, last cv   sequencer.rs:24-27
+//   PATSEQ  : current_step | step_last << 16 | sync_last << 17 (one copy per instruction)
+constexpr int kStateOsc = 3, kStateNoise = 2, kStateMoog = 10, kStateAdsr = 4, kStateGridSeq = 2, kStatePatSeq = 1;
 // Per-voice parameter words (SoA [word][voice] in HBM)
 //   OSC   : val, delta (f64, 2 words; host-computed 440*2^val/sr, used when CV is None), antialiasing (0/1)
 //   MOOG  : freq, res, exp_amt        ADSR : a_sec, d_sec, s_val, r_sec
@@ -88,6 +92,7 @@ struct Program {
   std::vector<Instr> code;             // sorted by (warp, plan order), terminated by OP_END
   std::vector<uint16_t> warp_begin;    // n_warps + 1 offsets into `code`
   std::vector<WireDesc> wires;         // one per wire slot
+  std::vector<int32_t> tables;         // sequencer step tables (uniform over voices), Instr::aux indexes it
   std::vector<uint32_t> state_init;    // one initial value per state word
   std::vector<ParamSource> param_src;  // one per parameter word
   uint32_t n_tiles = 0;                // wire tiles per group

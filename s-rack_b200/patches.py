@@ -12,6 +12,7 @@ import math
 import numpy as np
 
 from ._ffi import PARAM as P
+from ._ffi import SEQ_NONE, grid_cell
 
 SEED = 0x5EED5EED
 SAMPLE_RATE = 48000
@@ -204,6 +205,59 @@ def cfg5_gated_sine(b, n_voices, seed=SEED):
     b.connect(out, 0, vca, 0)
     b.connect(out, 1, vca, 0)
     return dict(lfo=lfo, adsr=adsr, osc=osc, vca=vca, out=out)
+
+
+def sequenced(b, n_voices, seed=SEED):
+    """the reference's own way of playing a patch.  A per-voice clock steps a Grid
+    Sequencer (melody -> oscillator CV, gate -> ADSR) and a Pattern Sequencer (row 0 holds a gate for
+    a noise burst through a second VCA, row 3 passes the clock through); the grid's sync output
+    hard-syncs the oscillator at the top of the sequence."""
+    clock = b.module_create("OSCILLATOR")
+    grid = b.module_create("GRID_SEQUENCER")
+    pat = b.module_create("PATTERN_SEQUENCER")
+    osc = b.module_create("OSCILLATOR")
+    adsr = b.module_create("ADSR")
+    filt = b.module_create("MOOG_FILTER")
+    vca = b.module_create("VCA")
+    nz = b.module_create("NOISE")
+    adsr2 = b.module_create("ADSR")
+    vca2 = b.module_create("VCA")
+    mix = b.module_create("MONO_MIXER")
+    out = b.module_create("OUTPUT")
+    b.set_seed(seed)
+    tempo = 24.0 + 16.0 * uniform01(seed, 5, n_voices)  # steps per second
+    b.set_param_per_voice(clock, P["OSC_VAL"], np.log2(tempo / 440.0).astype(np.float32))
+    melody = [0, 3, 7, 12, SEQ_NONE, 10, 7, 3, 0, SEQ_NONE, 5, 8, 12, 15, 12, SEQ_NONE]
+    cells = [SEQ_NONE if v == SEQ_NONE else grid_cell(v, hold=(i % 3 != 1)) for i, v in enumerate(melody)]
+    b.set_sequence(grid, np.array(cells, dtype=np.int32))
+    rows = np.full((8, 16), SEQ_NONE, dtype=np.int32)
+    rows[0, ::4] = 1          # held gate on every fourth step
+    rows[3, 1::2] = 0         # clock passed through on odd steps
+    b.set_sequence(pat, rows)
+    b.set_param(osc, P["OSC_VAL"], -1.0)
+    for a, vals in ((adsr, (0.002, 0.02, 0.6, 0.01)), (adsr2, (0.0, 0.008, 0.0, 0.004))):
+        for pid, v in zip(("ADSR_A_SEC", "ADSR_D_SEC", "ADSR_S_VAL", "ADSR_R_SEC"), vals):
+            b.set_param(a, P[pid], v)
+    b.connect(grid, 0, clock, SQUARE)
+    b.connect(pat, 0, clock, SQUARE)
+    b.connect(osc, 0, grid, 0)        # CV (V/oct)
+    b.connect(osc, 1, grid, 2)        # sync at step 0
+    b.connect(adsr, 0, grid, 1)       # gate
+    b.connect(filt, 0, osc, SAW)
+    b.connect(filt, 1, adsr, 0)
+    b.connect(vca, 0, filt, LOWPASS)
+    b.connect(vca, 1, adsr, 0)
+    b.connect(adsr2, 0, pat, 0)
+    b.connect(vca2, 0, nz, 0)
+    b.connect(vca2, 1, adsr2, 0)
+    b.connect(mix, 0, vca, 0)
+    b.connect(mix, 1, vca2, 0)
+    b.connect(mix, 2, pat, 3)
+    b.set_param(mix, P["MIXER_GAIN2"], 0.05)
+    b.connect(out, 0, mix, 0)
+    b.connect(out, 1, pat, 8)          # the pattern sequencer's sync output
+    return dict(clock=clock, grid=grid, pat=pat, osc=osc, adsr=adsr, filt=filt, vca=vca, noise=nz, adsr2=adsr2,
+                vca2=vca2, mix=mix, out=out)
 
 
 # name -> (builder, BASELINE voice count, description)

@@ -120,6 +120,23 @@ class SynthModule:
         self._patch.per_voice[(self, _pid(param))] = a  # host copy, e.g. to re-send or re-shard
 
 
+    def set_sequence(self, cells):
+        """The step table a sequencer's ui() edits (sequencer.rs:98-188, :388-470): int32 cells,
+        [n_steps] for the grid sequencer (SEQ_NONE or grid_cell(val, hold)), [8][n_steps] for the
+        pattern sequencer (SEQ_NONE, 0 = pass the clock, 1 = hold)."""
+        a = np.ascontiguousarray(cells, dtype=np.int32)
+        self._check(lib.srk_set_sequence(self._h, a.ctypes.data_as(C.POINTER(C.c_int32)), a.shape[-1]))
+
+    def get_sequence(self):
+        n = C.c_size_t()
+        self._check(lib.srk_get_sequence(self._h, None, 0, C.byref(n)))
+        rows = 8 if self.get_kind() == "PATTERN_SEQUENCER" else 1
+        buf = (C.c_int32 * (rows * n.value))()
+        self._check(lib.srk_get_sequence(self._h, buf, rows * n.value, C.byref(n)))
+        a = np.array(buf, dtype=np.int32)
+        return a.reshape(rows, n.value) if rows > 1 else a
+
+
 def _pid(param):
     return PARAM[param] if isinstance(param, str) else int(param)
 
@@ -219,6 +236,9 @@ class Patch:
 
     def set_param_per_voice(self, module, pid, values):
         module.set_param_per_voice(pid, values)
+
+    def set_sequence(self, module, cells):
+        module.set_sequence(cells)
 
     # -- planning ------------------------------------------------------------
     def plan(self):

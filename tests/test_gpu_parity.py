@@ -212,14 +212,25 @@ def test_random_patches(srk, orc, cuda_device, seed):
     N = 64 * max(1, 1024 // 64) if B > 64 else 640 // B * B
     n_par = dict(OSCILLATOR=1, ADSR=4, MOOG_FILTER=3, MONO_MIXER=4, ADD=1, SUBTRACT=1, MULTIPLY=1, NON_LINEAR=1)
     ranges = dict(OSCILLATOR=(-3, 3), ADSR=(0.0, 0.01), MOOG_FILTER=(0.05, 0.9), MONO_MIXER=(0, 1), ADD=(-1, 1),
-                  SUBTRACT=(-1, 1), MULTIPLY=(-1, 1), NON_LINEAR=(0.5, 2.0))
+                  SUBTRACT=(-1, 1), MULTIPLY=(-1, 1), NON_LINEAR=(0.5, 2.0))  # (sequencers: tables below)
     pvals = {(m, pid): (rng.random() < 0.5, srk.patches._u(seed, 17 * m + pid, V, *ranges[k]))
              for m, k in enumerate(kinds) if k in n_par for pid in range(n_par[k])}
+
+    tables = {}
+    for m, k in enumerate(kinds):  # sequencers get a random table (and the grid a random scale)
+        steps = rng.choice([1, 3, 16, 64])
+        if k == "GRID_SEQUENCER":
+            tables[m] = np.array([-1 if rng.random() < 0.3 else srk.grid_cell(rng.randrange(24), rng.random() < 0.5)
+                                  for _ in range(steps)], dtype=np.int32)
+        elif k == "PATTERN_SEQUENCER":
+            tables[m] = np.array([[rng.choice([-1, 0, 1]) for _ in range(steps)] for _ in range(8)], dtype=np.int32)
 
     def build(b, n_voices, seed=0):
         mods = [b.module_create(k) for k in kinds]
         for sink, i, src, port in wires:
             b.connect(mods[sink], i, mods[src], port)
+        for m, cells in tables.items():
+            b.set_sequence(mods[m], cells)
         for (m, pid), (per_voice, vals) in pvals.items():
             if per_voice:
                 b.set_param_per_voice(mods[m], pid, vals)
@@ -373,7 +384,41 @@ def test_baseline_size_cfg3_sampled_parity(srk, orc, cuda_device):
     assert s["bit_identical"] > 0.99
 
 
-@pytest.mark.parametrize("name,B", [("cfg2", 1024), ("cfg4", 1024), ("cfg3b", 256), ("cfg5_two_osc", 1024)])
+def test_sequenced_patch(srk, orc, cuda_device):
+    """Grid + Pattern sequencers driving a voice, per-voice tempo."""
+    gp, op, g, g_mix, o, o_mix = render_pair(srk, orc, srk.patches.sequenced, 67, 24000)
+    assert np.abs(o[0]).max() > 0.05 and set(np.unique(o[1])) == {0.0, 1.0}
+    assert_parity(g[1], o[1], exact=True, what="pattern sequencer sync output")
+    s = assert_parity(g[0], o[0], what="sequenced voice")  # the oscillator's CV goes through exp2: tolerance
+    assert s["bit_identical"] > 0.98
+    assert_mix_parity(g_mix, o_mix, 67)
+
+
+def test_sequence_edit_keeps_voice_state(srk, orc, cuda_device):
+    """The reference's ui() edits the table under the running module: counters, detectors, envelopes and
+    filter state carry on."""
+    V = 40
+    gp = srk.Patch()
+    gh = srk.patches.sequenced(gp, V)
+    gp.plan()
+    parts_g, parts_o = [], []
+    for k in range(3):
+        parts_g.append(gp.render(V, 7001, stems=True)[0])
+        cells = np.array([srk.grid_cell((5 * k + i) % 19, i % 2 == 0) for i in range(8 + k)], dtype=np.int32)
+        gp.set_sequence(gh["grid"], cells)
+    # the oracle renders whole blocks only: one 7001-sample block per call, the same edits in between
+    op2 = orc.OraclePatch(48000, 7001, 2)
+    oh2 = srk.patches.sequenced(op2, V)
+    for k in range(3):
+        parts_o.append(op2.render(V, 7001)[0])
+        cells = np.array([srk.grid_cell((5 * k + i) % 19, i % 2 == 0) for i in range(8 + k)], dtype=np.int32)
+        op2.set_sequence(oh2["grid"], cells)
+    g, o = np.concatenate(parts_g, axis=1), np.concatenate(parts_o, axis=1)
+    assert_parity(g[1], o[1], exact=True, what="sync after edits")
+    assert_parity(g[0], o[0], what="voice after edits")
+
+
+@pytest.mark.parametrize("name,B", [("cfg2", 1024), ("cfg4", 1024), ("cfg3b", 256), ("cfg5_two_osc", 1024), ("sequenced", 1024)])
 def test_schedule_invariance(srk, orc, cuda_device, monkeypatch, name, B):
     """The same patch rendered as one warp per voice group in plan order (SRK_WARPS=1) and as a
     software pipeline over 4/16 warps, with different chunk sizes, gives the same bits: the

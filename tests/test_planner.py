@@ -28,11 +28,11 @@ def test_topological_sort_through_the_abi(srk):
 
 
 KINDS = ["OSCILLATOR", "NOISE", "ADSR", "VCA", "MOOG_FILTER", "MONO_MIXER", "ADD", "SUBTRACT", "MULTIPLY",
-         "NON_LINEAR"]
+         "NON_LINEAR", "GRID_SEQUENCER", "PATTERN_SEQUENCER"]
 N_IN = dict(OSCILLATOR=2, NOISE=0, ADSR=1, VCA=2, MOOG_FILTER=2, MONO_MIXER=4, ADD=2, SUBTRACT=2, MULTIPLY=2,
-            NON_LINEAR=2, OUTPUT=2)
+            NON_LINEAR=2, GRID_SEQUENCER=2, PATTERN_SEQUENCER=2, OUTPUT=2)
 N_OUT = dict(OSCILLATOR=3, NOISE=1, ADSR=1, VCA=1, MOOG_FILTER=3, MONO_MIXER=1, ADD=1, SUBTRACT=1, MULTIPLY=1,
-             NON_LINEAR=1, OUTPUT=0)
+             NON_LINEAR=1, GRID_SEQUENCER=3, PATTERN_SEQUENCER=9, OUTPUT=0)
 
 
 def random_graph(rng, n_modules, density):
