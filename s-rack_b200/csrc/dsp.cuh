@@ -453,22 +453,83 @@ struct MoogOp {
     s[8 * L] = __float_as_uint(c_freq); s[9 * L] = __float_as_uint(c_res);
   }
 
-  // COEF: 0 = no CV (constant cutoff), 1 = CV, coefficients computed here, 2 = coefficients
-  // from a MoogCoefOp.  OUTS: bit 0 lowpass, bit 1 bandpass, bit 2 highpass are read by
-  // somebody (compile-time, like OscOp's).
-  template <int COEF, int OUTS>
-  __device__ __forceinline__ void run_t(const Lane& ln, int kk) {
-    constexpr bool HAS_CV = COEF == 1;
-    const float* audio = p_audio.at(ln);
-    const float* cv = p_cv.at(ln);
-    const float* wf = p_f.at(ln);
-    const float* wp = p_p.at(ln);
-    const float* wq = p_q.at(ln);
-    float* lowpass = p_lp.at(ln);
-    float* bandpass = p_bp.at(ln);
-    float* highpass = p_hp.at(ln);
-    bool virgin = (c_freq == 0.0f) & (c_res == 0.0f) & (f == 0.0f);
-    if (COEF == 0 && kk > 0) {  // cutoff is constant over the chunk: one cache check (:61)
+  struct Taps {  // this chunk's tiles
+    const float *audio, *cv, *wf, *wp, *wq;
+    float *lowpass, *bandpass, *highpass;
+  };
+  __device__ __forceinline__ Taps taps(const Lane& ln) const {
+    return Taps{p_audio.at(ln), p_cv.at(ln), p_f.at(ln), p_p.at(ln), p_q.at(ln), p_lp.at(ln), p_bp.at(ln), p_hp.at(ln)};
+  }
+
+  // U samples starting at k0.  COEF: 0 = no CV (constant cutoff), 1 = CV, coefficients computed
+  // here, 2 = coefficients from a MoogCoefOp.  OUTS: bit 0 lowpass, bit 1 bandpass, bit 2 highpass
+  // are read by somebody (compile-time, like OscOp's).  First everything that does not depend on
+  // the ladder state (input loads, the coefficient block, in sample order: the cache key and the
+  // `virgin` flag are sequential but cheap), then the dependent chain (:69-82) and the write-out.
+  template <int COEF, int OUTS, int U>
+  __device__ __forceinline__ void group(const Taps& t, int k0, bool& virgin) {
+    float a[U], fj[U], pj[U], qj[U], in_[U], o3[U], o4[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) a[j] = 0.0f;
+    if (t.audio) {
+#pragma unroll
+      for (int j = 0; j < U; ++j) a[j] = t.audio[(k0 + j) * L];
+    }
+    if (COEF == 1) {
+      float fc[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) fc[j] = fminf(fmaxf(fadd(freq, fmul(t.cv[(k0 + j) * L], exp_amt)), 0.0f), 0.9f);  // :213
+#pragma unroll
+      for (int j = 0; j < U; ++j) moog_coef(fc[j], r, fj[j], pj[j], qj[j]);
+      if (virgin) {  // only until (fc, r) first leaves (0, 0)
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          virgin = virgin & (fc[j] == 0.0f) & (r == 0.0f);
+          if (virgin) { fj[j] = 0.0f; pj[j] = 0.0f; qj[j] = 0.0f; }
+        }
+      }
+      if (!virgin) { c_freq = fc[U - 1]; c_res = r; }
+      f = fj[U - 1]; p = pj[U - 1]; q = qj[U - 1];
+    } else if (COEF == 2) {
+#pragma unroll
+      for (int j = 0; j < U; ++j) { fj[j] = t.wf[(k0 + j) * L]; pj[j] = t.wp[(k0 + j) * L]; qj[j] = t.wq[(k0 + j) * L]; }
+    } else {
+#pragma unroll
+      for (int j = 0; j < U; ++j) { fj[j] = f; pj[j] = p; qj[j] = q; }
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const float in = fsub(a[j], fmul(qj[j], b4));
+      float t1 = b1;
+      b1 = fsub(fmul(fadd(in, b0), pj[j]), fmul(b1, fj[j]));
+      const float t2 = b2;
+      b2 = fsub(fmul(fadd(b1, t1), pj[j]), fmul(b2, fj[j]));
+      t1 = b3;
+      b3 = fsub(fmul(fadd(b2, t2), pj[j]), fmul(b3, fj[j]));
+      b4 = fsub(fmul(fadd(b3, t1), pj[j]), fmul(b4, fj[j]));
+      b4 = fsub(b4, fmul(fmul(fmul(b4, b4), b4), 0.166667f));  // powi(3)
+      b0 = clamp1(in);
+      b1 = clamp1(b1); b2 = clamp1(b2); b3 = clamp1(b3); b4 = clamp1(b4);
+      in_[j] = in; o3[j] = b3; o4[j] = b4;
+    }
+    // calc returns (b4, in - b4, 3*(b3-b4)) assigned to (lowpass, highpass, bandpass), :211
+    if (OUTS & 1) {
+#pragma unroll
+      for (int j = 0; j < U; ++j) t.lowpass[(k0 + j) * L] = o4[j];
+    }
+    if (OUTS & 4) {
+#pragma unroll
+      for (int j = 0; j < U; ++j) t.highpass[(k0 + j) * L] = fsub(in_[j], o4[j]);
+    }
+    if (OUTS & 2) {
+#pragma unroll
+      for (int j = 0; j < U; ++j) t.bandpass[(k0 + j) * L] = fmul(3.0f, fsub(o3[j], o4[j]));
+    }
+  }
+
+  template <int COEF>
+  __device__ __forceinline__ bool begin(int kk) {  // -> the `virgin` flag for this stretch
+    if (COEF == 0 && kk > 0) {  // cutoff is constant: one cache check (:61)
       const float fc = fminf(fmaxf(fadd(freq, fmul(0.0f, exp_amt)), 0.0f), 0.9f);  // :213 with cv = 0.0
       if (fc != c_freq || r != c_res) {
         c_freq = fc;
@@ -476,98 +537,81 @@ struct MoogOp {
         moog_coef(fc, r, f, p, q);
       }
     }
-    // prep(): everything that does not depend on the ladder state -- input loads and the
-    // coefficient block, in sample order (the cache key and the `virgin` flag are sequential
-    // but cheap).  ladder(): the dependent chain (:69-82) and the write-out.
-    auto prep = [&](auto u, int k0, float* a, float* fj, float* pj, float* qj) {
-      constexpr int U = decltype(u)::value;
-#pragma unroll
-      for (int j = 0; j < U; ++j) a[j] = 0.0f;
-      if (audio) {
-#pragma unroll
-        for (int j = 0; j < U; ++j) a[j] = audio[(k0 + j) * L];
-      }
-      if (HAS_CV) {
-        float fc[U];
-#pragma unroll
-        for (int j = 0; j < U; ++j) fc[j] = fminf(fmaxf(fadd(freq, fmul(cv[(k0 + j) * L], exp_amt)), 0.0f), 0.9f);  // :213
-#pragma unroll
-        for (int j = 0; j < U; ++j) moog_coef(fc[j], r, fj[j], pj[j], qj[j]);
-        if (virgin) {  // only until (fc, r) first leaves (0, 0)
-#pragma unroll
-          for (int j = 0; j < U; ++j) {
-            virgin = virgin & (fc[j] == 0.0f) & (r == 0.0f);
-            if (virgin) { fj[j] = 0.0f; pj[j] = 0.0f; qj[j] = 0.0f; }
-          }
-        }
-        if (!virgin) { c_freq = fc[U - 1]; c_res = r; }
-        f = fj[U - 1]; p = pj[U - 1]; q = qj[U - 1];
-      } else if (COEF == 2) {
-#pragma unroll
-        for (int j = 0; j < U; ++j) { fj[j] = wf[(k0 + j) * L]; pj[j] = wp[(k0 + j) * L]; qj[j] = wq[(k0 + j) * L]; }
-      } else {
-#pragma unroll
-        for (int j = 0; j < U; ++j) { fj[j] = f; pj[j] = p; qj[j] = q; }
-      }
-    };
-    auto ladder = [&](auto u, int k0, const float* a, const float* fj, const float* pj, const float* qj) {
-      constexpr int U = decltype(u)::value;
-      float in_[U], o3[U], o4[U];
-#pragma unroll
-      for (int j = 0; j < U; ++j) {
-        const float in = fsub(a[j], fmul(qj[j], b4));
-        float t1 = b1;
-        b1 = fsub(fmul(fadd(in, b0), pj[j]), fmul(b1, fj[j]));
-        const float t2 = b2;
-        b2 = fsub(fmul(fadd(b1, t1), pj[j]), fmul(b2, fj[j]));
-        t1 = b3;
-        b3 = fsub(fmul(fadd(b2, t2), pj[j]), fmul(b3, fj[j]));
-        b4 = fsub(fmul(fadd(b3, t1), pj[j]), fmul(b4, fj[j]));
-        b4 = fsub(b4, fmul(fmul(fmul(b4, b4), b4), 0.166667f));  // powi(3)
-        b0 = clamp1(in);
-        b1 = clamp1(b1); b2 = clamp1(b2); b3 = clamp1(b3); b4 = clamp1(b4);
-        in_[j] = in; o3[j] = b3; o4[j] = b4;
-      }
-      // calc returns (b4, in - b4, 3*(b3-b4)) assigned to (lowpass, highpass, bandpass), :211
-      if (OUTS & 1) {
-#pragma unroll
-        for (int j = 0; j < U; ++j) lowpass[(k0 + j) * L] = o4[j];
-      }
-      if (OUTS & 4) {
-#pragma unroll
-        for (int j = 0; j < U; ++j) highpass[(k0 + j) * L] = fsub(in_[j], o4[j]);
-      }
-      if (OUTS & 2) {
-#pragma unroll
-        for (int j = 0; j < U; ++j) bandpass[(k0 + j) * L] = fmul(3.0f, fsub(o3[j], o4[j]));
-      }
-    };
-    // Software pipeline over groups: group g+1's prep sits in the same basic block as group
-    // g's ladder, so its loads and ~20 flops per sample fill the chain's latency bubbles.
-    constexpr int G = kGroup;
-    const int n_full = kk / G;
+    return (c_freq == 0.0f) & (c_res == 0.0f) & (f == 0.0f);
+  }
+
+  template <int COEF, int OUTS>
+  __device__ __forceinline__ void run_t(const Lane& ln, int kk) {
+    bool virgin = begin<COEF>(kk);
+    const Taps t = taps(ln);
     int k0 = 0;
-    if (n_full > 0) {
-      float a0[G], f0[G], p0[G], q0[G];
-      prep(UC<G>(), 0, a0, f0, p0, q0);
 #pragma unroll 1
-      for (int g = 1; g < n_full; ++g) {
-        float a1[G], f1[G], p1[G], q1[G];
-        prep(UC<G>(), k0 + G, a1, f1, p1, q1);
-        ladder(UC<G>(), k0, a0, f0, p0, q0);
-#pragma unroll
-        for (int j = 0; j < G; ++j) { a0[j] = a1[j]; f0[j] = f1[j]; p0[j] = p1[j]; q0[j] = q1[j]; }
-        k0 += G;
+    for (; k0 + kGroup <= kk; k0 += kGroup) group<COEF, OUTS, kGroup>(t, k0, virgin);
+#pragma unroll 1
+    for (; k0 < kk; ++k0) group<COEF, OUTS, 1>(t, k0, virgin);
+  }
+
+  // The resident form for a whole render: ONE loop over every group of every full chunk, the
+  // block barrier and the four tile pointers inline at the chunk boundaries.  The filter is the
+  // pipeline's critical stage, and the chunk-at-a-time form spent ~1.5k cycles per barrier
+  // interval refetching its cold prologue / epilogue code (profiles/r01i_k8, r01t).
+  template <int COEF, int OUTS, class Sync>
+  __device__ __forceinline__ void run_all_t(Lane& ln, uint32_t n_samples, Sync&& sync) {
+    const uint32_t K = ln.tile_elems / L;
+    const uint32_t full_chunks = n_samples / K, groups_per_chunk = K / kGroup;
+    bool virgin = begin<COEF>((int)n_samples);
+    Taps t = taps(ln);
+    uint32_t in_chunk = 0;
+    int k0 = 0;
+    ln.chunk = 0;
+    t = taps(ln);
+#pragma unroll 1
+    for (uint32_t g = 0; g < full_chunks * groups_per_chunk; ++g) {
+      if (in_chunk == groups_per_chunk) {
+        sync();
+        in_chunk = 0;
+        k0 = 0;
+        ++ln.chunk;
+        t = taps(ln);
       }
-      ladder(UC<G>(), k0, a0, f0, p0, q0);
-      k0 += G;
+      group<COEF, OUTS, kGroup>(t, k0, virgin);
+      k0 += kGroup;
+      ++in_chunk;
     }
+    if (full_chunks) sync();
+    const int rest = (int)(n_samples - full_chunks * K);
+    if (rest) {  // ragged last chunk
+      ln.chunk = full_chunks;
+      t = taps(ln);
+      int k = 0;
 #pragma unroll 1
-    for (; k0 < kk; ++k0) {
-      float a1[1], f1[1], p1[1], q1[1];
-      prep(UC<1>(), k0, a1, f1, p1, q1);
-      ladder(UC<1>(), k0, a1, f1, p1, q1);
+      for (; k + kGroup <= rest; k += kGroup) group<COEF, OUTS, kGroup>(t, k, virgin);
+#pragma unroll 1
+      for (; k < rest; ++k) group<COEF, OUTS, 1>(t, k, virgin);
+      sync();
     }
+  }
+
+  template <int COEF, class Sync>
+  __device__ __forceinline__ void run_all_outs(Lane& ln, uint32_t n_samples, Sync&& sync) {
+    const int outs = (p_lp.base ? 1 : 0) | (p_bp.base ? 2 : 0) | (p_hp.base ? 4 : 0);
+    switch (outs) {
+      case 0: run_all_t<COEF, 0>(ln, n_samples, sync); break;
+      case 1: run_all_t<COEF, 1>(ln, n_samples, sync); break;
+      case 2: run_all_t<COEF, 2>(ln, n_samples, sync); break;
+      case 3: run_all_t<COEF, 3>(ln, n_samples, sync); break;
+      case 4: run_all_t<COEF, 4>(ln, n_samples, sync); break;
+      case 5: run_all_t<COEF, 5>(ln, n_samples, sync); break;
+      case 6: run_all_t<COEF, 6>(ln, n_samples, sync); break;
+      default: run_all_t<COEF, 7>(ln, n_samples, sync); break;
+    }
+  }
+  // One sync() after every chunk, like the chunk-at-a-time loop.  K must be a multiple of kGroup.
+  template <class Sync>
+  __device__ __forceinline__ void run_all(Lane& ln, uint32_t n_samples, Sync&& sync) {
+    if (ext) run_all_outs<2>(ln, n_samples, sync);
+    else if (p_cv.base) run_all_outs<1>(ln, n_samples, sync);
+    else run_all_outs<0>(ln, n_samples, sync);
   }
 
   template <int COEF>

@@ -247,7 +247,19 @@ __global__ void __launch_bounds__(SOLO ? 32 : kMaxThreads, 1) render_voices_kern
         if (op.owns_state(ins)) op.store();
         break;
       }
-      case OP_MOOG: run_resident<dsp::MoogOp>(ins, ln, a, n_chunks, n_iter); break;
+      case OP_MOOG: {  // the critical stage: one flat loop over the whole render (MoogOp::run_all)
+        dsp::MoogOp op;
+        op.load(ins, ln);
+        if (K % dsp::kGroup == 0) {
+          for (uint32_t it = 0; it < ins.stage; ++it) __syncthreads();
+          op.run_all(ln, a.n_samples, [] { __syncthreads(); });
+          for (uint32_t it = ins.stage + n_chunks; it < n_iter; ++it) __syncthreads();
+        } else {
+          resident_loop(ins, ln, a, n_chunks, n_iter, [&](int kk) { op.run(ins, ln, kk); });
+        }
+        op.store();
+        break;
+      }
       case OP_MOOG_COEF: run_resident<dsp::MoogCoefOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_GRIDSEQ: run_resident<dsp::GridSeqOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_PATSEQ: run_resident<dsp::PatSeqOp>(ins, ln, a, n_chunks, n_iter); break;
