@@ -176,6 +176,13 @@ struct OscOp {
     float* sine = p_sine.at(ln);
     float* square = p_square.at(ln);
     float* saw = p_saw.at(ln);
+    // Work on copies: when the op object itself ends up in local memory (it is captured by
+    // reference in the resident loop), the recurrence must not go through it every sample
+    // (r01x: 27 % long-scoreboard stalls on the phase add).
+    double pos = this->pos;
+    bool last = this->last;
+    const double val = this->val, delta_const = this->delta_const, sr = this->sr;
+    const bool aa = this->aa;
     for_groups(kb, ke, [&](auto u, int k0) {
       constexpr int U = decltype(u)::value;
       float cvv[U];
@@ -271,6 +278,8 @@ struct OscOp {
     });
     // with no sync input the detector sees 0.0 every sample: `last` just goes false
     if (!has_sync && ke > kb) last = false;
+    this->pos = pos;
+    this->last = last;
   }
 
   template <bool HAS_CV, bool HAS_SYNC>
@@ -293,6 +302,7 @@ struct OscOp {
   // sample, 8 samples per loop trip, the odd-step test once per trip.
   __device__ __forceinline__ void advance(int kb, int ke) {
     const double dl = delta_const;
+    double pos = this->pos;  // (a register copy, see run_t)
     int k = kb;
 #pragma unroll 1
     for (; k + 8 <= ke; k += 8) {
@@ -315,6 +325,7 @@ struct OscOp {
       const double x = dadd(pos, dl);
       pos = x < 2.0 ? wrap01(x) : fmod1_exact(x);
     }
+    this->pos = pos;
     if (ke > kb) last = false;
   }
 
