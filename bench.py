@@ -47,16 +47,55 @@ def ncu_traffic(config):
         return None
 
 
+def ncu_utilization(config):
+    """issue / pipe utilisation of the same capture (SURVEY.md §8d asks for it next to the HBM fraction)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(config + "_utilization")
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons every 200 ms while the timed region runs."""
+    """SM clock + throttle reasons while the timed region runs: NVML (nvidia_ml_py) every 20 ms,
+    `nvidia-smi --query-gpu` every 200 ms as the fallback (the B200_PROFILING.md clocks line)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, uuid=None):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu_index, [], threading.Event()
+        self.gpu, self.uuid, self.rows, self.stop_flag = gpu_index, uuid, [], threading.Event()
+        self.sm_max, self.source = None, "nvidia-smi"
 
-    def run(self):
+    def _nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = None
+        if self.uuid:
+            for u in (self.uuid, "GPU-" + self.uuid):
+                try:
+                    h = nv.nvmlDeviceGetHandleByUUID(u.encode() if isinstance(u, str) else u)
+                    break
+                except Exception:
+                    h = None
+        if h is None:
+            h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+        self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        bits = [(nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else nv.nvmlClocksThrottleReasonHwSlowdown),
+                (nv.nvmlClocksEventReasonHwThermalSlowdown if hasattr(nv, "nvmlClocksEventReasonHwThermalSlowdown") else nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                (nv.nvmlClocksEventReasonSwThermalSlowdown if hasattr(nv, "nvmlClocksEventReasonSwThermalSlowdown") else nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                (nv.nvmlClocksEventReasonSwPowerCap if hasattr(nv, "nvmlClocksEventReasonSwPowerCap") else nv.nvmlClocksThrottleReasonSwPowerCap)]
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        get(h)  # raises here if unsupported -> fallback
+        self.source = "nvml"
+        while not self.stop_flag.is_set():
+            mask = get(h)
+            self.rows.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(self.sm_max)] +
+                             ["Active" if mask & b else "Not Active" for b in bits])
+            self.stop_flag.wait(0.02)
+
+    def _smi(self):
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
@@ -68,16 +107,21 @@ class ClockSampler(threading.Thread):
                 pass
             self.stop_flag.wait(0.2)
 
+    def run(self):
+        try:
+            self._nvml()
+        except Exception:
+            self._smi()
+
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=6)
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in self.rows for n, v in zip(self.NAMES, r[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]),
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows), "source": self.source}
 
 
 def cpu_reference_run(config, steps, warmup, sample_voices=None):
@@ -204,7 +248,11 @@ def main():
             ms = float(t.item())
         return ms / steps, patch.launch_count() - launches0
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    try:
+        uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local_rank, uuid) if rank == 0 else None
     if sampler:
         sampler.start()
     ms_step, launches = timed(step_resident, args.steps, args.warmup)
@@ -214,7 +262,6 @@ def main():
         step_resident()
         torch.cuda.synchronize()
         k_ms.append(patch.last_render_ms()[0])
-    clocks = sampler.summary() if sampler else None
     kernel_ms = sum(k_ms) / len(k_ms)
     value = V_total * N_SAMPLES / (ms_step * 1e-3)
 
@@ -243,6 +290,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = V_total * N_SAMPLES / e2e_s
+    clocks = sampler.summary() if sampler else None  # covers the device-timed and the e2e-timed regions
 
     # ---- e2e with all stems to pinned host memory as well (PCIe bound), N = 1 only, bounded memory
     e2e_stems = None
@@ -287,7 +335,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(args.config), "peak_source": peak_src,
                          "algorithmic_bytes_per_voice_sample": bpvs, "kernel": "render_voices_kernel",
-                         "kernel_ms": kernel_ms,
+                         "kernel_ms": kernel_ms, "ncu_utilization": ncu_utilization(args.config),
                          "note": "latency/issue-bound DSP recurrences: HBM fraction is small by construction (SURVEY.md §8d)"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
