@@ -455,9 +455,18 @@ static int choose_max_warps(const Engine& e, size_t V) {
   if (forced > 0) return std::min(forced, (int)kMaxWarps);
   const size_t groups = (V + kVoicesPerGroup - 1) / kVoicesPerGroup;
   const size_t per_sm = (groups + std::max(e.n_sm, 1) - 1) / std::max(e.n_sm, 1);
-  // measured on B200 (profiles/r01j sweep): with 3+ groups per SM the one-warp schedule wins
-  // (cfg2 at 14 groups/SM: 42 ms vs 54 ms pipelined; cfg4 at 7 groups/SM: 78 ms vs 100 ms)
-  return per_sm <= 2 ? kMaxWarps : 1;
+  // Upper bound only; pipelined_pays() decides with the compiled program's cost model.
+  return per_sm <= 8 ? kMaxWarps : 1;
+}
+
+// Pipelined groups finish in (groups per SM) x (slowest stage); a one-warp group in the sum of all
+// its modules, however few the groups.  Measured on B200 (profiles/r01z_crossover_sweep.txt): cfg2
+// pipelines up to ~5 groups per SM (16384 voices: 14.7 ms vs 24.6 ms; 24576: 31 ms vs 27 ms), cfg3 --
+// whose CV-driven oscillator is one long stage -- only at 1-2 (16384 voices: 58 ms pipelined).
+static bool pipelined_pays(const Engine& e, const Program& prog, size_t V) {
+  const size_t groups = (V + kVoicesPerGroup - 1) / kVoicesPerGroup;
+  const size_t per_sm = std::max<size_t>((groups + std::max(e.n_sm, 1) - 1) / std::max(e.n_sm, 1), 1);
+  return env_int("SRK_WARPS", 0) > 0 || 2 * per_sm * prog.max_cost <= 3 * (size_t)prog.sum_cost;
 }
 
 static size_t smem_bytes_for(const Program& prog, size_t blob_vec, int K) {
@@ -470,19 +479,17 @@ static size_t smem_bytes_for(const Program& prog, size_t blob_vec, int K) {
 // instruction-cache refill for the code outside the sample loops (profiles/r01i_k8), and only
 // pays (stages - 1) chunks of fill/drain per render.
 constexpr int kMaxChunk = 128;
-static int choose_chunk(const Engine& e, const Program& prog, size_t blob_vec, size_t n_samples, size_t V) {
+static int choose_chunk(const Engine& e, const Program& prog, size_t blob_vec, size_t V) {
   const bool pipelined = prog.n_warps > 1;
   // shared memory one block may take so that every group of this launch is resident at once
   const size_t groups = (V + kVoicesPerGroup - 1) / kVoicesPerGroup;
   const size_t per_sm = std::max<size_t>((groups + std::max(e.n_sm, 1) - 1) / std::max(e.n_sm, 1), 1);
-  const size_t smem_cap = pipelined && per_sm <= 4 ? std::min<size_t>(e.smem_optin, (size_t)(e.smem_sm / per_sm) - 1024)
-                                                   : (size_t)e.smem_optin;
+  const size_t smem_cap = pipelined ? std::min<size_t>(e.smem_optin, (size_t)(e.smem_sm / per_sm) - 1024)
+                                    : (size_t)e.smem_optin;
   int K = env_int("SRK_STEP", pipelined ? kMaxChunk : 16);
   if (K < 1) K = 1;
   if (K > kMaxChunk) K = kMaxChunk;
   while (K & (K - 1)) K &= K - 1;  // power of two
-  if (pipelined)  // keep fill/drain under ~1/8 of the render
-    while (K > 8 && (size_t)K * (prog.n_stages - 1) * 8 > std::max<size_t>(n_samples, 1)) K /= 2;
   if (prog.n_rings) {
     // a delayed wire's sample n - B must have been stored in an EARLIER iteration than the one
     // that loads sample n: K <= B when one warp runs everything in order, K * (stage + 2) <= B
@@ -494,7 +501,15 @@ static int choose_chunk(const Engine& e, const Program& prog, size_t blob_vec, s
   }
   while (K > 1 && smem_bytes_for(prog, blob_vec, K) > smem_cap) K /= 2;
   if (smem_bytes_for(prog, blob_vec, K) > smem_cap) return 0;
-  if (pipelined && K < 8) return 0;  // a barrier every few samples: not worth pipelining
+  if (pipelined && K < (per_sm > 2 ? 32 : 8)) return 0;  // short chunks: the barrier interval costs more than it buys
+  return K;
+}
+
+// The chunk actually used for a render of n_samples: a pipelined program pays (stages - 1) chunks of
+// fill and drain, kept under ~1/8 of the render.
+static int chunk_for_length(const Program& prog, int K, size_t n_samples) {
+  if (prog.n_warps > 1)
+    while (K > 8 && (size_t)K * (prog.n_stages - 1) * 8 > std::max<size_t>(n_samples, 1)) K /= 2;
   return K;
 }
 
@@ -580,12 +595,12 @@ static int engine_prepare(srk_patch* patch, size_t n_voices, size_t voice_offset
     int rc = compile_program(*patch, want_warps, e.prog, err);
     if (rc != SRK_OK) { patch->last_error = err; return rc; }
     build_blob(e.prog, e.blob);
-    e.chunk = choose_chunk(e, e.prog, e.blob.size(), 1u << 30, n_voices);
-    if (e.chunk == 0 && e.prog.n_warps > 1) {  // does not fit as a pipeline: one warp, plan order
+    e.chunk = e.prog.n_warps > 1 && !pipelined_pays(e, e.prog, n_voices) ? 0 : choose_chunk(e, e.prog, e.blob.size(), n_voices);
+    if (e.chunk == 0 && e.prog.n_warps > 1) {  // does not fit or does not pay as a pipeline: one warp, plan order
       rc = compile_program(*patch, 1, e.prog, err);
       if (rc != SRK_OK) { patch->last_error = err; return rc; }
       build_blob(e.prog, e.blob);
-      e.chunk = choose_chunk(e, e.prog, e.blob.size(), 1u << 30, n_voices);
+      e.chunk = choose_chunk(e, e.prog, e.blob.size(), n_voices);
     }
     if (e.chunk == 0) { patch->last_error = "patch needs more shared memory than one block can have"; return SRK_ERR_LIMIT; }
     SRK_CUDA(e.d_prog.ensure(e.blob.size() * sizeof(uint4)));
@@ -643,7 +658,7 @@ int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t
 
   const Program& prog = e.prog;
   const size_t C = prog.channels;
-  const int K = choose_chunk(e, prog, e.blob.size(), n_samples, n_voices);  // <= e.chunk, which fitted
+  const int K = chunk_for_length(prog, e.chunk, n_samples);  // <= e.chunk, which fitted
   const int T = (int)prog.n_warps * 32;
   const size_t smem = smem_bytes_for(prog, e.blob.size(), K);
   const unsigned grid = (unsigned)((n_voices + kVoicesPerGroup - 1) / kVoicesPerGroup);
@@ -766,12 +781,12 @@ static int probe_program(srk_patch* patch, size_t n_voices, Program& prog, std::
   int rc = compile_program(*patch, choose_max_warps(probe, n_voices), prog, err);
   if (rc != SRK_OK) { patch->last_error = err; return rc; }
   build_blob(prog, blob);
-  K = choose_chunk(probe, prog, blob.size(), 1u << 30, n_voices);
+  K = prog.n_warps > 1 && !pipelined_pays(probe, prog, n_voices) ? 0 : choose_chunk(probe, prog, blob.size(), n_voices);
   if (K == 0 && prog.n_warps > 1) {
     rc = compile_program(*patch, 1, prog, err);
     if (rc != SRK_OK) { patch->last_error = err; return rc; }
     build_blob(prog, blob);
-    K = choose_chunk(probe, prog, blob.size(), 1u << 30, n_voices);
+    K = choose_chunk(probe, prog, blob.size(), n_voices);
   }
   if (K == 0) { patch->last_error = "patch needs more shared memory than one block can have"; return SRK_ERR_LIMIT; }
   return SRK_OK;

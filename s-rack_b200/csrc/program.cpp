@@ -280,6 +280,7 @@ int compile_program(const srk_patch& patch, int max_warps, Program& prog, std::s
       int w = code[i].out_vw[k];
       if (w >= 0 && vw[w].last_use < 0) code[i].out_vw[k] = -1;
     }
+  for (const Pending& p : code) prog.sum_cost += (uint32_t)op_cost(p);  // before any splitting: one warp does it all
   const bool pipelined = max_warps > 1 && code.size() > 1;
   if (pipelined) {
     // Time-split heavy oscillators.  An oscillator without a CV input spends ~25 cycles per
@@ -340,7 +341,10 @@ int compile_program(const srk_patch& patch, int max_warps, Program& prog, std::s
   for (int i = 0; i < nc; ++i)
     for (int k = 0; k < 3; ++k)
       if (code[i].out_vw[k] >= 0) vw[code[i].out_vw[k]].def = i;
-  for (auto& p : code) p.cost = op_cost(p);
+  for (auto& p : code) {
+    p.cost = op_cost(p);
+    prog.max_cost = std::max<uint32_t>(prog.max_cost, (uint32_t)p.cost);
+  }
 
   std::vector<int> stage(nc, 0), warp(nc, 0);
   if (!pipelined) {

@@ -99,6 +99,7 @@ struct Program {
   uint32_t n_warps = 1;                // S
   uint32_t n_stages = 1;               // max stage + 1
   uint32_t max_ring_store_stage = 0;
+  uint32_t max_cost = 0, sum_cost = 0; // cost model (program.cpp): slowest scheduled instruction / all modules in series
   uint32_t n_rings = 0;
   uint32_t channels = 0;
   uint32_t ring_len = 0;               // buffer_size
