@@ -55,7 +55,7 @@ __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a,
 // every finite x, NaN for +-inf like fmod.  Kept out of line: the phase accumulator only
 // ever sees x in [0, 2), where the result is x or x - 1 (both exact), and tests once per
 // group whether anything else turned up (wrap01 / the `odd` flag in OscOp).
-__device__ __noinline__ double fmod1_exact(double x) { return dsub(x, trunc(x)); }
+static __device__ __noinline__ double fmod1_exact(double x) { return dsub(x, trunc(x)); }
 // fmod(x, 1.0) for x in [0, 2); NaN stays NaN.
 __device__ __forceinline__ double wrap01(double x) { return x >= 1.0 ? dsub(x, 1.0) : x; }
 
@@ -933,7 +933,7 @@ struct MixerOp {
 // math.rs:203-205 `if a > 0.0 { a.powf(b) } else { -(-a).powf(b) }` in f32.  glibc's powf
 // evaluates in f64 and rounds once; f64 pow here then one rounding agrees with it except
 // when the f64 results straddle an f32 rounding boundary.  Out of line: pow() is large.
-__device__ __noinline__ float nonlinear(float a, float b) {
+static __device__ __noinline__ float nonlinear(float a, float b) {
   return a > 0.0f ? __double2float_rn(pow((double)a, (double)b)) : -__double2float_rn(pow((double)(-a), (double)b));
 }
 

@@ -1,0 +1,38 @@
+// Launch arguments of the voice kernel and the two host-side launchers (one per schedule, each
+// in its own translation unit: voice_kernel_solo.cu, voice_kernel_pipelined.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+#include "program.hpp"
+
+namespace srk {
+
+struct RenderArgs {
+  const uint4* blob;      // [Instr x n_instr][WireDesc x n_wires][u16 warp_begin x (n_warps + 1)][pad][i32 tables]
+  uint32_t* state;
+  const uint32_t* params;
+  float* rings;
+  float* stems;
+  float* partial;
+  uint32_t blob_vec;      // blob size in uint4
+  uint32_t table_off;     // byte offset of the sequencer tables inside the blob
+  uint32_t n_instr, n_wires, n_warps, n_stages, n_tiles;
+  uint32_t V;             // voices rendered by this launch
+  uint32_t voice_offset;  // global index of voice 0 (noise key)
+  uint32_t n_samples;
+  uint32_t S, P, C, B;
+  uint32_t K;             // samples per chunk: power of two <= 128
+  uint32_t log2K;
+  uint32_t ring_phase;    // absolute sample index of sample 0, mod B
+  uint32_t seed_lo, seed_hi;
+};
+
+constexpr int kMaxThreads = kMaxWarps * 32;
+
+cudaError_t launch_voices_solo(const RenderArgs& a, unsigned grid, size_t smem, cudaStream_t stream);
+cudaError_t launch_voices_pipelined(const RenderArgs& a, unsigned grid, unsigned threads, size_t smem, cudaStream_t stream);
+
+}  // namespace srk
