@@ -448,3 +448,60 @@ def test_schedule_invariance(srk, orc, cuda_device, monkeypatch, name, B):
     gp, op, _, _ = build_both(srk, orc, builder, V, buffer_size=B)
     o_st, _ = op.render(V, N + 997)
     assert_parity(results[0][1], o_st, what=f"{name} schedule 0")
+
+
+def test_baseline_size_cfg4_sampled_parity(srk, orc, cuda_device):
+    """BASELINE configs[3] per GPU (32768 of the 262144 voices x 48000 samples, the one-warp
+    schedule): mix-only render at full size, then the stems of two voice slices (a middle one and the
+    ragged tail of the shard) rendered with voice_offset and compared with the oracle -- the per-voice
+    noise key is the global voice index, so the slices must reproduce the shard's voices exactly."""
+    import torch
+
+    V_total, V, N = 262144, 32768, 48000
+    off = srk.shard.voice_range(V_total, 5, 8)[0]  # rank 5's shard
+    p = srk.Patch(device=0)
+    srk.patches.cfg4(p, V_total)
+    p.plan()
+    assert p.program_info(V)["n_warps"] == 1
+    mix = torch.empty((2, N), dtype=torch.float32, device="cuda:0")
+    p.render_into(V, N, off, None, mix.data_ptr(), device_out=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(mix).all() and float(mix.abs().max()) > 10.0
+    total = np.zeros((2, N))
+    for first, cnt in ((off + 12345, 40), (off + V - 37, 37)):
+        q = srk.Patch(device=0)
+        srk.patches.cfg4(q, V_total)
+        q.plan()
+        st, _ = q.render(cnt, N, voice_offset=first, stems=True)
+        op = orc.OraclePatch()
+        srk.patches.cfg4(op, V_total)
+        ref, _ = op.render(cnt, N, voice_offset=first)
+        s = assert_parity(st, ref, what=f"cfg4 voices {first}..")
+        assert s["bit_identical"] > 0.99
+        total += st.astype(np.float64).sum(axis=2)
+    assert np.abs(total).max() > 0.1
+
+
+def test_baseline_size_cfg3b_feedback(srk, orc, cuda_device):
+    """BASELINE configs[2] with the in-graph feedback wire (one cut edge, buffer_size 1024 of delay),
+    65536 voices x 48000: mix-only at full size (rings: 268 MB of HBM), a voice slice against the oracle."""
+    import torch
+
+    V, N = 65536, 48000
+    p = srk.Patch(device=0)
+    srk.patches.cfg3b(p, V)
+    p.plan()
+    assert p.program_info(V)["n_rings"] == 1
+    mix = torch.empty((2, N), dtype=torch.float32, device="cuda:0")
+    p.render_into(V, N, 0, None, mix.data_ptr(), device_out=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(mix).all() and float(mix.abs().max()) > 10.0
+    q = srk.Patch(device=0)
+    srk.patches.cfg3b(q, V)
+    q.plan()
+    st, _ = q.render(33, N, voice_offset=40000, stems=True)
+    op = orc.OraclePatch()
+    srk.patches.cfg3b(op, V)
+    ref, _ = op.render(33, N, voice_offset=40000)
+    s = assert_parity(st, ref, what="cfg3b voice slice")
+    assert s["bit_identical"] > 0.98
