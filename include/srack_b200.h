@@ -250,7 +250,8 @@ SRK_API int srk_get_program_info(srk_patch* patch, size_t n_voices, srk_program_
 typedef struct srk_instr_info {
   uint8_t op;      /* 0 end, 1 ring load, 2 ring store, 3 oscillator, 4 noise, 5 moog, 6 adsr, 7 vca,
                       8 mixer, 9 math, 10 output (stems), 11 mix, 12 moog coefficients,
-                      13 grid sequencer, 14 pattern sequencer (three output ports per instruction) */
+                      13 grid sequencer, 14 pattern sequencer (three output ports per instruction),
+                      15 oscillator V/oct conversion (delta = 440 * 2^cv / sr on a wire pair) */
   uint8_t flags;   /* math: operation; oscillator: (copies << 4) | copy index when time-split */
   uint8_t warp;    /* warp of the 32-voice group that executes it */
   uint8_t stage;   /* works on chunk (iteration - stage) */

@@ -145,7 +145,8 @@ struct OscOp {
   uint32_t* s;
   double pos, val, delta_const, sr;
   bool last, aa;
-  Port p_cv, p_sync, p_sine, p_square, p_saw;
+  Port p_cv, p_sync, p_sine, p_square, p_saw, p_dlo, p_dhi;
+  bool ext;  // delta arrives on a pair of wires from an OscDeltaOp
 
   __device__ __forceinline__ void load(const Instr& ins, const Lane& ln) {
     s = ln.st + ins.state * L;
@@ -156,7 +157,9 @@ struct OscOp {
     delta_const = __hiloint2double((int)p[2 * L], (int)p[L]);
     sr = (double)ins.imm;
     aa = __uint_as_float(p[3 * L]) != 0.0f;
+    ext = ins.n_ch != 0;
     p_cv = port(ln, ins.in[0]); p_sync = port(ln, ins.in[1]);
+    p_dlo = port(ln, ext ? ins.in[2] : -1); p_dhi = port(ln, ext ? ins.in[3] : -1);
     p_sine = port(ln, ins.out[0]); p_square = port(ln, ins.out[1]); p_saw = port(ln, ins.out[2]);
   }
   __device__ __forceinline__ void store() {
@@ -167,10 +170,15 @@ struct OscOp {
 
   // OUTS: bit 0 sine, bit 1 square, bit 2 saw are read by somebody.  Compile-time, because a
   // per-group `if (port connected)` costs more than the arithmetic it guards (see header).
-  template <bool HAS_CV, bool HAS_SYNC, int OUTS>
+  // DM: where delta comes from -- 0 the voice's constant, 1 the CV input (converted here),
+  // 2 an OscDeltaOp's wire pair.
+  template <int DM, bool HAS_SYNC, int OUTS>
   __device__ __forceinline__ void run_t(const Lane& ln, int kb, int ke) {
     constexpr bool SINE = OUTS & 1, SQUARE = OUTS & 2, SAW = OUTS & 4;
+    constexpr bool HAS_CV = DM == 1;
     const float* cv = p_cv.at(ln);
+    const float* dlo = p_dlo.at(ln);
+    const float* dhi = p_dhi.at(ln);
     const float* sync = p_sync.at(ln);
     constexpr bool has_sync = HAS_SYNC;
     float* sine = p_sine.at(ln);
@@ -204,8 +212,12 @@ struct OscOp {
       }
       // get_freq_in_hz (:43-48) then / sample_rate (:132): stateless
 #pragma unroll
-      for (int j = 0; j < U; ++j)
-        dl[j] = HAS_CV ? __ddiv_rn(dmul(440.0, exp2(dadd((double)cvv[j], val))), sr) : delta_const;
+      for (int j = 0; j < U; ++j) {
+        if (DM == 2)
+          dl[j] = __hiloint2double(__float_as_int(dhi[(k0 + j) * L]), __float_as_int(dlo[(k0 + j) * L]));
+        else
+          dl[j] = HAS_CV ? __ddiv_rn(dmul(440.0, exp2(dadd((double)cvv[j], val))), sr) : delta_const;
+      }
       // the recurrence: sync reset, pos += delta; pos %= 1.0 (:151-152)
       const double pos0 = pos;
       bool odd = false;
@@ -282,18 +294,18 @@ struct OscOp {
     this->last = last;
   }
 
-  template <bool HAS_CV, bool HAS_SYNC>
+  template <int DM, bool HAS_SYNC>
   __device__ __forceinline__ void run_outs(const Lane& ln, int kb, int ke) {
     const int outs = (p_sine.base ? 1 : 0) | (p_square.base ? 2 : 0) | (p_saw.base ? 4 : 0);
     switch (outs) {
-      case 0: run_t<HAS_CV, HAS_SYNC, 0>(ln, kb, ke); break;
-      case 1: run_t<HAS_CV, HAS_SYNC, 1>(ln, kb, ke); break;
-      case 2: run_t<HAS_CV, HAS_SYNC, 2>(ln, kb, ke); break;
-      case 3: run_t<HAS_CV, HAS_SYNC, 3>(ln, kb, ke); break;
-      case 4: run_t<HAS_CV, HAS_SYNC, 4>(ln, kb, ke); break;
-      case 5: run_t<HAS_CV, HAS_SYNC, 5>(ln, kb, ke); break;
-      case 6: run_t<HAS_CV, HAS_SYNC, 6>(ln, kb, ke); break;
-      default: run_t<HAS_CV, HAS_SYNC, 7>(ln, kb, ke); break;
+      case 0: run_t<DM, HAS_SYNC, 0>(ln, kb, ke); break;
+      case 1: run_t<DM, HAS_SYNC, 1>(ln, kb, ke); break;
+      case 2: run_t<DM, HAS_SYNC, 2>(ln, kb, ke); break;
+      case 3: run_t<DM, HAS_SYNC, 3>(ln, kb, ke); break;
+      case 4: run_t<DM, HAS_SYNC, 4>(ln, kb, ke); break;
+      case 5: run_t<DM, HAS_SYNC, 5>(ln, kb, ke); break;
+      case 6: run_t<DM, HAS_SYNC, 6>(ln, kb, ke); break;
+      default: run_t<DM, HAS_SYNC, 7>(ln, kb, ke); break;
     }
   }
 
@@ -335,31 +347,71 @@ struct OscOp {
   __device__ __forceinline__ void run(const Instr& ins, const Lane& ln, int kk) {
     const uint32_t n = ins.flags >> 4;
     const bool cv = p_cv.base != nullptr, sync = p_sync.base != nullptr;
-    if (n > 1 && !cv && !sync) {
+    int lo = 0, hi = kk;  // the span this copy shapes
+    if (n > 1) {
       const int span = (int)(ln.tile_elems / L / n);
-      const int lo = min(kk, (int)(ins.flags & 15u) * span), hi = min(kk, lo + span);
-      advance(0, lo);
-      run_outs<false, false>(ln, lo, hi);
-      advance(hi, kk);
-      return;
+      lo = min(kk, (int)(ins.flags & 15u) * span);
+      hi = min(kk, lo + span);
     }
-    if (n > 1) {  // (a split copy with a sync input: same ranges through the general body)
-      const int span = (int)(ln.tile_elems / L / n);
-      const int lo = min(kk, (int)(ins.flags & 15u) * span), hi = min(kk, lo + span);
-      run_t<false, true, 0>(ln, 0, lo);
-      run_outs<false, true>(ln, lo, hi);
-      run_t<false, true, 0>(ln, hi, kk);
-      return;
-    }
-    if (cv) {
-      if (sync) run_outs<true, true>(ln, 0, kk);
-      else run_outs<true, false>(ln, 0, kk);
+    if (ext) {  // delta from an OscDeltaOp: the phase runs over the whole chunk, shaping over [lo, hi)
+      if (sync) {
+        run_t<2, true, 0>(ln, 0, lo); run_outs<2, true>(ln, lo, hi); run_t<2, true, 0>(ln, hi, kk);
+      } else {
+        run_t<2, false, 0>(ln, 0, lo); run_outs<2, false>(ln, lo, hi); run_t<2, false, 0>(ln, hi, kk);
+      }
+    } else if (cv) {  // (never split: program.cpp takes the conversion out first when warps allow)
+      if (sync) run_outs<1, true>(ln, 0, kk);
+      else run_outs<1, false>(ln, 0, kk);
+    } else if (sync) {
+      run_t<0, true, 0>(ln, 0, lo); run_outs<0, true>(ln, lo, hi); run_t<0, true, 0>(ln, hi, kk);
     } else {
-      if (sync) run_outs<false, true>(ln, 0, kk);
-      else run_outs<false, false>(ln, 0, kk);
+      advance(0, lo); run_outs<0, false>(ln, lo, hi); advance(hi, kk);
     }
   }
   __device__ __forceinline__ bool owns_state(const Instr& ins) const { return (ins.flags & 15u) == 0; }
+};
+
+// The V/oct conversion of a CV-driven oscillator on its own warp(s) (program.cpp splits it off
+// when warps are spare): delta = 440 * 2^(cv + val) / sample_rate, get_freq_in_hz (:43-48) then
+// `/ sample_rate` (:132), the same f64 operations as OscOp's DM == 1 path; the result travels as
+// the two 32-bit halves of the f64 on a pair of wires.  Stateless, so a time-split copy
+// (flags = (n << 4) | i) simply converts its n-th of every chunk.
+struct OscDeltaOp {
+  double val, sr;
+  Port p_cv, p_lo, p_hi;
+  __device__ __forceinline__ void load(const Instr& ins, const Lane& ln) {
+    val = (double)__uint_as_float(ln.pr[ins.param * L]);
+    sr = (double)ins.imm;
+    p_cv = port(ln, ins.in[0]);
+    p_lo = port(ln, ins.out[0]); p_hi = port(ln, ins.out[1]);
+  }
+  __device__ __forceinline__ void store() {}
+  __device__ __forceinline__ void run(const Instr& ins, const Lane& ln, int kk) {
+    const float* cv = p_cv.at(ln);
+    float* lo = p_lo.at(ln);
+    float* hi = p_hi.at(ln);
+    const uint32_t n = ins.flags >> 4;
+    int kb = 0, ke = kk;
+    if (n > 1) {
+      const int span = (int)(ln.tile_elems / L / n);
+      kb = min(kk, (int)(ins.flags & 15u) * span);
+      ke = min(kk, kb + span);
+    }
+    for_groups(kb, ke, [&](auto u, int k0) {
+      constexpr int U = decltype(u)::value;
+      float c[U];
+      double d[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) c[j] = cv[(k0 + j) * L];
+#pragma unroll
+      for (int j = 0; j < U; ++j) d[j] = __ddiv_rn(dmul(440.0, exp2(dadd((double)c[j], val))), sr);
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        lo[(k0 + j) * L] = __int_as_float(__double2loint(d[j]));
+        hi[(k0 + j) * L] = __int_as_float(__double2hiint(d[j]));
+      }
+    });
+  }
 };
 
 // ---- NoiseModule::calc, src/synth/oscillator.rs:381-388 (seeded generator) ----

@@ -32,8 +32,12 @@ struct Pending {
 // Rough cycles per sample of a warp that runs only this instruction (measured on B200,
 // profiles/r01j): used to balance warps over the 4 SM sub-partitions and to decide
 // which oscillators to time-split.
-int osc_phase_cost(const Pending& p) { return 25 + (p.in_vw[0] >= 0 ? 100 : 0); }  // recurrence (+ 2^cv / sr)
-int osc_shape_cost(const Pending& p) {
+int osc_phase_cost(const Pending& p) {  // the recurrence (+ 2^cv / sr when the CV is converted here)
+  if (p.ins.op == OP_OSC_DELTA) return 0;
+  return 25 + (p.in_vw[0] >= 0 ? 100 : 0) + (p.ins.n_ch ? 10 : 0);
+}
+int osc_shape_cost(const Pending& p) {  // the stateless part a time-split copy shares
+  if (p.ins.op == OP_OSC_DELTA) return 125;
   return (p.out_vw[0] >= 0 ? 90 : 0) + (p.out_vw[1] >= 0 ? 90 : 0) + (p.out_vw[2] >= 0 ? 100 : 0);
 }
 
@@ -42,7 +46,7 @@ int op_cost(const Pending& p) {
     case OP_MOOG: return p.ins.flags & F_MOOG_EXT_COEF ? 95 : 115;
     case OP_MOOG_COEF: return 45;
     case OP_GRIDSEQ: case OP_PATSEQ: return 20;
-    case OP_OSC: {
+    case OP_OSC: case OP_OSC_DELTA: {
       const int n = std::max(1, p.ins.flags >> 4);  // time-split copies share the shaping work
       return osc_phase_cost(p) + osc_shape_cost(p) / n;
     }
@@ -289,13 +293,42 @@ int compile_program(const srk_patch& patch, int max_warps, Program& prog, std::s
     // the recurrence (identical state, bit for bit) and copy i shapes only chunks with
     // chunk % n == i, so the slowest pipeline stage shrinks from phase + shape to
     // phase + shape / n.  Copy 0 alone stores the state back.
-    std::vector<int> copies(code.size(), 1);
     int spare = std::min(max_warps, kMaxWarps) - (int)code.size();
+    // First take the V/oct conversion out of CV-driven oscillators: delta = 440 * 2^(cv + val) / sr
+    // (oscillator.rs:43-48,132) is an f64 exp2 and an f64 division per sample, stateless, and four
+    // times the cost of the phase recurrence it feeds.  It becomes an OP_OSC_DELTA instruction of its
+    // own writing the f64 delta to a pair of wires; the oscillator then reads delta like a CV-less
+    // one reads its constant, and both can be time-split below.
+    {
+      std::vector<Pending> with_delta;
+      for (Pending& p : code) {
+        if (p.ins.op == OP_OSC && p.in_vw[0] >= 0 && spare > 0) {
+          --spare;
+          Pending d = p;
+          d.ins.op = OP_OSC_DELTA;
+          d.in_vw[1] = -1;
+          for (int j = 0; j < 3; ++j) d.out_vw[j] = -1;
+          for (int j = 0; j < 2; ++j) {
+            vw.push_back(VWire());
+            vw.back().last_use = 0;  // read by the oscillator below
+            d.out_vw[j] = (int)vw.size() - 1;
+            p.in_vw[2 + j] = d.out_vw[j];
+          }
+          p.in_vw[0] = -1;
+          p.ins.n_ch = 1;
+          with_delta.push_back(d);
+        }
+        with_delta.push_back(p);
+      }
+      code.swap(with_delta);
+    }
+    std::vector<int> copies(code.size(), 1);
     for (;;) {  // double the copies of the currently slowest splittable oscillator while warps last
       int best = -1, best_cost = 60;  // per-copy cost under which splitting further is pointless
       for (size_t i = 0; i < code.size(); ++i) {
         const Pending& p = code[i];
-        if (p.ins.op != OP_OSC || p.in_vw[0] >= 0 || copies[i] >= 4 || spare < copies[i]) continue;
+        const bool splittable = (p.ins.op == OP_OSC && p.in_vw[0] < 0) || p.ins.op == OP_OSC_DELTA;
+        if (!splittable || copies[i] >= 4 || spare < copies[i]) continue;
         const int c = osc_phase_cost(p) + osc_shape_cost(p) / copies[i];
         if (c > best_cost) { best = (int)i; best_cost = c; }
       }

@@ -33,6 +33,7 @@ enum Op : uint8_t {
   OP_MOOG_COEF,   // out[0..2] <- ladder coefficients (f, p, q) of a filter's CV input in[0]
   OP_GRIDSEQ,     // grid sequencer: in step, sync; out cv, gate, sync; table at aux, n_ch steps
   OP_PATSEQ,      // pattern sequencer: in step, sync; out ports flags..flags+2 of its 9; table at aux
+  OP_OSC_DELTA,   // out[0..1] <- lo / hi words of delta = 440 * 2^(cv + val) / sample_rate per sample (f64)
 };
 
 // Instr::flags
@@ -57,7 +58,8 @@ struct alignas(16) Instr {
   uint8_t warp;     // warp of the group that executes this instruction
   uint8_t stage;    // pipeline delay in chunks
   float imm;        // oscillator / ADSR sample rate
-  uint8_t n_ch;     // OUTPUT / MIX: channels covered by this instruction (1..4); sequencers: steps (1..64)
+  uint8_t n_ch;     // OUTPUT / MIX: channels covered by this instruction (1..4); sequencers: steps (1..64);
+                    // OSC: 1 = delta arrives on wires in[2] (lo) / in[3] (hi) from an OP_OSC_DELTA
   uint8_t pad[3];
 };
 static_assert(sizeof(Instr) == 32, "Instr must stay 32 bytes (staged to shared memory as uint4 pairs)");

@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(SOLO ? 32 : kMaxThreads, 1) render_voices_kern
       }
       case OP_MOOG_COEF: run_resident<dsp::MoogCoefOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_GRIDSEQ: run_resident<dsp::GridSeqOp>(ins, ln, a, n_chunks, n_iter); break;
+      case OP_OSC_DELTA: run_resident<dsp::OscDeltaOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_PATSEQ: run_resident<dsp::PatSeqOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_ADSR: run_resident<dsp::AdsrOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_NOISE: run_resident<dsp::NoiseOp>(ins, ln, a, n_chunks, n_iter); break;
@@ -245,6 +246,7 @@ __global__ void __launch_bounds__(SOLO ? 32 : kMaxThreads, 1) render_voices_kern
           case OP_MOOG: run_once<dsp::MoogOp>(ins, ln, kk); break;
           case OP_MOOG_COEF: run_once<dsp::MoogCoefOp>(ins, ln, kk); break;
           case OP_GRIDSEQ: run_once<dsp::GridSeqOp>(ins, ln, kk); break;
+          case OP_OSC_DELTA: run_once<dsp::OscDeltaOp>(ins, ln, kk); break;
           case OP_PATSEQ: run_once<dsp::PatSeqOp>(ins, ln, kk); break;
           case OP_ADSR: run_once<dsp::AdsrOp>(ins, ln, kk); break;
           case OP_NOISE: run_once<dsp::NoiseOp>(ins, ln, kk); break;

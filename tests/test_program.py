@@ -54,9 +54,10 @@ def _check_program(srk, p, n_voices, B):
             ps, cs = producers.get(s, []), consumers.get(s, [])
             assert ps and cs, "every materialised wire is written and read"
             assert len({q["stage"] for q in ps}) == 1
-            if len(ps) > 1:  # only time-split oscillator copies share a wire
+            if len(ps) > 1:  # only time-split copies (oscillators, their V/oct conversions) share a wire
                 n = ps[0]["flags"] >> 4
-                assert all(q["op"] == "OSC" and q["flags"] >> 4 == n and q["ins"][0] < 0 for q in ps) and n == len(ps)
+                assert len({q["op"] for q in ps}) == 1 and ps[0]["op"] in ("OSC", "OSC_DELTA")
+                assert all(q["flags"] >> 4 == n and (q["ins"][0] < 0) == (q["op"] == "OSC") for q in ps) and n == len(ps)
                 assert sorted(q["flags"] & 15 for q in ps) == list(range(n))
                 assert len({(q["state"], q["param"]) for q in ps}) == 1
                 assert len({q["warp"] for q in ps}) == n, "copies on one warp would be pointless"
@@ -104,12 +105,18 @@ def test_oscillators_are_time_split_only_when_pipelined(srk):
     assert [i["warp"] for i in code if i["op"] == "MOOG"] == [0]        # the critical stage, alone on sub-partition 0
     _, code = _check_program(srk, p, SOLO_V, 1024)
     assert len([i for i in code if i["op"] == "OSC"]) == 2
-    # CV-driven oscillators are not split (their phase needs 2^cv per sample)
+    # a CV-driven oscillator first loses its V/oct conversion to an OSC_DELTA stage (a wire pair carries
+    # the f64 delta); then both are time-split like a CV-less oscillator
     q = _build(srk, srk.patches.cfg3)
     _, code = _check_program(srk, q, PIPELINED_V, 1024)
-    split = [i for i in code if i["op"] == "OSC" and i["flags"] >> 4 > 1]
-    assert split and all(i["ins"][0] < 0 for i in split)
-    assert any(i["op"] == "OSC" and i["ins"][0] >= 0 and i["flags"] == 0 for i in code)
+    deltas = [i for i in code if i["op"] == "OSC_DELTA"]
+    assert deltas and all(i["ins"][0] >= 0 and i["outs"][0] >= 0 and i["outs"][1] >= 0 for i in deltas)
+    fm = [i for i in code if i["op"] == "OSC" and i["n_ch"] == 1]
+    assert fm and all(i["ins"][0] < 0 and i["ins"][2] == deltas[0]["outs"][0] and i["ins"][3] == deltas[0]["outs"][1]
+                      for i in fm)
+    assert not any(i["op"] == "OSC" and i["ins"][0] >= 0 for i in code)
+    _, code = _check_program(srk, q, SOLO_V, 1024)
+    assert not any(i["op"] == "OSC_DELTA" for i in code) and any(i["op"] == "OSC" and i["ins"][0] >= 0 for i in code)
 
 
 @pytest.mark.parametrize("B", [1, 4, 17, 64, 1024])
