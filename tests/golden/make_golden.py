@@ -24,11 +24,17 @@ CASES = {  # name: (n_voices, n_samples, buffer_size)
     "cfg3": (6, 4096, 1024),
     "cfg3b": (6, 4096, 256),
     "cfg4": (4, 30000, 1024),
+    "sequenced": (4, 24000, 1024),  # Grid + Pattern sequencers driving a voice
 }
+BUILDERS = {name: srk.patches.CONFIGS[name][0] for name in ("cfg1", "cfg2", "cfg3", "cfg3b", "cfg4")}
+BUILDERS["sequenced"] = srk.patches.sequenced
+ONLY = sys.argv[1:]  # e.g. `make_golden.py sequenced` adds one fixture without touching the others
 
 for name, (V, N, B) in CASES.items():
+    if ONLY and name not in ONLY:
+        continue
     p = orc.OraclePatch(48000, B, 2)
-    srk.patches.CONFIGS[name][0](p, V)
+    BUILDERS[name](p, V)
     stems, _ = p.render(V, N)
     np.savez_compressed(os.path.join(HERE, f"{name}.npz"), stems=stems, n_voices=V, n_samples=N, buffer_size=B)
     print(name, stems.shape, float(np.abs(stems).max()))

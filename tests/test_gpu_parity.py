@@ -81,12 +81,12 @@ def test_cfg5_graphs(srk, orc, cuda_device, idx):
     assert_mix_parity(g_mix, o_mix, 37)
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg3b", "cfg4"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg3b", "cfg4", "sequenced"])
 def test_against_committed_golden_vectors(srk, cuda_device, name):
     g = np.load(os.path.join(GOLDEN, f"{name}.npz"))
     V, N, B = int(g["n_voices"]), int(g["n_samples"]), int(g["buffer_size"])
     p = srk.Patch(srk.AudioConfig(48000, B, 2))
-    srk.patches.CONFIGS[name][0](p, V)
+    (srk.patches.sequenced if name == "sequenced" else srk.patches.CONFIGS[name][0])(p, V)
     p.plan()
     st, _ = p.render(V, N, stems=True)
     assert_parity(st, g["stems"], exact=(name == "cfg2"), what=f"golden {name}")
