@@ -2,7 +2,7 @@
  * srack_b200.h -- C ABI of the B200-native s-rack voice renderer.
  *
  * Drop-in boundary for the reference's module-graph tick (sharph/s-rack,
- * src/synth.rs + src/synth/{oscillator,filter,adsr,vca,mixer,math,output}.rs).
+ * src/synth.rs + src/synth/{oscillator,filter,adsr,vca,mixer,math,sequencer,sample,output}.rs).
  * The reference has no FFI of its own: its seam is the Rust `SynthModule`
  * trait plus the free functions `plan_execution`, `execute`, `get_catalog`.
  * Every entry point below names the reference interface (file:line) it
@@ -71,7 +71,8 @@ enum srk_kind {
   SRK_KIND_NON_LINEAR = 10, /* src/synth/math.rs        "Non-Linear"  */
   SRK_KIND_GRID_SEQUENCER = 11,    /* src/synth/sequencer.rs  "Grid Sequencer"    */
   SRK_KIND_PATTERN_SEQUENCER = 12, /* src/synth/sequencer.rs  "Pattern Sequencer" */
-  SRK_KIND_COUNT = 13
+  SRK_KIND_SAMPLE = 13,            /* src/synth/sample.rs     "Sample"            */
+  SRK_KIND_COUNT = 14
 };
 
 /* ---- parameter ids (the reference mutates struct fields from ui(); there
@@ -135,7 +136,7 @@ SRK_API const char* srk_status_string(int status);
 SRK_API int srk_catalog_size(void);
 /* Name of entry i, e.g. "Oscillator"; NULL when i is out of range. */
 SRK_API const char* srk_catalog_name(int i);
-/* srk_kind of entry i, or -1 for entries outside the hot path ("Sample", "Freeverb"). */
+/* srk_kind of entry i, or -1 for entries outside the hot path ("Freeverb"). */
 SRK_API int srk_catalog_kind(int i);
 
 /* ---- patch lifetime ----------------------------------------------------- */
@@ -197,6 +198,26 @@ SRK_API int srk_set_sequence(srk_module* m, const int32_t* cells, size_t n_steps
 /* *n_steps receives the current length; up to `cap` cells are copied out (rows x steps for the pattern). */
 SRK_API int srk_get_sequence(const srk_module* m, int32_t* cells, size_t cap, size_t* n_steps);
 
+/* ---- Sample module: the WaveBox (sample.rs:14-20) behind "Load Sample..." (sample.rs:242-257).
+ * One table per module, shared by every voice (each voice has its own play position).  As in the
+ * reference (`new = true`, sample.rs:66,212-216) a load rewinds every voice at the start of the
+ * next render: position 0, not playing; the gate detector keeps its state. ------------------- */
+/* WaveBox::load, sample.rs:32-69 (WAV parsing as hound 3.5.1 does it): RIFF/WAVE, PCM 8/16/24 bit
+ * or 32-bit float, channel 0 only, converted as sample.rs:49-54.  Malformed header: SRK_ERR_ARG,
+ * the module keeps what it had.  32-bit integer PCM or a truncated data chunk: SRK_ERR_UNSUPPORTED
+ * and -- like the reference, which has already run `samples.clear()` by then -- an EMPTY table. */
+SRK_API int srk_load_wav(srk_module* m, const void* wav_bytes, size_t n_bytes);
+/* The decoded state directly: `samples[n]` (copied) and the file's sample rate. */
+SRK_API int srk_set_sample(srk_module* m, const float* samples, size_t n, float sample_rate);
+/* *n receives the table length; up to `cap` samples are copied out. */
+SRK_API int srk_get_sample(const srk_module* m, float* samples, size_t cap, size_t* n, float* sample_rate);
+
+/* ---- WAV export of a render (the reference only reads WAV).  `planar` is
+ * [channels][n_samples] f32 as srk_render() writes `mix`; bits = 32 -> IEEE float, 16 / 24 ->
+ * PCM (x * 2^(bits-1), rounded to nearest, clamped).  Host-only, no device involved. --------- */
+SRK_API int srk_write_wav(const char* path, const float* planar, unsigned channels, size_t n_samples,
+                          uint32_t sample_rate, int bits);
+
 /* ---- planning: plan_execution(output, &all_modules, &mut plan), src/synth.rs:128-212,
  *      called as in ui.rs:63-82 (output = first Output in the module list) -------- */
 SRK_API int srk_plan(srk_patch* patch);
@@ -251,7 +272,8 @@ typedef struct srk_instr_info {
   uint8_t op;      /* 0 end, 1 ring load, 2 ring store, 3 oscillator, 4 noise, 5 moog, 6 adsr, 7 vca,
                       8 mixer, 9 math, 10 output (stems), 11 mix, 12 moog coefficients,
                       13 grid sequencer, 14 pattern sequencer (three output ports per instruction),
-                      15 oscillator V/oct conversion (delta = 440 * 2^cv / sr on a wire pair) */
+                      15 oscillator V/oct conversion (delta = 440 * 2^cv / sr on a wire pair),
+                      16 sample player */
   uint8_t flags;   /* math: operation; oscillator: (copies << 4) | copy index when time-split */
   uint8_t warp;    /* warp of the 32-voice group that executes it */
   uint8_t stage;   /* works on chunk (iteration - stage) */

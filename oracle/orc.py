@@ -15,7 +15,7 @@ _SO = os.path.join(_HERE, "_build", "libsrack_oracle.so")
 
 # numeric ids, equal to include/srack_b200.h (tests/test_abi.py checks that)
 KIND = dict(OUTPUT=0, OSCILLATOR=1, NOISE=2, ADSR=3, VCA=4, MOOG_FILTER=5, MONO_MIXER=6,
-            ADD=7, SUBTRACT=8, MULTIPLY=9, NON_LINEAR=10, GRID_SEQUENCER=11, PATTERN_SEQUENCER=12)
+            ADD=7, SUBTRACT=8, MULTIPLY=9, NON_LINEAR=10, GRID_SEQUENCER=11, PATTERN_SEQUENCER=12, SAMPLE=13)
 
 
 def build(force=False):
@@ -47,6 +47,9 @@ def lib():
         L.orc_set_param_per_voice.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
         L.orc_set_module_order.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.orc_set_sequence.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+        L.orc_set_sample.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_float]
+        L.orc_exp2f.restype = C.c_float
+        L.orc_exp2f.argtypes = [C.c_float]
         L.orc_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_reset.argtypes = [C.c_void_p]
         L.orc_render.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
@@ -118,6 +121,19 @@ class OraclePatch:
         rc = lib().orc_set_sequence(self._h, module, c.ctypes.data, c.shape[-1])
         if rc:
             raise ValueError(f"set_sequence failed rc={rc}")
+
+    def set_sample(self, module, samples, sample_rate):
+        """The WaveBox of a Sample module after a load (sample.rs:32-69): channel-0 f32 samples + file rate."""
+        a = np.ascontiguousarray(samples, dtype=np.float32)
+        rc = lib().orc_set_sample(self._h, module, a.ctypes.data, a.size, float(sample_rate))
+        if rc:
+            raise ValueError(f"set_sample failed rc={rc}")
+
+    def load_wav(self, module, data):
+        """WaveBox::load (sample.rs:32-69) through the numpy restatement in oracle/wav.py."""
+        from . import wav
+        samples, rate = wav.load(data)
+        self.set_sample(module, samples, rate)
 
     def set_module_order(self, order):
         o = np.ascontiguousarray(order, dtype=np.int32)

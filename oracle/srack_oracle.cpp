@@ -51,7 +51,7 @@ namespace {
 // ---- kinds / params: numeric ids deliberately equal to include/srack_b200.h
 enum Kind {
   K_OUTPUT = 0, K_OSC = 1, K_NOISE = 2, K_ADSR = 3, K_VCA = 4, K_MOOG = 5,
-  K_MIXER = 6, K_ADD = 7, K_SUB = 8, K_MUL = 9, K_NONLIN = 10, K_GRIDSEQ = 11, K_PATSEQ = 12, K_COUNT
+  K_MIXER = 6, K_ADD = 7, K_SUB = 8, K_MUL = 9, K_NONLIN = 10, K_GRIDSEQ = 11, K_PATSEQ = 12, K_SAMPLE = 13, K_COUNT
 };
 
 // src/synth.rs:20-25
@@ -447,6 +447,58 @@ struct PatternSequencer : Module {
   }
 };
 
+// ---- src/synth/sample.rs:14-20 (WaveBox), :72-84 (struct), :192-240 (calc).
+// Inputs 0 = Gate, 1 = CV; output 0.  The WaveBox (decoded channel-0 samples + the file's sample
+// rate) is shared by all voices of the patch; `is_new` restates WaveBox.new per instance: the
+// first calc() after a load rewinds (:212-216).  The try_lock-failed arm (:205-210) only runs
+// while the GUI thread is decoding a file and is not restated.  WaveBox::load itself (hound WAV
+// decode, :32-69) is restated in oracle/wav.py.
+struct WaveBox {
+  std::vector<float> samples;
+  float sample_rate = 0.0f;  // Default (:14)
+};
+
+// Rust `f32 as usize`: truncates toward zero, saturates, NaN -> 0.
+inline size_t f32_as_usize(float x) {
+  if (!(x > 0.0f)) return 0;                       // NaN, negatives, -0.0, +0.0
+  if (x >= 18446744073709551616.0f) return SIZE_MAX;
+  return (size_t)x;
+}
+
+struct Sample : Module {
+  std::shared_ptr<const WaveBox> wavebox = std::make_shared<WaveBox>();
+  bool is_new = false;
+  TransitionDetector det;
+  float pos = 0.0f;
+  bool playing = false;
+  float sample_rate;
+  Sample(const AudioConfig& c) : Module(K_SAMPLE, 2, 1, c.buffer_size), sample_rate((float)c.sample_rate) {}
+  void reset() override {
+    det = TransitionDetector(); pos = 0.0f; playing = false;
+    std::fill(outs[0].begin(), outs[0].end(), 0.0f);
+  }
+  bool set_param(int, float) override { return false; }
+  void calc() override {
+    const float* gate_in = resolve(0);
+    const float* cv_in = resolve(1);
+    float* output = outs[0].data();
+    const WaveBox& wb = *wavebox;
+    if (is_new) { pos = 0.0f; playing = false; is_new = false; }   // :212-216
+    for (size_t idx = 0; idx < outs[0].size(); ++idx) {
+      const bool trigger = det.is_transition(gate_in ? gate_in[idx] : 0.0f);
+      if (trigger) { pos = 0.0f; playing = true; }
+      if (f32_as_usize(pos) >= wb.samples.size()) { pos = 0.0f; playing = false; }
+      output[idx] = !wb.samples.empty() ? wb.samples[f32_as_usize(pos)] : 0.0f;
+      if (playing) {
+        // `wavebox.sample_rate / self.sample_rate * 2.0_f32.powf(cv)` (:234-235); LLVM folds
+        // pow(2.0f, x) to exp2f(x) in optimised builds -> glibc exp2f.
+        const float e = exp2f(cv_in ? cv_in[idx] : 0.0f);
+        pos += (wb.sample_rate / sample_rate) * e;
+      }
+    }
+  }
+};
+
 // ---- src/synth/output.rs:46-60.  `bufs` are kept as outs[] so they can be read.
 struct Output : Module {
   Output(const AudioConfig& c) : Module(K_OUTPUT, c.channels, c.channels, c.buffer_size) {}
@@ -484,6 +536,7 @@ std::unique_ptr<Module> make_module(int kind, const AudioConfig& cfg) {
     case K_ADD: case K_SUB: case K_MUL: case K_NONLIN: return std::make_unique<Math>(cfg, kind);
     case K_GRIDSEQ: return std::make_unique<GridSequencer>(cfg);
     case K_PATSEQ: return std::make_unique<PatternSequencer>(cfg);
+    case K_SAMPLE: return std::make_unique<Sample>(cfg);
   }
   return nullptr;
 }
@@ -587,6 +640,7 @@ struct Patch {
   std::vector<std::vector<std::optional<std::pair<int, int>>>> wiring;  // [module][input] -> (src, port)
   std::vector<ParamSetting> params;  // applied in order
   std::unordered_map<int, std::vector<int32_t>> sequences;  // module -> cells (rows x steps for the pattern sequencer)
+  std::unordered_map<int, std::shared_ptr<const WaveBox>> waves;  // Sample module -> its WaveBox
   std::vector<int> order;            // all_modules order (module indices); empty = creation order
   // voice bank
   std::vector<Instance> voices;
@@ -597,7 +651,7 @@ struct Patch {
     switch (kinds[m]) {
       case K_OUTPUT: return cfg.channels;
       case K_OSC: case K_VCA: case K_MOOG: case K_ADD: case K_SUB: case K_MUL: case K_NONLIN: return 2;
-      case K_GRIDSEQ: case K_PATSEQ: return 2;
+      case K_GRIDSEQ: case K_PATSEQ: case K_SAMPLE: return 2;
       case K_NOISE: return 0;
       case K_ADSR: return 1;
       case K_MIXER: return 4;
@@ -610,6 +664,10 @@ struct Patch {
     for (size_t m = 0; m < kinds.size(); ++m) {
       auto mod = make_module(kinds[m], cfg);
       mod->index = (int)m;
+      if (kinds[m] == K_SAMPLE) {
+        auto it = waves.find((int)m);
+        if (it != waves.end()) { static_cast<Sample*>(mod.get())->wavebox = it->second; static_cast<Sample*>(mod.get())->is_new = true; }
+      }
       if (kinds[m] == K_NOISE) {
         auto* nz = static_cast<Noise*>(mod.get());
         nz->seed = seed;
@@ -744,6 +802,27 @@ int orc_set_sequence(void* h, int module, const int32_t* cells, size_t n_steps) 
   for (size_t v = 0; v < p->voices.size(); ++v) p->apply_params(p->voices[v], p->bank_offset + v);
   return 0;
 }
+
+// What WaveBox::load leaves behind (sample.rs:32-69): channel-0 samples as f32, the file's sample
+// rate, new = true.  Every voice shares the table; each instance rewinds at its next calc().
+int orc_set_sample(void* h, int module, const float* samples, size_t n, float sample_rate) {
+  auto* p = static_cast<Patch*>(h);
+  if (module < 0 || module >= (int)p->kinds.size()) return 1;
+  if (p->kinds[module] != K_SAMPLE) return 2;
+  auto wb = std::make_shared<WaveBox>();
+  wb->samples.assign(samples, samples + n);
+  wb->sample_rate = sample_rate;
+  p->waves[module] = wb;
+  for (auto& inst : p->voices) {
+    auto* sm = static_cast<Sample*>(inst.modules[module].get());
+    sm->wavebox = wb;
+    sm->is_new = true;
+  }
+  return 0;
+}
+
+// glibc exp2f, exposed so the device restatement of it can be checked value by value.
+float orc_exp2f(float x) { return exp2f(x); }
 
 // all_modules order for plan_execution (a permutation of module indices); n == 0 restores creation order
 void orc_set_module_order(void* h, const int* order, int n) {

@@ -6,7 +6,7 @@ library and fails loudly if it has not been built; there is no CPU path.
 """
 from ._ffi import KIND, PARAM, SEQ_NONE, STATUS, LIB_PATH, grid_cell, lib  # noqa: F401
 from .synth import (AudioConfig, Patch, PortError, SrackError, SynthModule, execute, get_catalog, get_inputs,  # noqa: F401
-                    plan_execution)
+                    plan_execution, write_wav)
 from . import patches, shard  # noqa: F401
 
 __version__ = lib.srk_version().decode()

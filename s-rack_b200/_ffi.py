@@ -33,7 +33,7 @@ class srk_wire_info(C.Structure):
 
 
 OPS = ["END", "RING_LOAD", "RING_STORE", "OSC", "NOISE", "MOOG", "ADSR", "VCA", "MIXER", "MATH", "OUTPUT", "MIX",
-       "MOOG_COEF", "GRIDSEQ", "PATSEQ", "OSC_DELTA"]
+       "MOOG_COEF", "GRIDSEQ", "PATSEQ", "OSC_DELTA", "SAMPLE"]
 SEQ_NONE = -1
 
 
@@ -46,7 +46,7 @@ def grid_cell(val, hold=True):
 STATUS = dict(OK=0, ERR_ARG=1, ERR_PORT=2, ERR_KIND=3, ERR_UNSUPPORTED=4, ERR_PARAM=5, ERR_SELF_LOOP=6,
               ERR_NO_OUTPUT=7, ERR_NOT_PLANNED=8, ERR_SIZE=9, ERR_NO_DEVICE=10, ERR_CUDA=11, ERR_LIMIT=12)
 KIND = dict(OUTPUT=0, OSCILLATOR=1, NOISE=2, ADSR=3, VCA=4, MOOG_FILTER=5, MONO_MIXER=6, ADD=7, SUBTRACT=8,
-            MULTIPLY=9, NON_LINEAR=10, GRID_SEQUENCER=11, PATTERN_SEQUENCER=12)
+            MULTIPLY=9, NON_LINEAR=10, GRID_SEQUENCER=11, PATTERN_SEQUENCER=12, SAMPLE=13)
 PARAM = dict(OSC_VAL=0, OSC_ANTIALIASING=1, ADSR_A_SEC=0, ADSR_D_SEC=1, ADSR_S_VAL=2, ADSR_R_SEC=3, VCA_NEGATIVE=0,
              MOOG_FREQ=0, MOOG_RES=1, MOOG_EXP_AMT=2, MIXER_GAIN0=0, MIXER_GAIN1=1, MIXER_GAIN2=2, MIXER_GAIN3=3,
              GRIDSEQ_STEPS_PER_OCTAVE=0,             MATH_CONSTANT=0)
@@ -88,6 +88,10 @@ _SIGNATURES = {
     "srk_set_param_f32_per_voice": (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
     "srk_set_sequence": (C.c_int, [_P, C.POINTER(C.c_int32), C.c_size_t]),
     "srk_get_sequence": (C.c_int, [_P, C.POINTER(C.c_int32), C.c_size_t, C.POINTER(C.c_size_t)]),
+    "srk_load_wav": (C.c_int, [_P, _P, C.c_size_t]),
+    "srk_set_sample": (C.c_int, [_P, _P, C.c_size_t, C.c_float]),
+    "srk_get_sample": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_float)]),
+    "srk_write_wav": (C.c_int, [C.c_char_p, _P, C.c_uint, C.c_size_t, C.c_uint32, C.c_int]),
     "srk_plan": (C.c_int, [_P]),
     "srk_plan_get": (C.c_int, [_P, C.POINTER(_P), C.c_size_t, C.POINTER(C.c_size_t)]),
     "srk_plan_cuts": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -7,6 +7,7 @@
 
 #include "engine.hpp"
 #include "patch.hpp"
+#include "wav.hpp"
 
 namespace {
 
@@ -17,7 +18,7 @@ const CatalogEntry kCatalog[] = {
     {"Grid Sequencer", SRK_KIND_GRID_SEQUENCER}, {"Pattern Sequencer", SRK_KIND_PATTERN_SEQUENCER},
     {"ADSR", SRK_KIND_ADSR},             {"VCA", SRK_KIND_VCA},
     {"Moog Filter", SRK_KIND_MOOG_FILTER}, {"Mono Mixer", SRK_KIND_MONO_MIXER},
-    {"Sample", -1},                      {"Add", SRK_KIND_ADD},
+    {"Sample", SRK_KIND_SAMPLE},        {"Add", SRK_KIND_ADD},
     {"Subtract", SRK_KIND_SUBTRACT},     {"Multiply", SRK_KIND_MULTIPLY},
     {"Non-Linear", SRK_KIND_NON_LINEAR}, {"Freeverb", -1},
     {"Output", SRK_KIND_OUTPUT},
@@ -85,7 +86,7 @@ int srk_set_audio_config(srk_patch* p, const srk_audio_config* cfg) {
   if (cfg->buffer_size == 0 || cfg->sample_rate == 0) return fail(p, SRK_ERR_ARG, "zero buffer_size / sample_rate");
   p->cfg = *cfg;
   for (srk_module* m : p->modules) {
-    if (m->kind == SRK_KIND_OSCILLATOR) m->osc_sample_rate = cfg->sample_rate;  // oscillator.rs:83-84
+    if (m->kind == SRK_KIND_OSCILLATOR || m->kind == SRK_KIND_SAMPLE) m->osc_sample_rate = cfg->sample_rate;  // oscillator.rs:83-84, sample.rs:120-123
     // ADSR keeps its construction-time sample rate (adsr.rs:69-71)
     if (m->kind == SRK_KIND_OUTPUT) m->inputs.assign(cfg->channels, {nullptr, 0});  // output.rs:40-45
   }
@@ -269,6 +270,49 @@ int srk_get_sequence(const srk_module* m, int32_t* cells, size_t cap, size_t* n_
   if (n_steps) *n_steps = m->seq_steps;
   for (size_t i = 0; cells && i < cap && i < m->sequence.size(); ++i) cells[i] = m->sequence[i];
   return SRK_OK;
+}
+
+int srk_set_sample(srk_module* m, const float* samples, size_t n, float sample_rate) {
+  if (!m || (!samples && n)) return SRK_ERR_ARG;
+  if (m->kind != SRK_KIND_SAMPLE) return fail(m->patch, SRK_ERR_KIND, "module has no sample table");
+  if (n >= (1ull << 31)) return fail(m->patch, SRK_ERR_LIMIT, "sample table longer than 2^31 - 1");
+  m->wave.assign(samples, samples + n);
+  m->wave_rate = sample_rate;
+  m->wave_new = true;  // sample.rs:66
+  ++m->patch->wave_epoch;
+  ++m->patch->table_epoch;
+  return SRK_OK;
+}
+
+int srk_load_wav(srk_module* m, const void* bytes, size_t n_bytes) {
+  if (!m || (!bytes && n_bytes)) return SRK_ERR_ARG;
+  if (m->kind != SRK_KIND_SAMPLE) return fail(m->patch, SRK_ERR_KIND, "module has no sample table");
+  std::string err;
+  float rate = m->wave_rate;
+  const srk::WavStatus st = srk::wav_decode(bytes, n_bytes, m->wave, rate, err);
+  if (st == srk::WAV_BAD_HEADER) return fail(m->patch, SRK_ERR_ARG, err.c_str());
+  ++m->patch->wave_epoch;
+  ++m->patch->table_epoch;
+  if (st == srk::WAV_UNSUPPORTED) return fail(m->patch, SRK_ERR_UNSUPPORTED, err.c_str());  // table now empty (sample.rs:36,53)
+  if (m->wave.size() >= (1ull << 31)) { m->wave.clear(); return fail(m->patch, SRK_ERR_LIMIT, "sample table longer than 2^31 - 1"); }
+  m->wave_rate = rate;
+  m->wave_new = true;
+  return SRK_OK;
+}
+
+int srk_get_sample(const srk_module* m, float* samples, size_t cap, size_t* n, float* sample_rate) {
+  if (!m) return SRK_ERR_ARG;
+  if (m->kind != SRK_KIND_SAMPLE) return SRK_ERR_KIND;
+  if (n) *n = m->wave.size();
+  if (sample_rate) *sample_rate = m->wave_rate;
+  for (size_t i = 0; samples && i < cap && i < m->wave.size(); ++i) samples[i] = m->wave[i];
+  return SRK_OK;
+}
+
+int srk_write_wav(const char* path, const float* planar, unsigned channels, size_t n_samples, uint32_t sample_rate,
+                  int bits) {
+  std::string err;
+  return srk::wav_write(path, planar, channels, n_samples, sample_rate, bits, err) ? SRK_OK : SRK_ERR_ARG;
 }
 
 int srk_plan(srk_patch* p) {

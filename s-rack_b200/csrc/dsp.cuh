@@ -98,7 +98,8 @@ struct Lane {
   uint32_t chunk;      // chunk the current instruction works on
   uint32_t voice;      // global voice index (noise key)
   uint32_t seed_lo, seed_hi;
-  const int32_t* tables;  // sequencer step tables (shared memory, uniform over voices)
+  const int32_t* tables;  // sequencer step tables / WaveDescs (shared memory, uniform over voices)
+  const float* waves;     // Sample modules' tables (HBM, uniform over voices)
 };
 
 __device__ __forceinline__ float* wire(const Lane& ln, int slot) {
@@ -1145,6 +1146,98 @@ struct PatSeqOp {
         }
         out[j][k * L] = v;
       }
+    }
+  }
+};
+
+// ---- glibc 2.39 exp2f (sysdeps/ieee754/flt-32/e_exp2f.c), restated operation by operation ----
+// The Sample module's playback rate is `ratio * 2.0_f32.powf(cv)` (sample.rs:234-235) -> exp2f of
+// the platform libm, and its result steers an INDEX: a 1-ulp difference moves the play position
+// and eventually picks another table entry, so "a few ulp" is not good enough here.  glibc's
+// algorithm is short and all in f64: x = k/32 + r, 2^x = 2^(k/32) * (1 + C2 r + r^2 (C1 + C0 r)),
+// rounded to f32 once at the end.  Checked on the CPU against glibc for every one of the 2^32
+// inputs, with and without FMA contraction (both agree; tests/test_sample.py samples it, and the
+// GPU test compares the device result with the oracle's glibc call).
+static __device__ const unsigned long long kExp2fTab[32] = {
+    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,
+    0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull,
+    0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
+    0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull,
+    0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,
+    0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,
+    0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
+    0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull,
+};
+__device__ __forceinline__ float exp2f_glibc(float x) {
+  const double xd = (double)x;
+  const double shift = 0x1.8p+52 / 32.0;
+  double kd = dadd(xd, shift);
+  const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
+  kd = dsub(kd, shift);
+  const double r = dsub(xd, kd);
+  const unsigned long long t = __ldg(&kExp2fTab[ki & 31u]) + (ki << 47);
+  const double s = __longlong_as_double((long long)t);
+  const double z = dadd(dmul(0x1.c6af84b912394p-5, r), 0x1.ebfce50fac4f3p-3);
+  const double r2 = dmul(r, r);
+  double y = dadd(dmul(0x1.62e42ff0c52d6p-1, r), 1.0);
+  y = dadd(dmul(z, r2), y);
+  y = dmul(y, s);
+  float out = __double2float_rn(y);
+  // |x| >= 128 (and NaN): overflow, underflow, x + x  (e_exp2f.c special cases)
+  out = x >= 128.0f ? __int_as_float(0x7f800000) : out;
+  out = x <= -150.0f ? 0.0f : out;
+  return x != x ? fadd(x, x) : out;
+}
+
+// ---- SampleModule::calc, src/synth/sample.rs:192-240 --------------------------------------
+// Inputs gate, cv; one output.  The table (WaveBox.samples) is uniform over voices and stays in
+// HBM -- a per-lane gather through the read-only path; per voice: play position (f32), playing,
+// gate detector.  `pos as usize` is Rust's saturating cast (NaN / negative -> 0) == cvt.rzi.u32.
+struct SampleOp {
+  uint32_t* s;
+  float pos, ratio;
+  bool playing, last;
+  const float* wave;
+  uint32_t len;
+  Port p_gate, p_cv, p_out;
+
+  __device__ __forceinline__ void load(const Instr& ins, const Lane& ln) {
+    s = ln.st + ins.state * L;
+    pos = __uint_as_float(s[0]);
+    playing = s[L] & 1u;
+    last = (s[L] >> 1) & 1u;
+    const WaveDesc* d = reinterpret_cast<const WaveDesc*>(ln.tables + ins.aux);
+    wave = ln.waves + d->offset;
+    len = d->len;
+    ratio = d->ratio;
+    if (d->is_new && ln.chunk == 0) { pos = 0.0f; playing = false; }  // :212-216, first block after a load
+    p_gate = port(ln, ins.in[0]); p_cv = port(ln, ins.in[1]); p_out = port(ln, ins.out[0]);
+  }
+  __device__ __forceinline__ void store() {
+    s[0] = __float_as_uint(pos);
+    s[L] = (playing ? 1u : 0u) | (last ? 2u : 0u);
+  }
+  __device__ __forceinline__ void run(const Instr&, const Lane& ln, int kk) {
+    const float* gate = p_gate.at(ln);
+    const float* cv = p_cv.at(ln);
+    float* out = p_out.at(ln);
+#pragma unroll 2
+    for (int k = 0; k < kk; ++k) {
+      const float g = gate ? gate[k * L] : 0.0f;
+      const bool above = g > 0.0f;
+      const bool trigger = above & !last;              // :219-221
+      last = above;
+      pos = trigger ? 0.0f : pos;                      // :222-225
+      playing |= trigger;
+      uint32_t idx = __float2uint_rz(pos);
+      const bool past = idx >= len;                    // :226-229
+      pos = past ? 0.0f : pos;
+      playing &= !past;
+      idx = past ? 0u : idx;
+      const float x = len ? __ldg(wave + idx) : 0.0f;  // :230-234
+      if (out) out[k * L] = x;
+      const float e = cv ? exp2f_glibc(cv[k * L]) : 1.0f;
+      pos = playing ? fadd(pos, fmul(ratio, e)) : pos; // :235-238
     }
   }
 };

@@ -86,14 +86,14 @@ struct Engine {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // call start, kernel start, kernel end, call end
   bool timed = false;
   Program prog;
-  uint64_t compiled_epoch = 0, uploaded_param_epoch = 0, compiled_table_epoch = 0;
+  uint64_t compiled_epoch = 0, uploaded_param_epoch = 0, compiled_table_epoch = 0, uploaded_wave_epoch = 0;
   int compiled_max_warps = 0;       // schedule the program was compiled for
   int chunk = 0;                    // samples per chunk (K) for the compiled program
   std::vector<uint4> blob;          // device image of the program (see RenderArgs::blob)
   size_t V = 0, voice_offset = 0;
   uint64_t n_abs = 0;  // samples rendered since reset
   bool state_valid = false;
-  DevBuf d_prog, d_state, d_state_init, d_params, d_rings, d_partial, d_stems, d_mix;
+  DevBuf d_prog, d_state, d_state_init, d_params, d_rings, d_partial, d_stems, d_mix, d_waves;
   uint32_t* h_params = nullptr;  // pinned staging
   size_t h_params_bytes = 0;
   uint64_t launches = 0;
@@ -105,7 +105,7 @@ struct Engine {
   ~Engine() {
     if (device >= 0) {
       cudaSetDevice(device);
-      for (auto* b : {&d_prog, &d_state, &d_state_init, &d_params, &d_rings, &d_partial, &d_stems, &d_mix}) b->release();
+      for (auto* b : {&d_prog, &d_state, &d_state_init, &d_params, &d_rings, &d_partial, &d_stems, &d_mix, &d_waves}) b->release();
       if (h_params) cudaFreeHost(h_params);
       for (auto& e : ev)
         if (e) cudaEventDestroy(e);
@@ -338,6 +338,20 @@ static int engine_prepare(srk_patch* patch, size_t n_voices, size_t voice_offset
     e.compiled_max_warps = want_warps;
     e.compiled_table_epoch = patch->table_epoch;
     fresh = rewired;
+    e.uploaded_wave_epoch = 0;  // WaveDesc offsets follow the plan: re-concatenate
+  }
+  if (e.uploaded_wave_epoch != patch->wave_epoch) {
+    // Sample tables (WaveBox.samples), back to back in the order compile_program laid them out
+    SRK_CUDA(e.d_waves.ensure(std::max<size_t>(e.prog.wave_total, 1) * sizeof(float)));
+    size_t off = 0;
+    for (int mi : e.prog.wave_modules) {
+      const std::vector<float>& w = patch->modules[mi]->wave;
+      if (!w.empty())
+        SRK_CUDA(cudaMemcpyAsync((float*)e.d_waves.p + off, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice, e.stream));
+      off += w.size();
+    }
+    SRK_CUDA(cudaStreamSynchronize(e.stream));  // pageable host vectors may change after we return
+    e.uploaded_wave_epoch = patch->wave_epoch;
   }
   if (fresh || e.V != n_voices || e.voice_offset != voice_offset || !e.state_valid) {
     e.V = n_voices;
@@ -406,6 +420,7 @@ int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t
   a.rings = (float*)e.d_rings.p;
   a.stems = d_stems;
   a.partial = mix ? (float*)e.d_partial.p : nullptr;
+  a.waves = (const float*)e.d_waves.p;
   a.blob_vec = (uint32_t)e.blob.size();
   a.table_off = (uint32_t)blob_table_offset(prog);
   a.n_instr = (uint32_t)prog.code.size();
@@ -446,6 +461,10 @@ int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t
   SRK_CUDA(cudaEventRecord(e.ev[3], work));
   e.timed = true;
   e.n_abs += n_samples;
+  // WaveBox.new is consumed by the first calc() after a load (sample.rs:212-216): the program image of
+  // the next render carries is_new = 0 again
+  for (int mi : prog.wave_modules)
+    if (patch->modules[mi]->wave_new) { patch->modules[mi]->wave_new = false; ++patch->table_epoch; }
   e.block_threads = T;
   e.step = K;
   e.n_warps = (int)prog.n_warps;

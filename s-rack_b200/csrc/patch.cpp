@@ -33,6 +33,8 @@ const KindInfo kKinds[SRK_KIND_COUNT] = {
   {"Grid Sequencer", 2, 3, {"Step", "Sync", nullptr, nullptr}, {"CV", "Gate", "Sync"}, 1, {12.0f, 0, 0, 0}, {true, false, false, false}},
   // Pattern sequencer: sequencer.rs:551-596: 8 gate rows labelled "0".."7", then "Sync"
   {"Pattern Sequencer", 2, 9, {"Step", "Sync", nullptr, nullptr}, {"0", "1", "2", "3", "4", "5", "6", "7", "Sync"}, 0, {0, 0, 0, 0}, {false, false, false, false}},
+  // Sample: sample.rs:163-190 (inputs "Gate", "CV"; one unlabelled output), no numeric parameters
+  {"Sample",       2, 1, {"Gate", "CV", nullptr, nullptr}, {nullptr, nullptr, nullptr}, 0, {0, 0, 0, 0}, {false, false, false, false}},
 };
 // clang-format on
 }  // namespace

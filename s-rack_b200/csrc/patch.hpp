@@ -45,7 +45,11 @@ struct srk_module {
   // Sequencers: the step table (sequencer.rs:18,341), -1 = None; rows x seq_steps for the pattern
   std::vector<int32_t> sequence;
   size_t seq_steps = 0;
-  uint16_t osc_sample_rate = 0;  // Oscillator: follows set_audio_config (oscillator.rs:83-84)
+  // Sample: the WaveBox (sample.rs:14-20): decoded channel-0 samples, the file's rate, `new`
+  std::vector<float> wave;
+  float wave_rate = 0.0f;
+  bool wave_new = false;
+  uint16_t osc_sample_rate = 0;  // Oscillator / Sample: follows set_audio_config (oscillator.rs:83-84, sample.rs:120-123)
   float adsr_sample_rate = 0;    // ADSR: fixed at construction (adsr.rs:47,69-71)
   int n_outputs() const;
 };
@@ -63,6 +67,7 @@ struct srk_patch {
   uint64_t wiring_epoch = 1;  // bumped by every wiring / list change
   uint64_t param_epoch = 1;   // bumped by every parameter change
   uint64_t table_epoch = 1;   // bumped by every sequence-table change (program image, not state)
+  uint64_t wave_epoch = 1;    // bumped by every Sample table change (device copy of the waves)
   std::string last_error;
   std::unique_ptr<srk::Engine, void (*)(srk::Engine*)> engine{nullptr, nullptr};
 

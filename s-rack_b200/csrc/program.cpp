@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 
 #include "patch.hpp"
@@ -46,6 +47,7 @@ int op_cost(const Pending& p) {
     case OP_MOOG: return p.ins.flags & F_MOOG_EXT_COEF ? 95 : 115;
     case OP_MOOG_COEF: return 45;
     case OP_GRIDSEQ: case OP_PATSEQ: return 20;
+    case OP_SAMPLE: return p.in_vw[1] >= 0 ? 70 : 40;
     case OP_OSC: case OP_OSC_DELTA: {
       const int n = std::max(1, p.ins.flags >> 4);  // time-split copies share the shaping work
       return osc_phase_cost(p) + osc_shape_cost(p) / n;
@@ -209,6 +211,22 @@ int compile_program(const srk_patch& patch, int max_warps, Program& prog, std::s
         p.ins.imm = 1.0f / (float)(uint16_t)mod->param[SRK_GRIDSEQ_STEPS_PER_OCTAVE];
         prog.tables.insert(prog.tables.end(), mod->sequence.begin(), mod->sequence.end());
         break;
+      case SRK_KIND_SAMPLE: {
+        p.ins.op = OP_SAMPLE;
+        p.ins.state = alloc_state(kStateSample, {0u, 1u << 1});  // pos 0.0, not playing, gate detector last = true
+        p.ins.aux = (uint16_t)prog.tables.size();
+        WaveDesc d;
+        d.offset = (uint32_t)prog.wave_total;
+        d.len = (uint32_t)mod->wave.size();
+        d.ratio = mod->wave_rate / (float)mod->osc_sample_rate;  // f32 division, as sample.rs:234
+        d.is_new = mod->wave_new ? 1u : 0u;
+        int32_t words[4];
+        std::memcpy(words, &d, sizeof d);
+        prog.tables.insert(prog.tables.end(), words, words + 4);
+        prog.wave_modules.push_back(m);
+        prog.wave_total += mod->wave.size();
+        break;
+      }
       case SRK_KIND_PATTERN_SEQUENCER: {
         // 9 output ports, 3 per instruction; every instruction keeps its own copy of the step
         // counter (identical evolution), triples nobody reads are not emitted

@@ -34,6 +34,7 @@ enum Op : uint8_t {
   OP_GRIDSEQ,     // grid sequencer: in step, sync; out cv, gate, sync; table at aux, n_ch steps
   OP_PATSEQ,      // pattern sequencer: in step, sync; out ports flags..flags+2 of its 9; table at aux
   OP_OSC_DELTA,   // out[0..1] <- lo / hi words of delta = 440 * 2^(cv + val) / sample_rate per sample (f64)
+  OP_SAMPLE,      // sample player: in gate, cv; out[0]; descriptor (WaveDesc) at tables[aux]
 };
 
 // Instr::flags
@@ -70,6 +71,16 @@ struct WireDesc {
   uint16_t mask;
 };
 
+// A Sample module's table as the device sees it: four words in Program::tables (uniform over voices).
+// The samples themselves stay in HBM (RenderArgs::waves), all modules' tables back to back.
+struct WaveDesc {
+  uint32_t offset;  // first sample inside the concatenated wave buffer
+  uint32_t len;     // samples (< 2^31)
+  float ratio;      // wavebox.sample_rate / self.sample_rate, the f32 quotient (sample.rs:234)
+  uint32_t is_new;  // WaveBox.new (sample.rs:212-216): rewind at the start of this render
+};
+static_assert(sizeof(WaveDesc) == 16, "WaveDesc is four table words");
+
 // Per-voice state words (u32 slots, SoA [word][voice] in HBM)
 //   OSC   : pos (f64, 2 words), sync_last                         oscillator.rs:21,23
 //   NOISE : sample counter (u64, 2 words)
@@ -77,7 +88,8 @@ struct WireDesc {
 //   ADSR  : phase, r_val, from_a_val, mode | gate_last << 8        adsr.rs:14-21
 //   GRIDSEQ : current_step | step_last << 16 | sync_last << 17, last cv   sequencer.rs:24-27
 //   PATSEQ  : current_step | step_last << 16 | sync_last << 17 (one copy per instruction)
-constexpr int kStateOsc = 3, kStateNoise = 2, kStateMoog = 10, kStateAdsr = 4, kStateGridSeq = 2, kStatePatSeq = 1;
+//   SAMPLE  : pos (f32), playing | gate_last << 1                    sample.rs:78-82
+constexpr int kStateOsc = 3, kStateNoise = 2, kStateMoog = 10, kStateAdsr = 4, kStateGridSeq = 2, kStatePatSeq = 1, kStateSample = 2;
 // Per-voice parameter words (SoA [word][voice] in HBM)
 //   OSC   : val, delta (f64, 2 words; host-computed 440*2^val/sr, used when CV is None), antialiasing (0/1)
 //   MOOG  : freq, res, exp_amt        ADSR : a_sec, d_sec, s_val, r_sec
@@ -94,7 +106,9 @@ struct Program {
   std::vector<Instr> code;             // sorted by (warp, plan order), terminated by OP_END
   std::vector<uint16_t> warp_begin;    // n_warps + 1 offsets into `code`
   std::vector<WireDesc> wires;         // one per wire slot
-  std::vector<int32_t> tables;         // sequencer step tables (uniform over voices), Instr::aux indexes it
+  std::vector<int32_t> tables;         // sequencer step tables / WaveDescs (uniform over voices), Instr::aux indexes it
+  std::vector<int> wave_modules;       // Sample modules (patch list index) in the order their tables are concatenated
+  uint64_t wave_total = 0;             // samples in the concatenated wave buffer
   std::vector<uint32_t> state_init;    // one initial value per state word
   std::vector<ParamSource> param_src;  // one per parameter word
   uint32_t n_tiles = 0;                // wire tiles per group

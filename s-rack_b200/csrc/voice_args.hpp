@@ -17,6 +17,7 @@ struct RenderArgs {
   float* rings;
   float* stems;
   float* partial;
+  const float* waves;     // Sample modules' tables back to back (WaveDesc::offset indexes it)
   uint32_t blob_vec;      // blob size in uint4
   uint32_t table_off;     // byte offset of the sequencer tables inside the blob
   uint32_t n_instr, n_wires, n_warps, n_stages, n_tiles;

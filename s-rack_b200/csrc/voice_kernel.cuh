@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(SOLO ? 32 : kMaxThreads, 1) render_voices_kern
   __syncthreads();
 
   dsp::Lane ln{st + lane, pr + lane, tiles + lane, wd, a.K * 32, 0, a.voice_offset + v, a.seed_lo, a.seed_hi,
-               reinterpret_cast<const int32_t*>(smem_raw + a.table_off)};
+               reinterpret_cast<const int32_t*>(smem_raw + a.table_off), a.waves};
   const uint32_t pc0 = warp_begin[wid], pc1 = warp_begin[wid + 1];
   const uint32_t K = a.K;
   const uint32_t n_chunks = (a.n_samples + K - 1) / K;
@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(SOLO ? 32 : kMaxThreads, 1) render_voices_kern
       case OP_GRIDSEQ: run_resident<dsp::GridSeqOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_OSC_DELTA: run_resident<dsp::OscDeltaOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_PATSEQ: run_resident<dsp::PatSeqOp>(ins, ln, a, n_chunks, n_iter); break;
+      case OP_SAMPLE: run_resident<dsp::SampleOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_ADSR: run_resident<dsp::AdsrOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_NOISE: run_resident<dsp::NoiseOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_VCA: run_resident<dsp::VcaOp>(ins, ln, a, n_chunks, n_iter); break;
@@ -248,6 +249,7 @@ __global__ void __launch_bounds__(SOLO ? 32 : kMaxThreads, 1) render_voices_kern
           case OP_GRIDSEQ: run_once<dsp::GridSeqOp>(ins, ln, kk); break;
           case OP_OSC_DELTA: run_once<dsp::OscDeltaOp>(ins, ln, kk); break;
           case OP_PATSEQ: run_once<dsp::PatSeqOp>(ins, ln, kk); break;
+          case OP_SAMPLE: run_once<dsp::SampleOp>(ins, ln, kk); break;
           case OP_ADSR: run_once<dsp::AdsrOp>(ins, ln, kk); break;
           case OP_NOISE: run_once<dsp::NoiseOp>(ins, ln, kk); break;
           case OP_VCA: run_once<dsp::VcaOp>(ins, ln, kk); break;

@@ -260,6 +260,45 @@ def sequenced(b, n_voices, seed=SEED):
                 vca2=vca2, mix=mix, out=out)
 
 
+def sampler_wave(n=6000, rate=22050.0):
+    """A deterministic test table for the Sample module: a decaying two-partial pluck, f32."""
+    t = np.arange(n, dtype=np.float64) / rate
+    x = np.exp(-6.0 * t) * (0.7 * np.sin(2 * np.pi * 220.0 * t) + 0.3 * np.sin(2 * np.pi * 663.0 * t + 0.5))
+    return x.astype(np.float32), np.float32(rate)
+
+
+def sampler(b, n_voices, seed=SEED, cv=True):
+    """a Sample module (sample.rs) retriggered by a per-voice clock, its playback
+    rate bent by a slow sine through the CV input (`ratio * 2^cv`, an index path: bit-exact or
+    nothing), shaped by an ADSR-driven VCA; the raw player goes to channel 1."""
+    clock = b.module_create("OSCILLATOR")
+    lfo = b.module_create("OSCILLATOR")
+    depth = b.module_create("MULTIPLY")
+    smp = b.module_create("SAMPLE")
+    adsr = b.module_create("ADSR")
+    vca = b.module_create("VCA")
+    out = b.module_create("OUTPUT")
+    b.set_seed(seed)
+    rate = 3.0 + 9.0 * uniform01(seed, 6, n_voices)  # retriggers per second
+    b.set_param_per_voice(clock, P["OSC_VAL"], np.log2(rate / 440.0).astype(np.float32))
+    b.set_param(lfo, P["OSC_VAL"], hz_to_val(1.3))
+    b.set_param_per_voice(depth, P["MATH_CONSTANT"], _u(seed, 7, n_voices, 0.0, 1.5))
+    wave, wave_rate = sampler_wave()
+    b.set_sample(smp, wave, wave_rate)
+    for pid, v in zip(("ADSR_A_SEC", "ADSR_D_SEC", "ADSR_S_VAL", "ADSR_R_SEC"), (0.001, 0.05, 0.4, 0.03)):
+        b.set_param(adsr, P[pid], v)
+    b.connect(depth, 0, lfo, SINE)
+    b.connect(smp, 0, clock, SQUARE)
+    if cv:
+        b.connect(smp, 1, depth, 0)
+    b.connect(adsr, 0, clock, SQUARE)
+    b.connect(vca, 0, smp, 0)
+    b.connect(vca, 1, adsr, 0)
+    b.connect(out, 0, vca, 0)
+    b.connect(out, 1, smp, 0)
+    return dict(clock=clock, lfo=lfo, depth=depth, sample=smp, adsr=adsr, vca=vca, out=out)
+
+
 # name -> (builder, BASELINE voice count, description)
 CONFIGS = {
     "cfg1": (cfg1, 1, "single sine Oscillator->Output, 1 voice, 48000 samples"),

@@ -136,6 +136,24 @@ class SynthModule:
         a = np.array(buf, dtype=np.int32)
         return a.reshape(rows, n.value) if rows > 1 else a
 
+    # Sample module: the WaveBox behind "Load Sample..." (sample.rs:14-20, 242-257)
+    def load_wav(self, data):
+        """WaveBox::load (sample.rs:32-69): WAV file bytes -> channel-0 f32 table + the file's rate."""
+        data = bytes(data)
+        self._check(lib.srk_load_wav(self._h, data, len(data)))
+
+    def set_sample(self, samples, sample_rate):
+        a = np.ascontiguousarray(samples, dtype=np.float32)
+        self._check(lib.srk_set_sample(self._h, a.ctypes.data, a.size, float(sample_rate)))
+
+    def get_sample(self):
+        """-> (samples f32, sample_rate)"""
+        n, rate = C.c_size_t(), C.c_float()
+        self._check(lib.srk_get_sample(self._h, None, 0, C.byref(n), C.byref(rate)))
+        a = np.empty(n.value, dtype=np.float32)
+        self._check(lib.srk_get_sample(self._h, a.ctypes.data, a.size, C.byref(n), C.byref(rate)))
+        return a, rate.value
+
 
 def _pid(param):
     return PARAM[param] if isinstance(param, str) else int(param)
@@ -240,6 +258,12 @@ class Patch:
     def set_sequence(self, module, cells):
         module.set_sequence(cells)
 
+    def set_sample(self, module, samples, sample_rate):
+        module.set_sample(samples, sample_rate)
+
+    def load_wav(self, module, data):
+        module.load_wav(data)
+
     # -- planning ------------------------------------------------------------
     def plan(self):
         """plan_execution (synth.rs:128-212) -> modules in execution order."""
@@ -323,6 +347,16 @@ def plan_execution(patch):
 
 def execute(patch, n_voices, **kw):
     return patch.execute(n_voices, **kw)
+
+
+def write_wav(path, planar, sample_rate=48000, bits=32):
+    """WAV export of a render (`mix` [C][N] as Patch.render returns it): 32-bit float or 16/24-bit PCM."""
+    a = np.ascontiguousarray(planar, dtype=np.float32)
+    if a.ndim == 1:
+        a = a[None, :]
+    rc = lib.srk_write_wav(str(path).encode(), a.ctypes.data, a.shape[0], a.shape[1], int(sample_rate), int(bits))
+    if rc:
+        raise SrackError(rc, f"cannot write {path}")
 
 
 def get_catalog():

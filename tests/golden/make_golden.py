@@ -25,9 +25,11 @@ CASES = {  # name: (n_voices, n_samples, buffer_size)
     "cfg3b": (6, 4096, 256),
     "cfg4": (4, 30000, 1024),
     "sequenced": (4, 24000, 1024),  # Grid + Pattern sequencers driving a voice
+    "sampler": (4, 24000, 1024),    # Sample module with a bent playback rate
 }
 BUILDERS = {name: srk.patches.CONFIGS[name][0] for name in ("cfg1", "cfg2", "cfg3", "cfg3b", "cfg4")}
 BUILDERS["sequenced"] = srk.patches.sequenced
+BUILDERS["sampler"] = srk.patches.sampler
 ONLY = sys.argv[1:]  # e.g. `make_golden.py sequenced` adds one fixture without touching the others
 
 for name, (V, N, B) in CASES.items():

@@ -81,15 +81,15 @@ def test_cfg5_graphs(srk, orc, cuda_device, idx):
     assert_mix_parity(g_mix, o_mix, 37)
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg3b", "cfg4", "sequenced"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg3b", "cfg4", "sequenced", "sampler"])
 def test_against_committed_golden_vectors(srk, cuda_device, name):
     g = np.load(os.path.join(GOLDEN, f"{name}.npz"))
     V, N, B = int(g["n_voices"]), int(g["n_samples"]), int(g["buffer_size"])
     p = srk.Patch(srk.AudioConfig(48000, B, 2))
-    (srk.patches.sequenced if name == "sequenced" else srk.patches.CONFIGS[name][0])(p, V)
+    (getattr(srk.patches, name) if name in ("sequenced", "sampler") else srk.patches.CONFIGS[name][0])(p, V)
     p.plan()
     st, _ = p.render(V, N, stems=True)
-    assert_parity(st, g["stems"], exact=(name == "cfg2"), what=f"golden {name}")
+    assert_parity(st, g["stems"], exact=(name in ("cfg2", "sampler")), what=f"golden {name}")
 
 
 def test_every_module_kind_and_port(srk, orc, cuda_device):
@@ -418,7 +418,54 @@ def test_sequence_edit_keeps_voice_state(srk, orc, cuda_device):
     assert_parity(g[0], o[0], what="voice after edits")
 
 
-@pytest.mark.parametrize("name,B", [("cfg2", 1024), ("cfg4", 1024), ("cfg3b", 256), ("cfg5_two_osc", 1024), ("sequenced", 1024)])
+def test_sampler_patch_is_bit_exact(srk, orc, cuda_device):
+    """Sample module: the play position is an index path -- the rate goes through the
+    device's restatement of glibc exp2f -- so anything short of equal bits would show as wrong table
+    entries.  Channel 1 is the raw player, channel 0 the enveloped one."""
+    for cv in (True, False):
+        gp, op, g, g_mix, o, o_mix = render_pair(srk, orc, srk.patches.sampler, 70, 26000, cv=cv)
+        assert np.abs(o[1]).max() > 0.3
+        assert_parity(g, o, exact=True, what=f"sampler cv={cv}")
+        assert_mix_parity(g_mix, o_mix, 70)
+    # many voices x a bent rate: ~1.7e7 exp2f results steering indices, one-warp schedule
+    gp, op, g, g_mix, o, o_mix = render_pair(srk, orc, srk.patches.sampler, 2048, 8192)
+    assert_parity(g, o, exact=True, what="sampler 2048 voices")
+
+
+def test_sample_reload_rewinds_and_keeps_the_detector(srk, orc, cuda_device):
+    """WaveBox.new (sample.rs:66,212-216): a load rewinds every voice at the start of the next block and
+    playback waits for the next gate edge; envelope and clock state carry on.  Also a WAV load through
+    both decoders, an empty table, and reset()."""
+    V, B = 40, 4096
+    gp, op, gh, oh = build_both(srk, orc, srk.patches.sampler, V, buffer_size=B)
+    gp.plan()
+    wave2 = (np.linspace(-1, 1, 997) ** 3).astype(np.float32)
+    import io, wave as wavmod
+    buf = io.BytesIO()
+    with wavmod.open(buf, "wb") as w:
+        w.setnchannels(2); w.setsampwidth(2); w.setframerate(32000)
+        w.writeframes((np.stack([wave2, -wave2], 1) * 32767).astype("<i2").tobytes())
+    parts_g, parts_o = [], []
+    for k in range(4):
+        parts_g.append(gp.render(V, 2 * B, stems=True)[0])
+        parts_o.append(op.render(V, 2 * B)[0])
+        if k == 0:
+            gp.set_sample(gh["sample"], wave2, 96000.0); op.set_sample(oh["sample"], wave2, 96000.0)
+        elif k == 1:
+            gp.load_wav(gh["sample"], buf.getvalue()); op.load_wav(oh["sample"], buf.getvalue())
+        elif k == 2:
+            gp.set_sample(gh["sample"], np.zeros(0, np.float32), 48000.0)
+            op.set_sample(oh["sample"], np.zeros(0, np.float32), 48000.0)
+    g, o = np.concatenate(parts_g, axis=1), np.concatenate(parts_o, axis=1)
+    assert np.abs(o[1, 2 * B:6 * B]).max() > 0.3 and (o[1, 6 * B:] == 0).all()
+    assert_parity(g, o, exact=True, what="sampler across reloads")
+    gp.reset(); op.reset()
+    gp.set_sample(gh["sample"], wave2, 8000.0); op.set_sample(oh["sample"], wave2, 8000.0)
+    assert_parity(gp.render(V, 3 * B, stems=True)[0], op.render(V, 3 * B)[0], exact=True, what="sampler after reset")
+
+
+@pytest.mark.parametrize("name,B", [("cfg2", 1024), ("cfg4", 1024), ("cfg3b", 256), ("cfg5_two_osc", 1024), ("sequenced", 1024),
+                                    ("sampler", 1024)])
 def test_schedule_invariance(srk, orc, cuda_device, monkeypatch, name, B):
     """The same patch rendered as one warp per voice group in plan order (SRK_WARPS=1) and as a
     software pipeline over 4/16 warps, with different chunk sizes, gives the same bits: the
