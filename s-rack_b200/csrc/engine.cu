@@ -192,9 +192,28 @@ static bool pipelined_pays(const Engine& e, const Program& prog, size_t V) {
   return env_int("SRK_WARPS", 0) > 0 || 2 * per_sm * prog.max_cost <= 3 * (size_t)prog.sum_cost;
 }
 
-static size_t smem_bytes_for(const Program& prog, size_t blob_vec, int K) {
+static size_t smem_bytes_for(const Program& prog, size_t blob_vec, int K, int groups_per_block = 1) {
   return blob_vec * 16 + ((size_t)prog.state_init.size() + prog.param_src.size() + (size_t)prog.n_tiles * K) *
-                             kVoicesPerGroup * sizeof(uint32_t);
+                             kVoicesPerGroup * sizeof(uint32_t) * groups_per_block;
+}
+
+// One-warp schedule: how many voice groups (warps) share a thread block.  All groups of the launch
+// should be resident at once and spread evenly, and the warps of one SM should sit in as few blocks
+// as possible -- the per-chunk barrier keeps a block's warps in the same op bodies, which is what
+// makes the instruction caches work (profiles/r03c: 33 % "no instruction" stalls with 14 independent
+// one-warp blocks per SM).
+static int choose_solo_groups(const Engine& e, const Program& prog, size_t blob_vec, int K, size_t V) {
+  const size_t groups = (V + kVoicesPerGroup - 1) / kVoicesPerGroup;
+  const size_t n_sm = (size_t)std::max(e.n_sm, 1);
+  const size_t per_sm = std::max<size_t>((groups + n_sm - 1) / n_sm, 1);
+  int G = env_int("SRK_SOLO_GROUPS", 0);
+  if (G <= 0) {
+    const size_t blocks_per_sm = (per_sm + kMaxWarps - 1) / kMaxWarps;
+    G = (int)((per_sm + blocks_per_sm - 1) / blocks_per_sm);
+  }
+  G = std::max(1, std::min(G, (int)kMaxWarps));
+  while (G > 1 && smem_bytes_for(prog, blob_vec, K, G) > (size_t)e.smem_optin) --G;
+  return G;
 }
 
 // Samples per chunk (a power of two) for this program and render length; 0 when it cannot fit.
@@ -397,8 +416,10 @@ int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t
   const size_t C = prog.channels;
   const int K = chunk_for_length(prog, e.chunk, n_samples);  // <= e.chunk, which fitted
   const int T = (int)prog.n_warps * 32;
-  const size_t smem = smem_bytes_for(prog, e.blob.size(), K);
-  const unsigned grid = (unsigned)((n_voices + kVoicesPerGroup - 1) / kVoicesPerGroup);
+  const unsigned n_groups = (unsigned)((n_voices + kVoicesPerGroup - 1) / kVoicesPerGroup);
+  const int G = prog.n_warps == 1 ? choose_solo_groups(e, prog, e.blob.size(), K, n_voices) : 1;
+  const size_t smem = smem_bytes_for(prog, e.blob.size(), K, G);
+  const unsigned grid = (n_groups + G - 1) / G;
   const bool device_out = flags & SRK_RENDER_DEVICE_OUT;
 
   float* d_stems = nullptr;
@@ -410,7 +431,7 @@ int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t
   if (mix) {
     if (device_out) d_mix = mix;
     else { SRK_CUDA(e.d_mix.ensure(C * n_samples * sizeof(float))); d_mix = (float*)e.d_mix.p; }
-    SRK_CUDA(e.d_partial.ensure((size_t)grid * C * n_samples * sizeof(float)));
+    SRK_CUDA(e.d_partial.ensure((size_t)n_groups * C * n_samples * sizeof(float)));
   }
 
   RenderArgs a{};
@@ -441,16 +462,20 @@ int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t
   a.ring_phase = (uint32_t)(e.n_abs % a.B);
   a.seed_lo = (uint32_t)patch->seed;
   a.seed_hi = (uint32_t)(patch->seed >> 32);
+  a.solo_op_barrier = G > 1 && env_int("SRK_SOLO_OP_BARRIER", 0) ? 1u : 0u;
 
   SRK_CUDA(cudaEventRecord(e.ev[1], work));
-  SRK_CUDA(prog.n_warps == 1 ? launch_voices_solo(a, grid, smem, work)
-                             : launch_voices_pipelined(a, grid, (unsigned)T, smem, work));
+  bool beyond_baseline = false;  // sequencers / sample player: the larger one-warp image
+  for (const Instr& ins : prog.code) beyond_baseline |= ins.op == OP_GRIDSEQ || ins.op == OP_PATSEQ || ins.op == OP_SAMPLE;
+  SRK_CUDA(prog.n_warps > 1 ? launch_voices_pipelined(a, grid, (unsigned)T, smem, work)
+           : beyond_baseline ? launch_voices_solo_full(a, grid, 32u * G, smem, work)
+                             : launch_voices_solo(a, grid, 32u * G, smem, work));
   SRK_CUDA(cudaGetLastError());
   ++e.launches;
   SRK_CUDA(cudaEventRecord(e.ev[2], work));
   if (mix) {
     const size_t cn = C * n_samples;
-    mix_reduce_kernel<<<(unsigned)((cn + 255) / 256), 256, 0, work>>>((const float*)e.d_partial.p, d_mix, grid, cn);
+    mix_reduce_kernel<<<(unsigned)((cn + 255) / 256), 256, 0, work>>>((const float*)e.d_partial.p, d_mix, n_groups, cn);
     SRK_CUDA(cudaGetLastError());
     ++e.launches;
   }
@@ -465,7 +490,7 @@ int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t
   // the next render carries is_new = 0 again
   for (int mi : prog.wave_modules)
     if (patch->modules[mi]->wave_new) { patch->modules[mi]->wave_new = false; ++patch->table_epoch; }
-  e.block_threads = T;
+  e.block_threads = prog.n_warps == 1 ? 32 * G : T;
   e.step = K;
   e.n_warps = (int)prog.n_warps;
   e.n_stages = (int)prog.n_stages;

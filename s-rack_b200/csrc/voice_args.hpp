@@ -1,5 +1,5 @@
-// Launch arguments of the voice kernel and the two host-side launchers (one per schedule, each
-// in its own translation unit: voice_kernel_solo.cu, voice_kernel_pipelined.cu).
+// Launch arguments of the voice kernel and the host-side launchers (each in its own translation unit:
+// voice_kernel_solo.cu, voice_kernel_solo_full.cu, voice_kernel_pipelined.cu).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -29,11 +29,13 @@ struct RenderArgs {
   uint32_t log2K;
   uint32_t ring_phase;    // absolute sample index of sample 0, mod B
   uint32_t seed_lo, seed_hi;
+  uint32_t solo_op_barrier;  // one-warp schedule, several groups per block: barrier after every instruction, not only per chunk
 };
 
 constexpr int kMaxThreads = kMaxWarps * 32;
 
-cudaError_t launch_voices_solo(const RenderArgs& a, unsigned grid, size_t smem, cudaStream_t stream);
+cudaError_t launch_voices_solo(const RenderArgs& a, unsigned grid, unsigned threads, size_t smem, cudaStream_t stream);       // BASELINE modules only
+cudaError_t launch_voices_solo_full(const RenderArgs& a, unsigned grid, unsigned threads, size_t smem, cudaStream_t stream);  // every module kind
 cudaError_t launch_voices_pipelined(const RenderArgs& a, unsigned grid, unsigned threads, size_t smem, cudaStream_t stream);
 
 }  // namespace srk

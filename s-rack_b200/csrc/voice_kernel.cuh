@@ -19,6 +19,7 @@ struct GroupCtx {
   bool active;
   int lane;
   bool solo;          // one warp runs the whole program in plan order
+  uint32_t group;     // voice group (of 32) this warp / block renders
 };
 
 // OP_RING_LOAD / OP_RING_STORE: the delayed (feedback) wires, rings f32 [R][B][V] in HBM.
@@ -89,7 +90,7 @@ __device__ __forceinline__ void run_output(const Instr& ins, const dsp::Lane& ln
 __device__ __forceinline__ void run_mix(const Instr& ins, const dsp::Lane& ln, const GroupCtx& g, int kk) {
   const RenderArgs& a = g.a;
   const uint32_t n0 = ln.chunk * a.K;
-  if (!a.partial) return;
+  if (!a.partial || g.n_active == 0) return;
   const uint32_t R = min(a.K, 32u), log2R = min(a.log2K, 5u);
   const int lane = g.lane;
   if (g.solo) __syncwarp();  // the tile was written by this warp a moment ago
@@ -121,7 +122,7 @@ __device__ __forceinline__ void run_mix(const Instr& ins, const dsp::Lane& ln, c
         for (uint32_t off = R; off < 32; off <<= 1) acc = dsp::fadd(acc, __shfl_xor_sync(0xFFFFFFFFu, acc, off));
         sum = acc;
       }  // else: same wire as the previous channel, same sums
-      if (kb + lane < kk) a.partial[((size_t)blockIdx.x * a.C + ins.aux + j) * a.n_samples + n0 + kb + lane] = sum;
+      if (kb + lane < kk) a.partial[((size_t)g.group * a.C + ins.aux + j) * a.n_samples + n0 + kb + lane] = sum;
     }
   }
   if (g.solo) __syncwarp();
@@ -166,34 +167,47 @@ __device__ __forceinline__ void run_once(const Instr& ins, const dsp::Lane& ln, 
 // program chunk by chunk; the throughput shape) carries only the interpreter, PIPELINED adds the
 // resident single-instruction loops.  Keeping them apart keeps each one's hot code close together
 // (the one-warp schedule lost 14 % when the resident variants grew the shared kernel, r01s).
-template <bool SOLO>
-__global__ void __launch_bounds__(SOLO ? 32 : kMaxThreads, 1) render_voices_kernel(const RenderArgs a) {
+// FULL adds the modules outside the BASELINE patches (sequencers, sample player) to the interpreter.
+// The one-warp kernel is compiled twice, with and without them: its speed follows the size and
+// layout of the whole switch (every added op body cost it 7 % even for programs that never
+// execute it, profiles/r03a), so the common patches run the smaller image.  Instructions only a
+// pipelined program contains (OP_OSC_DELTA, OP_MOOG_COEF) are left out of both one-warp images.
+template <bool SOLO, bool FULL>
+__global__ void __launch_bounds__(kMaxThreads, 1) render_voices_kernel(const RenderArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const Instr* prog = reinterpret_cast<const Instr*>(smem_raw);
   const WireDesc* wd = reinterpret_cast<const WireDesc*>(prog + a.n_instr);
   const uint16_t* warp_begin = reinterpret_cast<const uint16_t*>(wd + a.n_wires);
-  uint32_t* st = reinterpret_cast<uint32_t*>(smem_raw + (size_t)a.blob_vec * 16);
+  // PIPELINED: the block's warps share one voice group's tables.  SOLO: every warp of the block is a
+  // voice group of its own (own tables, same program), kept in step by the per-chunk barrier so that
+  // the warps of an SM walk the same op bodies together -- the one-warp schedule is bound by
+  // instruction fetch (33 % of its stall samples were "no instruction", profiles/r03c), and aligned
+  // warps share the fetched lines.
+  const uint32_t group = SOLO ? blockIdx.x * (blockDim.x >> 5) + wid : blockIdx.x;
+  const uint32_t group_words = (a.S + a.P + a.n_tiles * a.K) * 32;
+  uint32_t* st = reinterpret_cast<uint32_t*>(smem_raw + (size_t)a.blob_vec * 16) + (SOLO ? wid * group_words : 0u);
   uint32_t* pr = st + a.S * 32;
   float* tiles = reinterpret_cast<float*>(pr + a.P * 32);
 
   // stage the patch program (port/wire table) once per block
   for (uint32_t i = tid; i < a.blob_vec; i += blockDim.x) reinterpret_cast<uint4*>(smem_raw)[i] = a.blob[i];
-  const uint32_t v0 = blockIdx.x * 32;
-  const uint32_t n_active = min(32u, a.V - v0);
+  const uint32_t v0 = group * 32;
+  const uint32_t n_active = v0 < a.V ? min(32u, a.V - v0) : 0u;  // 0: a spare warp of the last SOLO block
   const bool active = (uint32_t)lane < n_active;
   const uint32_t v = active ? v0 + lane : a.V - 1;  // idle lanes shadow the last voice, never store
-  for (uint32_t w = wid; w < a.S; w += a.n_warps) st[w * 32 + lane] = a.state[(size_t)w * a.V + v];
-  for (uint32_t w = wid; w < a.P; w += a.n_warps) pr[w * 32 + lane] = a.params[(size_t)w * a.V + v];
+  const uint32_t w0 = SOLO ? 0u : (uint32_t)wid, dw = SOLO ? 1u : a.n_warps;
+  for (uint32_t w = w0; w < a.S; w += dw) st[w * 32 + lane] = a.state[(size_t)w * a.V + v];
+  for (uint32_t w = w0; w < a.P; w += dw) pr[w * 32 + lane] = a.params[(size_t)w * a.V + v];
   __syncthreads();
 
   dsp::Lane ln{st + lane, pr + lane, tiles + lane, wd, a.K * 32, 0, a.voice_offset + v, a.seed_lo, a.seed_hi,
                reinterpret_cast<const int32_t*>(smem_raw + a.table_off), a.waves};
-  const uint32_t pc0 = warp_begin[wid], pc1 = warp_begin[wid + 1];
+  const uint32_t pc0 = warp_begin[SOLO ? 0 : wid], pc1 = warp_begin[SOLO ? 1 : wid + 1];
   const uint32_t K = a.K;
   const uint32_t n_chunks = (a.n_samples + K - 1) / K;
   const uint32_t n_iter = n_chunks + a.n_stages - 1;
-  const GroupCtx g{a, v, n_active, active, lane, SOLO};
+  const GroupCtx g{a, v, n_active, active, lane, SOLO, group};
 
   if (!SOLO && pc1 == pc0 + 1) {
     const Instr ins = prog[pc0];
@@ -245,11 +259,11 @@ __global__ void __launch_bounds__(SOLO ? 32 : kMaxThreads, 1) render_voices_kern
         switch (ins.op) {
           case OP_OSC: run_once<dsp::OscOp>(ins, ln, kk); break;
           case OP_MOOG: run_once<dsp::MoogOp>(ins, ln, kk); break;
-          case OP_MOOG_COEF: run_once<dsp::MoogCoefOp>(ins, ln, kk); break;
-          case OP_GRIDSEQ: run_once<dsp::GridSeqOp>(ins, ln, kk); break;
-          case OP_OSC_DELTA: run_once<dsp::OscDeltaOp>(ins, ln, kk); break;
-          case OP_PATSEQ: run_once<dsp::PatSeqOp>(ins, ln, kk); break;
-          case OP_SAMPLE: run_once<dsp::SampleOp>(ins, ln, kk); break;
+          case OP_MOOG_COEF: if constexpr (!SOLO) run_once<dsp::MoogCoefOp>(ins, ln, kk); break;
+          case OP_OSC_DELTA: if constexpr (!SOLO) run_once<dsp::OscDeltaOp>(ins, ln, kk); break;
+          case OP_GRIDSEQ: if constexpr (FULL) run_once<dsp::GridSeqOp>(ins, ln, kk); break;
+          case OP_PATSEQ: if constexpr (FULL) run_once<dsp::PatSeqOp>(ins, ln, kk); break;
+          case OP_SAMPLE: if constexpr (FULL) run_once<dsp::SampleOp>(ins, ln, kk); break;
           case OP_ADSR: run_once<dsp::AdsrOp>(ins, ln, kk); break;
           case OP_NOISE: run_once<dsp::NoiseOp>(ins, ln, kk); break;
           case OP_VCA: run_once<dsp::VcaOp>(ins, ln, kk); break;
@@ -261,13 +275,14 @@ __global__ void __launch_bounds__(SOLO ? 32 : kMaxThreads, 1) render_voices_kern
           case OP_MIX: run_mix(ins, ln, g, kk); break;
           default: break;
         }
+        if (SOLO && a.solo_op_barrier) __syncthreads();  // (every SOLO instruction has stage 0: uniform)
       }
-      if (SOLO) __syncwarp(); else __syncthreads();
+      if (SOLO && blockDim.x == 32) __syncwarp(); else __syncthreads();
     }
   }
   __syncthreads();
   if (active)
-    for (uint32_t w = wid; w < a.S; w += a.n_warps) a.state[(size_t)w * a.V + v] = st[w * 32 + lane];
+    for (uint32_t w = w0; w < a.S; w += dw) a.state[(size_t)w * a.V + v] = st[w * 32 + lane];
 }
 
 }  // namespace srk

@@ -5,9 +5,9 @@
 namespace srk {
 
 cudaError_t launch_voices_pipelined(const RenderArgs& a, unsigned grid, unsigned threads, size_t smem, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(render_voices_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(render_voices_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  render_voices_kernel<false><<<grid, threads, smem, stream>>>(a);
+  render_voices_kernel<false, true><<<grid, threads, smem, stream>>>(a);
   return cudaGetLastError();
 }
 

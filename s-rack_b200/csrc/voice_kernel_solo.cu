@@ -1,13 +1,13 @@
-// SOLO instantiation of the voice kernel: one warp per 32-voice group runs the whole program chunk
-// by chunk (the throughput schedule).  sm_100a only.
+// SOLO instantiation of the voice kernel: one warp per 32-voice group (several groups per block) runs the whole program chunk
+// by chunk (the throughput schedule), for programs made of the BASELINE modules only.  sm_100a only.
 #include "voice_kernel.cuh"
 
 namespace srk {
 
-cudaError_t launch_voices_solo(const RenderArgs& a, unsigned grid, size_t smem, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(render_voices_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+cudaError_t launch_voices_solo(const RenderArgs& a, unsigned grid, unsigned threads, size_t smem, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(render_voices_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  render_voices_kernel<true><<<grid, 32, smem, stream>>>(a);
+  render_voices_kernel<true, false><<<grid, threads, smem, stream>>>(a);
   return cudaGetLastError();
 }
 

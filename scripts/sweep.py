@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Kernel-time sweep over schedules (SRK_WARPS / SRK_STEP) for the BASELINE configs; mix + stems in HBM.
-Usage: python scripts/sweep.py [cfg:V:warps:step ...]   (warps/step 0 = library default)"""
+Usage: python scripts/sweep.py [cfg:V:warps:step[:groups[:opbarrier]] ...]   (0 = library default;
+groups / opbarrier: SRK_SOLO_GROUPS / SRK_SOLO_OP_BARRIER of the one-warp schedule)"""
 import os
 import sys
 
@@ -18,9 +19,9 @@ DEFAULT = ["cfg2:4096:0:0", "cfg2:4096:16:16", "cfg2:4096:16:8", "cfg2:4096:1:8"
 
 
 def run(spec):
-    name, V, warps, step = spec.split(":")
-    V, warps, step = int(V), int(warps), int(step)
-    for k, v in (("SRK_WARPS", warps), ("SRK_STEP", step)):
+    name, V, warps, step, groups, opbar = (spec.split(":") + ["0", "0"])[:6]
+    V, warps, step, groups, opbar = int(V), int(warps), int(step), int(groups), int(opbar)
+    for k, v in (("SRK_WARPS", warps), ("SRK_STEP", step), ("SRK_SOLO_GROUPS", groups), ("SRK_SOLO_OP_BARRIER", opbar)):
         if v:
             os.environ[k] = str(v)
         else:
