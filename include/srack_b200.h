@@ -218,6 +218,21 @@ SRK_API int srk_get_sample(const srk_module* m, float* samples, size_t cap, size
 SRK_API int srk_write_wav(const char* path, const float* planar, unsigned channels, size_t n_samples,
                           uint32_t sample_rate, int bits);
 
+/* ---- .srk patch files: FileFormat (src/ui.rs:578-586) in MessagePack as rmp-serde 1.3.0 writes it
+ *      (ui.rs:98-114 serialize, :115-134 deserialize).
+ * Load empties the patch and rebuilds it: module list in the order the reference ends up with (the
+ * file's reversed, ui.rs:652-660), ids, parameters, sequencer tables, Sample tables, connections
+ * (entries naming unknown ids or bad ports are skipped like the reference's `let _ = set_input(..)`,
+ * ui.rs:662-681; their count goes to *n_skipped_connections when non-NULL).  Serialized port buffers
+ * and DSP state are not imported: every voice starts from X::new() state.  A file that contains a
+ * Freeverb module is refused with SRK_ERR_UNSUPPORTED and the patch is left as it was; a malformed file
+ * gives SRK_ERR_ARG.  Per-voice parameter arrays are dropped (the file has one value per field).
+ * Call srk_plan() afterwards (the reference plans at the end of deserialize). ------------------- */
+SRK_API int srk_patch_load_srk(srk_patch* patch, const void* bytes, size_t n_bytes, size_t* n_skipped_connections);
+/* The patch as the reference would save it with freshly constructed modules (zeroed port buffers of
+ * buffer_size samples, X::new() DSP state).  *bytes stays valid until the next save or patch destroy. */
+SRK_API int srk_patch_save_srk(srk_patch* patch, const void** bytes, size_t* n_bytes);
+
 /* ---- planning: plan_execution(output, &all_modules, &mut plan), src/synth.rs:128-212,
  *      called as in ui.rs:63-82 (output = first Output in the module list) -------- */
 SRK_API int srk_plan(srk_patch* patch);

@@ -135,6 +135,20 @@ class OraclePatch:
         samples, rate = wav.load(data)
         self.set_sample(module, samples, rate)
 
+    def set_adsr_sample_rate(self, module, sample_rate):
+        """The `sample_rate` field an ADSR carries through a .srk file (set_audio_config never updates it)."""
+        self.set_param(module, 100, sample_rate)
+
+    def load_srk(self, data):
+        """SynthModuleWorkspaceImpl::deserialize (ui.rs:115-134) via oracle/srk_file.py -> {id: module}."""
+        from . import srk_file
+        ff = srk_file.loads(data)
+        handles = srk_file.build(self, ff, channels=self.channels)
+        for variant, m in ff["modules"]:
+            if variant == "ADSRModuleV0":
+                self.set_adsr_sample_rate(handles[m["id"]], m["sample_rate"])
+        return handles
+
     def set_module_order(self, order):
         o = np.ascontiguousarray(order, dtype=np.int32)
         lib().orc_set_module_order(self._h, o.ctypes.data, o.size)

@@ -263,6 +263,7 @@ struct ADSR : Module {
       case 1: d_sec = v; return true;
       case 2: s_val = v; return true;
       case 3: r_sec = v; return true;
+      case 100: sample_rate = v; return true;  // a deserialized ADSR keeps the rate it was saved with (adsr.rs:17,69-71)
     }
     return false;
   }

@@ -92,6 +92,8 @@ _SIGNATURES = {
     "srk_set_sample": (C.c_int, [_P, _P, C.c_size_t, C.c_float]),
     "srk_get_sample": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_float)]),
     "srk_write_wav": (C.c_int, [C.c_char_p, _P, C.c_uint, C.c_size_t, C.c_uint32, C.c_int]),
+    "srk_patch_load_srk": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "srk_patch_save_srk": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "srk_plan": (C.c_int, [_P]),
     "srk_plan_get": (C.c_int, [_P, C.POINTER(_P), C.c_size_t, C.POINTER(C.c_size_t)]),
     "srk_plan_cuts": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.c_size_t, C.POINTER(C.c_size_t)]),

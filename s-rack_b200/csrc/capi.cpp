@@ -7,6 +7,7 @@
 
 #include "engine.hpp"
 #include "patch.hpp"
+#include "srkfile.hpp"
 #include "wav.hpp"
 
 namespace {
@@ -313,6 +314,97 @@ int srk_write_wav(const char* path, const float* planar, unsigned channels, size
                   int bits) {
   std::string err;
   return srk::wav_write(path, planar, channels, n_samples, sample_rate, bits, err) ? SRK_OK : SRK_ERR_ARG;
+}
+
+// SynthModuleWorkspaceImpl::deserialize, ui.rs:115-134: the patch is emptied and rebuilt from the file.
+int srk_patch_load_srk(srk_patch* p, const void* bytes, size_t n_bytes, size_t* n_skipped_connections) {
+  if (!p || (!bytes && n_bytes)) return SRK_ERR_ARG;
+  srk::SrkFile f;
+  std::string err;
+  if (!srk::srk_file_decode(bytes, n_bytes, f, err)) return fail(p, SRK_ERR_ARG, err.c_str());
+  for (const srk::SrkModule& m : f.modules)
+    if (m.kind < 0) return fail(p, SRK_ERR_UNSUPPORTED, (m.variant + " is outside the hot path").c_str());
+  // from here on the old patch is gone (the reference clears before it parses, ui.rs:117-122)
+  p->modules.clear();
+  p->owned.clear();
+  p->plan.clear();
+  p->cuts.clear();
+  p->positions.clear();
+  touch_wiring(p);
+  ++p->param_epoch;
+  ++p->table_epoch;
+  ++p->wave_epoch;
+  // unpack_modules pops from the back (ui.rs:652-660): the module list is the file's reversed
+  for (size_t k = f.modules.size(); k-- > 0;) {
+    const srk::SrkModule& fm = f.modules[k];
+    srk_module* m = nullptr;
+    int rc = srk_module_create(p, fm.kind, &m);
+    if (rc != SRK_OK) return rc;
+    m->id = fm.id;
+    const srk::KindInfo& ki = srk::kind_info(fm.kind);
+    for (int i = 0; i < ki.n_params; ++i) m->param[i] = fm.param[i];
+    if (fm.kind == SRK_KIND_GRID_SEQUENCER || fm.kind == SRK_KIND_PATTERN_SEQUENCER) {
+      m->sequence = fm.sequence;
+      m->seq_steps = fm.seq_steps;
+    }
+    if (fm.kind == SRK_KIND_SAMPLE) {
+      m->wave = fm.wave;
+      m->wave_rate = fm.wave_rate;
+      m->wave_new = false;  // a fresh voice starts rewound anyway
+    }
+    if (fm.has_adsr_rate) m->adsr_sample_rate = fm.adsr_sample_rate;  // set_audio_config leaves it alone (adsr.rs:69-71)
+  }
+  // unpack_connections pops from the back too (ui.rs:673): of two entries for one input the EARLIER wins
+  size_t skipped = 0;
+  for (size_t k = f.connections.size(); k-- > 0;) {
+    const srk::SrkConnection& c = f.connections[k];
+    srk_module *sink = nullptr, *src = nullptr;
+    for (srk_module* m : p->modules) {
+      if (m->id == c.sink_id) sink = m;
+      if (m->id == c.src_id) src = m;
+    }
+    if (!sink || !src || srk_connect(sink, c.sink_port, src, c.src_port) != SRK_OK) ++skipped;  // `let _ = set_input(..)`
+  }
+  for (const srk::SrkPosition& q : f.positions) p->positions.push_back({q.id, {q.x, q.y}});
+  p->last_error.clear();
+  if (n_skipped_connections) *n_skipped_connections = skipped;
+  return SRK_OK;
+}
+
+// SynthModuleWorkspaceImpl::serialize, ui.rs:98-114.
+int srk_patch_save_srk(srk_patch* p, const void** bytes, size_t* n_bytes) {
+  if (!p || !bytes || !n_bytes) return SRK_ERR_ARG;
+  srk::SrkFile f;
+  for (const srk_module* m : p->modules) {  // capture_modules: list order
+    srk::SrkModule fm;
+    fm.kind = m->kind;
+    fm.id = m->id;
+    for (int i = 0; i < srk::kMaxParams; ++i) fm.param[i] = m->param[i];
+    fm.sequence = m->sequence;
+    fm.seq_steps = m->seq_steps;
+    fm.wave = m->wave;
+    fm.wave_rate = m->wave_rate;
+    fm.adsr_sample_rate = m->adsr_sample_rate;
+    f.modules.push_back(std::move(fm));
+  }
+  for (const srk_module* m : p->modules)  // capture_connections: per module, inputs in index order
+    for (size_t i = 0; i < m->inputs.size(); ++i)
+      if (m->inputs[i].first) {
+        srk::SrkConnection c;
+        c.src_id = m->inputs[i].first->id;
+        c.src_port = m->inputs[i].second;
+        c.sink_id = m->id;
+        c.sink_port = (uint8_t)i;
+        f.connections.push_back(c);
+      }
+  for (const auto& q : p->positions)
+    if (std::any_of(p->modules.begin(), p->modules.end(), [&](const srk_module* m) { return m->id == q.first; }))
+      f.positions.push_back(srk::SrkPosition{q.first, q.second.first, q.second.second});
+  p->saved.clear();
+  srk::srk_file_encode(f, p->cfg.buffer_size, p->cfg.sample_rate, p->cfg.channels, p->saved);
+  *bytes = p->saved.data();
+  *n_bytes = p->saved.size();
+  return SRK_OK;
 }
 
 int srk_plan(srk_patch* p) {

@@ -69,6 +69,8 @@ struct srk_patch {
   uint64_t table_epoch = 1;   // bumped by every sequence-table change (program image, not state)
   uint64_t wave_epoch = 1;    // bumped by every Sample table change (device copy of the waves)
   std::string last_error;
+  std::vector<std::pair<std::string, std::pair<float, float>>> positions;  // GUI positions of a loaded .srk, written back on save
+  std::vector<unsigned char> saved;  // last srk_patch_save_srk() image
   std::unique_ptr<srk::Engine, void (*)(srk::Engine*)> engine{nullptr, nullptr};
 
   int index_of(const srk_module* m) const {

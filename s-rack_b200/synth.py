@@ -264,6 +264,29 @@ class Patch:
     def load_wav(self, module, data):
         module.load_wav(data)
 
+    # -- .srk patch files (FileFormat, ui.rs:578-586) ------------------------
+    def load_srk(self, data):
+        """SynthModuleWorkspaceImpl::deserialize (ui.rs:115-134): replace this patch by the file's.
+        -> number of connections skipped (unknown ids / bad ports, like the reference's `let _ =`)."""
+        data = bytes(data)
+        skipped = C.c_size_t()
+        self._check(lib.srk_patch_load_srk(self._h, data, len(data), C.byref(skipped)))
+        self._wrappers.clear()
+        self.per_voice.clear()
+        return skipped.value
+
+    def save_srk(self):
+        """SynthModuleWorkspaceImpl::serialize (ui.rs:98-114) -> bytes."""
+        ptr, n = C.c_void_p(), C.c_size_t()
+        self._check(lib.srk_patch_save_srk(self._h, C.byref(ptr), C.byref(n)))
+        return C.string_at(ptr.value, n.value)
+
+    def module_by_id(self, module_id):
+        for m in self.modules:
+            if m.get_id() == module_id:
+                return m
+        raise KeyError(module_id)
+
     # -- planning ------------------------------------------------------------
     def plan(self):
         """plan_execution (synth.rs:128-212) -> modules in execution order."""
