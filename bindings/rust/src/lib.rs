@@ -53,6 +53,12 @@ extern "C" {
     fn srk_set_param_f32(m: *mut srk_module, param_id: c_int, value: f32) -> c_int;
     fn srk_set_param_f32_per_voice(m: *mut srk_module, param_id: c_int, values: *const f32, n: usize) -> c_int;
     fn srk_set_sequence(m: *mut srk_module, cells: *const i32, n_steps: usize) -> c_int;
+    fn srk_load_wav(m: *mut srk_module, wav_bytes: *const c_void, n_bytes: usize) -> c_int;
+    fn srk_set_sample(m: *mut srk_module, samples: *const f32, n: usize, sample_rate: f32) -> c_int;
+    fn srk_write_wav(path: *const c_char, planar: *const f32, channels: c_uint, n_samples: usize,
+                     sample_rate: u32, bits: c_int) -> c_int;
+    fn srk_patch_load_srk(patch: *mut srk_patch, bytes: *const c_void, n_bytes: usize, n_skipped: *mut usize) -> c_int;
+    fn srk_patch_save_srk(patch: *mut srk_patch, bytes: *mut *const c_void, n_bytes: *mut usize) -> c_int;
     fn srk_plan(patch: *mut srk_patch) -> c_int;
     fn srk_plan_get(patch: *const srk_patch, out: *mut *mut srk_module, cap: usize, n: *mut usize) -> c_int;
     fn srk_render(patch: *mut srk_patch, n_voices: usize, voice_offset: usize, n_samples: usize,
@@ -117,6 +123,14 @@ impl Module {
     /// A sequencer's step table (`sequencer.rs:18,341`): `n_steps` cells (grid) or 8 rows x `n_steps` (pattern).
     pub fn set_sequence(&self, cells: &[i32], n_steps: usize) -> Result<(), Error> {
         self.check(unsafe { srk_set_sequence(self.h, cells.as_ptr(), n_steps) })
+    }
+    /// `WaveBox::load` (`sample.rs:32-69`): the bytes of a WAV file into a Sample module's table.
+    pub fn load_wav(&self, wav: &[u8]) -> Result<(), Error> {
+        self.check(unsafe { srk_load_wav(self.h, wav.as_ptr() as *const c_void, wav.len()) })
+    }
+    /// The decoded `WaveBox` directly (`sample.rs:16-20`).
+    pub fn set_sample(&self, samples: &[f32], sample_rate: f32) -> Result<(), Error> {
+        self.check(unsafe { srk_set_sample(self.h, samples.as_ptr(), samples.len(), sample_rate) })
     }
     pub fn set_param_per_voice(&self, param_id: i32, values: &[f32]) -> Result<(), Error> {
         self.check(unsafe { srk_set_param_f32_per_voice(self.h, param_id, values.as_ptr(), values.len()) })
@@ -190,6 +204,27 @@ impl Patch {
     }
     pub fn sync(&mut self) -> Result<(), Error> { self.check(unsafe { srk_sync(self.h) }) }
     pub fn reset(&mut self) -> Result<(), Error> { self.check(unsafe { srk_reset(self.h) }) }
+    /// `SynthModuleWorkspaceImpl::deserialize` (`ui.rs:115-134`): replace the patch by a `.srk` file's.
+    /// Returns how many connections were skipped (unknown ids / bad ports).  Call `plan()` afterwards.
+    pub fn load_srk(&mut self, bytes: &[u8]) -> Result<usize, Error> {
+        let mut skipped = 0usize;
+        self.check(unsafe { srk_patch_load_srk(self.h, bytes.as_ptr() as *const c_void, bytes.len(), &mut skipped) })?;
+        Ok(skipped)
+    }
+    /// `SynthModuleWorkspaceImpl::serialize` (`ui.rs:98-114`).
+    pub fn save_srk(&mut self) -> Result<Vec<u8>, Error> {
+        let (mut p, mut n) = (ptr::null(), 0usize);
+        self.check(unsafe { srk_patch_save_srk(self.h, &mut p, &mut n) })?;
+        Ok(unsafe { std::slice::from_raw_parts(p as *const u8, n) }.to_vec())
+    }
+}
+
+/// WAV export of a render: `planar` is `[channels][n_samples]` as `Patch::execute` writes `mix`.
+pub fn write_wav(path: &str, planar: &[f32], channels: u32, sample_rate: u32, bits: i32) -> Result<(), Error> {
+    let c = std::ffi::CString::new(path).map_err(|_| Error { status: 1, detail: "path contains NUL".into() })?;
+    let n = planar.len() / channels.max(1) as usize;
+    let rc = unsafe { srk_write_wav(c.as_ptr(), planar.as_ptr(), channels, n, sample_rate, bits) };
+    if rc == 0 { Ok(()) } else { Err(Error { status: rc, detail: "cannot write WAV".into() }) }
 }
 
 impl Drop for Patch {

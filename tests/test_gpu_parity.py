@@ -445,7 +445,7 @@ def test_loaded_srk_files_render_like_the_oracle(srk, orc, cuda_device):
         gp.plan()
         op = orc.OraclePatch(48000, B, 2)
         op.load_srk(data)
-        V, N = 33, 8 * B
+        V, N = 33, 16 * B  # (the 2 Hz gate of the first file opens at sample 12000)
         g, g_mix = gp.render(V, N, stems=True, mix=True)
         o, o_mix = op.render(V, N)
         assert np.abs(o).max() > 0.01
