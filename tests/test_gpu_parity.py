@@ -184,8 +184,10 @@ def test_adsr_corner_cases(srk, orc, cuda_device):
         assert_parity(g, o, exact=True, what=f"adsr a={a_sec}")
 
 
-def _fuzz_patch(rng, n_modules):
+def _fuzz_patch(rng, n_modules, with_sample=False):
     from test_planner import KINDS, N_IN, N_OUT
+    if with_sample:
+        KINDS, N_IN, N_OUT = KINDS + ["SAMPLE", "SAMPLE"], dict(N_IN, SAMPLE=2), dict(N_OUT, SAMPLE=1)
     kinds = [rng.choice(KINDS) for _ in range(n_modules)] + ["OUTPUT"]
     # make sure something audible reaches the output
     kinds[0] = "OSCILLATOR"
@@ -201,12 +203,12 @@ def _fuzz_patch(rng, n_modules):
     return kinds, wires
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", range(36))
 def test_random_patches(srk, orc, cuda_device, seed):
     """Random (often cyclic) graphs over every module kind with random parameters: exercises the
     patch compiler (wire liveness, rings, unconnected-input defaults) against the oracle."""
     rng = random.Random(1000 + seed)
-    kinds, wires = _fuzz_patch(rng, rng.randrange(3, 12))
+    kinds, wires = _fuzz_patch(rng, rng.randrange(3, 12), with_sample=seed >= 24)  # seeds 24..: Sample players too
     B = rng.choice([1, 5, 64, 1024])
     V = rng.choice([1, 31, 33, 64])
     N = 64 * max(1, 1024 // 64) if B > 64 else 640 // B * B
@@ -224,6 +226,8 @@ def test_random_patches(srk, orc, cuda_device, seed):
                                   for _ in range(steps)], dtype=np.int32)
         elif k == "PATTERN_SEQUENCER":
             tables[m] = np.array([[rng.choice([-1, 0, 1]) for _ in range(steps)] for _ in range(8)], dtype=np.int32)
+    waves = {m: (np.random.default_rng(seed * 100 + m).uniform(-1, 1, rng.choice([0, 1, 97, 4000])).astype(np.float32),
+                 rng.choice([8000.0, 44100.0, 192000.0])) for m, k in enumerate(kinds) if k == "SAMPLE"}
 
     def build(b, n_voices, seed=0):
         mods = [b.module_create(k) for k in kinds]
@@ -231,6 +235,8 @@ def test_random_patches(srk, orc, cuda_device, seed):
             b.connect(mods[sink], i, mods[src], port)
         for m, cells in tables.items():
             b.set_sequence(mods[m], cells)
+        for m, (wave, rate) in waves.items():
+            b.set_sample(mods[m], wave, rate)
         for (m, pid), (per_voice, vals) in pvals.items():
             if per_voice:
                 b.set_param_per_voice(mods[m], pid, vals)
@@ -526,6 +532,35 @@ def test_schedule_invariance(srk, orc, cuda_device, monkeypatch, name, B):
     gp, op, _, _ = build_both(srk, orc, builder, V, buffer_size=B)
     o_st, _ = op.render(V, N + 997)
     assert_parity(results[0][1], o_st, what=f"{name} schedule 0")
+
+
+@pytest.mark.parametrize("name,B", [("cfg4", 1024), ("cfg3b", 64), ("sampler", 1024)])
+def test_one_warp_schedule_groups_per_block(srk, orc, cuda_device, monkeypatch, name, B):
+    """The one-warp schedule puts several voice groups into one thread block (each warp its own tables,
+    one barrier per chunk, optionally one per instruction).  Grouping must not change a bit: 333 voices
+    = 10 full groups + 13 voices, so the last block has a ragged group and, for most G, spare warps."""
+    V, N = 333, 3001
+    builder = getattr(srk.patches, name)
+    monkeypatch.setenv("SRK_WARPS", "1")
+    results = []
+    for groups, op_barrier in [(1, 0), (3, 0), (4, 1), (16, 0), (16, 1), (5, 0)]:
+        monkeypatch.setenv("SRK_SOLO_GROUPS", str(groups))
+        monkeypatch.setenv("SRK_SOLO_OP_BARRIER", str(op_barrier))
+        p = srk.Patch(srk.AudioConfig(48000, B, 2))
+        builder(p, V)
+        p.plan()
+        st, mx = p.render(V, N, stems=True, mix=True)
+        st2, mx2 = p.render(V, 515, stems=True, mix=True)  # state written back by every warp of every block
+        results.append((np.concatenate([st, st2], axis=1), np.concatenate([mx, mx2], axis=1)))
+    for st, mx in results[1:]:
+        assert (st.view(np.uint32) == results[0][0].view(np.uint32)).all()
+        assert (mx.view(np.uint32) == results[0][1].view(np.uint32)).all()  # partials are per group, summed in group order
+    for k in ("SRK_WARPS", "SRK_SOLO_GROUPS", "SRK_SOLO_OP_BARRIER"):
+        monkeypatch.delenv(k)
+    gp, op, _, _ = build_both(srk, orc, builder, V, buffer_size=B)
+    o_st, o_mix = op.render(V, N + 515)
+    assert_parity(results[0][0], o_st, exact=(name == "sampler"), what=f"{name} one-warp groups")
+    assert_mix_parity(results[0][1], o_mix, V)
 
 
 def test_baseline_size_cfg4_sampled_parity(srk, orc, cuda_device):
