@@ -331,7 +331,7 @@ def main():
                        "l2": f"each step writes {C * N_SAMPLES * cnt * 4 / 1e6:.0f} MB of stems (> 126 MB L2), no flush needed",
                        "block_threads": info["block_threads"], "step_samples": info["step_samples"],
                        "smem_bytes": info["smem_bytes"], "warps_per_voice_group": info["n_warps"],
-                       "pipeline_stages": info["n_stages"]},
+                       "pipeline_stages": info["n_stages"], "voice_groups_per_block": info["groups_per_block"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(args.config), "peak_source": peak_src,
                          "algorithmic_bytes_per_voice_sample": bpvs, "kernel": "render_voices_kernel",

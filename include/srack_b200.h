@@ -269,12 +269,13 @@ SRK_API int srk_last_render_ms(srk_patch* patch, float* kernel_ms, float* total_
 SRK_API uint64_t srk_launch_count(const srk_patch* patch);
 /* Compiled-program facts for the last plan and `n_voices`: samples per chunk, threads per
  * block, shared-memory bytes per block, wire slots, state words and parameter words per
- * voice, feedback rings (delayed wires), warps per 32-voice group, pipeline stages and
- * wire tiles per group. */
+ * voice, feedback rings (delayed wires), warps per 32-voice group, pipeline stages,
+ * wire tiles per group and voice groups per thread block (> 1 only in the one-warp schedule,
+ * where block_threads = 32 * groups_per_block and smem_bytes covers all of them). */
 typedef struct srk_program_info {
   uint32_t n_instr, step_samples, block_threads, smem_bytes;
   uint32_t n_wires, state_words, param_words, n_rings;
-  uint32_t n_warps, n_stages, n_tiles, reserved;
+  uint32_t n_warps, n_stages, n_tiles, groups_per_block;
 } srk_program_info;
 SRK_API int srk_get_program_info(srk_patch* patch, size_t n_voices, srk_program_info* out);
 /* The compiled, scheduled device program itself (what execute() becomes for n_voices voices):

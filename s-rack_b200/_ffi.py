@@ -19,7 +19,7 @@ class srk_audio_config(C.Structure):
 class srk_program_info(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("n_instr", "step_samples", "block_threads", "smem_bytes",
                                           "n_wires", "state_words", "param_words", "n_rings",
-                                          "n_warps", "n_stages", "n_tiles", "reserved")]
+                                          "n_warps", "n_stages", "n_tiles", "groups_per_block")]
 
 
 class srk_instr_info(C.Structure):

@@ -533,7 +533,7 @@ uint64_t engine_launches(const srk_patch* patch) { return patch->engine ? patch-
 
 // Compiles the planned patch the way a render of n_voices would (no device needed: the sm_100
 // limits are assumed when the patch has no engine yet).
-static int probe_program(srk_patch* patch, size_t n_voices, Program& prog, std::vector<uint4>& blob, int& K) {
+static int probe_program(srk_patch* patch, size_t n_voices, Program& prog, std::vector<uint4>& blob, int& K, int* solo_groups = nullptr) {
   if (!patch->planned) { patch->last_error = "not planned"; return SRK_ERR_NOT_PLANNED; }
   Engine probe;
   probe.smem_optin = patch->engine ? patch->engine->smem_optin : 227 * 1024;
@@ -551,19 +551,20 @@ static int probe_program(srk_patch* patch, size_t n_voices, Program& prog, std::
     K = choose_chunk(probe, prog, blob.size(), n_voices);
   }
   if (K == 0) { patch->last_error = "patch needs more shared memory than one block can have"; return SRK_ERR_LIMIT; }
+  if (solo_groups) *solo_groups = prog.n_warps == 1 ? choose_solo_groups(probe, prog, blob.size(), K, n_voices) : 1;
   return SRK_OK;
 }
 
 int engine_program_info(srk_patch* patch, size_t n_voices, srk_program_info* out) {
   Program prog;
   std::vector<uint4> blob;
-  int K = 0;
-  int rc = probe_program(patch, n_voices, prog, blob, K);
+  int K = 0, G = 1;
+  int rc = probe_program(patch, n_voices, prog, blob, K, &G);
   if (rc != SRK_OK) return rc;
   out->n_instr = (uint32_t)prog.code.size();
   out->step_samples = (uint32_t)K;
-  out->block_threads = prog.n_warps * 32;
-  out->smem_bytes = (uint32_t)smem_bytes_for(prog, blob.size(), K);
+  out->block_threads = prog.n_warps * 32 * G;  // one-warp schedule: G voice groups (warps) per block
+  out->smem_bytes = (uint32_t)smem_bytes_for(prog, blob.size(), K, G);
   out->n_wires = (uint32_t)prog.wires.size();
   out->state_words = (uint32_t)prog.state_init.size();
   out->param_words = (uint32_t)prog.param_src.size();
@@ -571,7 +572,7 @@ int engine_program_info(srk_patch* patch, size_t n_voices, srk_program_info* out
   out->n_warps = prog.n_warps;
   out->n_stages = prog.n_stages;
   out->n_tiles = prog.n_tiles;
-  out->reserved = 0;
+  out->groups_per_block = (uint32_t)G;
   return SRK_OK;
 }
 

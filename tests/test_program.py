@@ -27,7 +27,8 @@ def _check_program(srk, p, n_voices, B):
     # sorted by warp, stages and warps in range
     assert [i["warp"] for i in code] == sorted(i["warp"] for i in code)
     assert all(i["warp"] < info["n_warps"] and i["stage"] < info["n_stages"] for i in code)
-    assert info["block_threads"] == 32 * info["n_warps"] <= 512
+    assert info["block_threads"] == 32 * info["n_warps"] * info["groups_per_block"] <= 512
+    assert info["groups_per_block"] == 1 or info["n_warps"] == 1  # only the one-warp schedule shares a block
     # wire rings tile the group's tile array without overlap; ring lengths are powers of two
     covered = sorted((first, first + n) for first, n in wires)
     assert all(n & (n - 1) == 0 and n >= 1 for _, n in wires)
