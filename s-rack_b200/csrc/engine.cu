@@ -202,7 +202,7 @@ static size_t smem_bytes_for(const Program& prog, size_t blob_vec, int K, int gr
 // as possible -- the per-chunk barrier keeps a block's warps in the same op bodies, which is what
 // makes the instruction caches work (profiles/r03c: 33 % "no instruction" stalls with 14 independent
 // one-warp blocks per SM).
-static int choose_solo_groups(const Engine& e, const Program& prog, size_t blob_vec, int K, size_t V) {
+static int solo_groups_wanted(const Engine& e, size_t V) {
   const size_t groups = (V + kVoicesPerGroup - 1) / kVoicesPerGroup;
   const size_t n_sm = (size_t)std::max(e.n_sm, 1);
   const size_t per_sm = std::max<size_t>((groups + n_sm - 1) / n_sm, 1);
@@ -211,7 +211,10 @@ static int choose_solo_groups(const Engine& e, const Program& prog, size_t blob_
     const size_t blocks_per_sm = (per_sm + kMaxWarps - 1) / kMaxWarps;
     G = (int)((per_sm + blocks_per_sm - 1) / blocks_per_sm);
   }
-  G = std::max(1, std::min(G, (int)kMaxWarps));
+  return std::max(1, std::min(G, (int)kMaxWarps));
+}
+static int choose_solo_groups(const Engine& e, const Program& prog, size_t blob_vec, int K, size_t V) {
+  int G = solo_groups_wanted(e, V);
   while (G > 1 && smem_bytes_for(prog, blob_vec, K, G) > (size_t)e.smem_optin) --G;
   return G;
 }
@@ -229,6 +232,16 @@ static int choose_chunk(const Engine& e, const Program& prog, size_t blob_vec, s
   const size_t smem_cap = pipelined ? std::min<size_t>(e.smem_optin, (size_t)(e.smem_sm / per_sm) - 1024)
                                     : (size_t)e.smem_optin;
   int K = env_int("SRK_STEP", pipelined ? kMaxChunk : 16);
+  if (!pipelined && env_int("SRK_STEP", 0) <= 0) {
+    // One-warp schedule: the longest chunk that still lets one block hold all the groups an SM gets.  Every
+    // chunk costs each op a trip through the interpreter and its state through shared memory; measured
+    // (profiles/r03m): cfg2 @ 32768 voices 30.0 ms at K = 16, 19.7 ms at K = 64; cfg3 @ 65536 42.7 -> 37.8 ms
+    // at K = 32 -- but a chunk that forces the groups of an SM into a second wave loses more than it gains
+    // (cfg2 @ 65536: 58 ms at K = 32 with 13 groups per block against 37 ms at K = 16 with 14).
+    const int G = solo_groups_wanted(e, V);
+    K = kMaxChunk;
+    while (K > 16 && smem_bytes_for(prog, blob_vec, K, G) > (size_t)e.smem_optin) K /= 2;
+  }
   if (K < 1) K = 1;
   if (K > kMaxChunk) K = kMaxChunk;
   while (K & (K - 1)) K &= K - 1;  // power of two

@@ -554,7 +554,9 @@ def test_one_warp_schedule_groups_per_block(srk, orc, cuda_device, monkeypatch, 
         results.append((np.concatenate([st, st2], axis=1), np.concatenate([mx, mx2], axis=1)))
     for st, mx in results[1:]:
         assert (st.view(np.uint32) == results[0][0].view(np.uint32)).all()
-        assert (mx.view(np.uint32) == results[0][1].view(np.uint32)).all()  # partials are per group, summed in group order
+        # (the chunk length follows the groups per block, and the order in which a group's 32 voices are summed
+        # follows the chunk length below 32 samples: the mix agrees to rounding, not to the bit)
+        assert np.abs(mx - results[0][1]).max() <= 1e-5 * np.sqrt(V)
     for k in ("SRK_WARPS", "SRK_SOLO_GROUPS", "SRK_SOLO_OP_BARRIER"):
         monkeypatch.delenv(k)
     gp, op, _, _ = build_both(srk, orc, builder, V, buffer_size=B)
