@@ -290,7 +290,8 @@ typedef struct srk_instr_info {
                       13 grid sequencer, 14 pattern sequencer (three output ports per instruction),
                       15 oscillator V/oct conversion (delta = 440 * 2^cv / sr on a wire pair),
                       16 sample player */
-  uint8_t flags;   /* math: operation; oscillator: (copies << 4) | copy index when time-split */
+  uint8_t flags;   /* math: operation; oscillator: (copies << 4) | copy index when time-split, bit 3 = antialiasing off;
+                      VCA: bit 0 = negative */
   uint8_t warp;    /* warp of the 32-voice group that executes it */
   uint8_t stage;   /* works on chunk (iteration - stage) */
   int16_t in[4];   /* wire slot per input, -1 = not connected */

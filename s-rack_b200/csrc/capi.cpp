@@ -228,6 +228,7 @@ int srk_set_param_f32(srk_module* m, int pid, float value) {
   m->param[pid] = value;
   m->param_pv[pid].clear();
   ++m->patch->param_epoch;
+  if (ki.param_uniform_only[pid]) ++m->patch->table_epoch;  // baked into the program image (flags / immediates), state kept
   return SRK_OK;
 }
 

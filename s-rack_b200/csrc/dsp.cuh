@@ -157,7 +157,7 @@ struct OscOp {
     val = (double)__uint_as_float(p[0]);
     delta_const = __hiloint2double((int)p[2 * L], (int)p[L]);
     sr = (double)ins.imm;
-    aa = __uint_as_float(p[3 * L]) != 0.0f;
+    aa = !(ins.flags & F_OSC_NO_ANTIALIASING);  // uniform over voices: rides in the instruction, not in a per-voice word
     ext = ins.n_ch != 0;
     p_cv = port(ln, ins.in[0]); p_sync = port(ln, ins.in[1]);
     p_dlo = port(ln, ext ? ins.in[2] : -1); p_dhi = port(ln, ext ? ins.in[3] : -1);
@@ -342,7 +342,7 @@ struct OscOp {
     if (ke > kb) last = false;
   }
 
-  // flags = (n << 4) | i for a time-split copy (program.cpp): every copy advances the phase
+  // flags = (n << 4) | i (| F_OSC_NO_ANTIALIASING) for a time-split copy (program.cpp): every copy advances the phase
   // through the whole chunk, copy i shapes the outputs of the i-th n-th of every chunk (so
   // within one barrier interval each copy does phase(K) + shape(K / n)).
   __device__ __forceinline__ void run(const Instr& ins, const Lane& ln, int kk) {
@@ -351,7 +351,7 @@ struct OscOp {
     int lo = 0, hi = kk;  // the span this copy shapes
     if (n > 1) {
       const int span = (int)(ln.tile_elems / L / n);
-      lo = min(kk, (int)(ins.flags & 15u) * span);
+      lo = min(kk, (int)(ins.flags & 7u) * span);
       hi = min(kk, lo + span);
     }
     if (ext) {  // delta from an OscDeltaOp: the phase runs over the whole chunk, shaping over [lo, hi)
@@ -369,7 +369,7 @@ struct OscOp {
       advance(0, lo); run_outs<0, false>(ln, lo, hi); advance(hi, kk);
     }
   }
-  __device__ __forceinline__ bool owns_state(const Instr& ins) const { return (ins.flags & 15u) == 0; }
+  __device__ __forceinline__ bool owns_state(const Instr& ins) const { return (ins.flags & 7u) == 0; }
 };
 
 // The V/oct conversion of a CV-driven oscillator on its own warp(s) (program.cpp splits it off
@@ -395,7 +395,7 @@ struct OscDeltaOp {
     int kb = 0, ke = kk;
     if (n > 1) {
       const int span = (int)(ln.tile_elems / L / n);
-      kb = min(kk, (int)(ins.flags & 15u) * span);
+      kb = min(kk, (int)(ins.flags & 7u) * span);
       ke = min(kk, kb + span);
     }
     for_groups(kb, ke, [&](auto u, int k0) {
@@ -910,7 +910,7 @@ struct VcaOp {
   bool negative;
   Port p_audio, p_cv, p_out;
   __device__ __forceinline__ void load(const Instr& ins, const Lane& ln) {
-    negative = __uint_as_float(ln.pr[ins.param * L]) != 0.0f;
+    negative = ins.flags & F_VCA_NEGATIVE;  // uniform over voices (vca.rs:14 has no per-voice meaning)
     p_audio = port(ln, ins.in[0]); p_cv = port(ln, ins.in[1]); p_out = port(ln, ins.out[0]);
   }
   __device__ __forceinline__ void store() {}

@@ -170,7 +170,8 @@ int compile_program(const srk_patch& patch, int max_warps, Program& prog, std::s
       case SRK_KIND_OSCILLATOR:
         p.ins.op = OP_OSC;
         p.ins.state = alloc_state(kStateOsc, {0u, 0u, 1u});  // pos = 0.0, sync detector last = true
-        p.ins.param = alloc_params(m, {SRK_OSC_VAL, -1, -2, SRK_OSC_ANTIALIASING});
+        p.ins.param = alloc_params(m, {SRK_OSC_VAL, -1, -2});
+        if (mod->param[SRK_OSC_ANTIALIASING] == 0.0f) p.ins.flags |= F_OSC_NO_ANTIALIASING;
         p.ins.imm = (float)mod->osc_sample_rate;
         break;
       case SRK_KIND_NOISE:
@@ -191,7 +192,7 @@ int compile_program(const srk_patch& patch, int max_warps, Program& prog, std::s
         break;
       case SRK_KIND_VCA:
         p.ins.op = OP_VCA;
-        p.ins.param = alloc_params(m, {SRK_VCA_NEGATIVE});
+        if (mod->param[SRK_VCA_NEGATIVE] != 0.0f) p.ins.flags |= F_VCA_NEGATIVE;
         break;
       case SRK_KIND_MONO_MIXER:
         p.ins.op = OP_MIXER;
@@ -383,7 +384,7 @@ int compile_program(const srk_patch& patch, int max_warps, Program& prog, std::s
           split.push_back(k);
         }
         Pending q = code[i];
-        if (copies[i] > 1) q.ins.flags = (uint8_t)((copies[i] << 4) | c);
+        if (copies[i] > 1) q.ins.flags = (uint8_t)((q.ins.flags & F_OSC_NO_ANTIALIASING) | (copies[i] << 4) | c);
         split.push_back(q);
       }
     code.swap(split);

@@ -39,7 +39,10 @@ enum Op : uint8_t {
 
 // Instr::flags
 enum : uint8_t { F_MATH_ADD = 0, F_MATH_SUB = 1, F_MATH_MUL = 2, F_MATH_NONLIN = 3 };
-enum : uint8_t { F_MOOG_EXT_COEF = 1 };  // OP_MOOG: in[1..3] carry (f, p, q) from an OP_MOOG_COEF instead of the CV
+enum : uint8_t { F_MOOG_EXT_COEF = 1 };
+// Uniform-only parameters ride in the instruction instead of taking a per-voice word (shared memory is what
+// limits the chunk length): OP_OSC bit 3 (bits 0-2 copy index, 4-7 copies), OP_VCA bit 0.
+enum : uint8_t { F_OSC_NO_ANTIALIASING = 8, F_VCA_NEGATIVE = 1 };  // OP_MOOG: in[1..3] carry (f, p, q) from an OP_MOOG_COEF instead of the CV
 
 // ADSR mode encoding in the state word (adsr.rs:26-33 order)
 enum : uint32_t { ADSR_ATTACK = 0, ADSR_DECAY = 1, ADSR_SUSTAIN = 2, ADSR_RELEASE = 3, ADSR_NONE = 4 };
@@ -91,10 +94,10 @@ static_assert(sizeof(WaveDesc) == 16, "WaveDesc is four table words");
 //   SAMPLE  : pos (f32), playing | gate_last << 1                    sample.rs:78-82
 constexpr int kStateOsc = 3, kStateNoise = 2, kStateMoog = 10, kStateAdsr = 4, kStateGridSeq = 2, kStatePatSeq = 1, kStateSample = 2;
 // Per-voice parameter words (SoA [word][voice] in HBM)
-//   OSC   : val, delta (f64, 2 words; host-computed 440*2^val/sr, used when CV is None), antialiasing (0/1)
+//   OSC   : val, delta (f64, 2 words; host-computed 440*2^val/sr, used when CV is None)
 //   MOOG  : freq, res, exp_amt        ADSR : a_sec, d_sec, s_val, r_sec
-//   MIXER : gain[0..3]                MATH : constant          VCA : negative (0/1)
-constexpr int kParamOsc = 4, kParamMoog = 3, kParamAdsr = 4, kParamMixer = 4, kParamMath = 1, kParamVca = 1;
+//   MIXER : gain[0..3]                MATH : constant
+constexpr int kParamOsc = 3, kParamMoog = 3, kParamAdsr = 4, kParamMixer = 4, kParamMath = 1;
 
 // Where a parameter word comes from when the table is (re)built for a voice range.
 struct ParamSource {
