@@ -312,6 +312,38 @@ def main():
                      "d2h_bytes_per_step": d2h_bytes + C * N_SAMPLES * cnt * 4}
         del stems_host
 
+    # ---- the same patch at the voice count where the chip is full (one-warp schedule): a second, throughput-shaped
+    #      data point next to the headline (which BASELINE.json quotes at 4096 voices, a latency-shaped launch)
+    full_chip = None
+    if world == 1 and args.voices_per_gpu == 0 and args.config == "cfg2":
+        Vf = 65536
+        del stems
+        torch.cuda.empty_cache()
+        pf = srk.Patch(device=local_rank)
+        srk.patches.CONFIGS[args.config][0](pf, Vf)
+        pf.plan()
+        info_f = pf.program_info(Vf)
+        stems_f = torch.empty((C, N_SAMPLES, Vf), dtype=torch.float32, device=dev)
+        kf = []
+        for i in range(2 + 4):
+            pf.render_into(Vf, N_SAMPLES, 0, stems_f.data_ptr(), mix.data_ptr(), device_out=True, stream=stream)
+            torch.cuda.synchronize()
+            if i >= 2:
+                kf.append(pf.last_render_ms())
+        k_f = sum(k for k, _ in kf) / len(kf)
+        t_f = sum(t for _, t in kf) / len(kf)
+        peak_f, _ = measured_peak_hbm()
+        full_chip = {"workload": f"{args.config} @ {Vf} voices x {N_SAMPLES} samples, stems + mix in HBM", "value": Vf * N_SAMPLES / (t_f * 1e-3),
+                     "unit": unit, "ms_per_step": t_f, "kernel_ms": k_f, "steps": len(kf), "warmup": 2,
+                     "roofline": {"bound": "hbm", "achieved": Vf * N_SAMPLES * BYTES_PER_VOICE_SAMPLE[args.config] / (k_f * 1e-3) / 1e9,
+                                  "peak": peak_f, "unit": "GB/s",
+                                  "frac": Vf * N_SAMPLES * BYTES_PER_VOICE_SAMPLE[args.config] / (k_f * 1e-3) / 1e9 / peak_f},
+                     "block_threads": info_f["block_threads"], "step_samples": info_f["step_samples"],
+                     "voice_groups_per_block": info_f["groups_per_block"], "smem_bytes": info_f["smem_bytes"],
+                     "gpu_launches": int(pf.launch_count()),
+                     "timing": "CUDA events on the render stream inside the library (whole call and voice kernel), 25 GB of stems per step (> L2)"}
+        del stems_f, pf
+
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         bpvs = BYTES_PER_VOICE_SAMPLE[args.config]
@@ -341,6 +373,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_s * 1e3, "what": "per-voice params from host + render + mix to pinned host"},
             "e2e_stems": e2e_stems,
+            "full_chip": full_chip,
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

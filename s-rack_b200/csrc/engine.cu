@@ -88,6 +88,7 @@ struct Engine {
   Program prog;
   uint64_t compiled_epoch = 0, uploaded_param_epoch = 0, compiled_table_epoch = 0, uploaded_wave_epoch = 0;
   int compiled_max_warps = 0;       // schedule the program was compiled for
+  size_t compiled_voices = 0;       // ... and the voice count (schedule choice and chunk length follow it)
   int chunk = 0;                    // samples per chunk (K) for the compiled program
   std::vector<uint4> blob;          // device image of the program (see RenderArgs::blob)
   size_t V = 0, voice_offset = 0;
@@ -342,7 +343,8 @@ static int engine_prepare(srk_patch* patch, size_t n_voices, size_t voice_offset
   Engine& e = *patch->engine;
   bool fresh = false;
   const int want_warps = choose_max_warps(e, n_voices);
-  const bool rewired = e.compiled_epoch != patch->wiring_epoch || e.compiled_max_warps != want_warps;
+  const bool rewired = e.compiled_epoch != patch->wiring_epoch || e.compiled_max_warps != want_warps ||
+                       e.compiled_voices != n_voices;  // (a new voice count resets the voice state anyway)
   if (rewired || e.compiled_table_epoch != patch->table_epoch) {
     // (a sequence-table edit alone rebuilds the program image but keeps the voice state: the state
     // layout depends on the wiring only)
@@ -368,6 +370,7 @@ static int engine_prepare(srk_patch* patch, size_t n_voices, size_t voice_offset
     SRK_CUDA(cudaStreamSynchronize(e.stream));
     e.compiled_epoch = patch->wiring_epoch;
     e.compiled_max_warps = want_warps;
+    e.compiled_voices = n_voices;
     e.compiled_table_epoch = patch->table_epoch;
     fresh = rewired;
     e.uploaded_wave_epoch = 0;  // WaveDesc offsets follow the plan: re-concatenate
