@@ -37,6 +37,20 @@ def test_every_declared_symbol_is_exported(srk):
     assert sorted(_ffi._SIGNATURES) == fns
 
 
+def test_abi_from_plain_c(srk, tmp_path):
+    """include/srack_b200.h is valid C99 and the library links and behaves from a C translation unit."""
+    import subprocess
+    lib_dir = os.path.dirname(srk.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", HEADER])
+    exe = str(tmp_path / "abi_smoke")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-o", exe, "-L", lib_dir, "-lsrack_b200",
+                           "-Wl,-rpath," + lib_dir])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "ok" in out.stdout
+
+
 def test_python_constants_match_the_header(srk, orc):
     st = header_enum("srk_status")
     assert {"SRK_" + k: v for k, v in srk.STATUS.items()} == st
