@@ -130,17 +130,23 @@ def cpu_reference_run(config, steps, warmup, sample_voices=None):
     from oracle import orc
 
     cores = os.cpu_count() or 1
-    V = sample_voices or 64 * cores
-    p = orc.OraclePatch(48000, 1024, 2)
-    srk.patches.CONFIGS[config][0](p, V)
-    p.render(V, 0, stems=False, mix=False, n_threads=cores)  # build the voice bank outside the timed region
+    builders = srk.patches.CFG5_GRAPHS if config == "cfg5" else [srk.patches.CONFIGS[config][0]]
+    V = sample_voices or (64 * cores) // len(builders)  # cfg5: the sample is spread over its 8 graphs
+    banks = []
+    for b in builders:
+        p = orc.OraclePatch(48000, 1024, 2)
+        b(p, V)
+        p.render(V, 0, stems=False, mix=False, n_threads=cores)  # build the voice bank outside the timed region
+        banks.append(p)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        p.render(V, N_SAMPLES, stems=False, mix=True, n_threads=cores)  # state carries over, like execute()
+        for p in banks:
+            p.render(V, N_SAMPLES, stems=False, mix=True, n_threads=cores)  # state carries over, like execute()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     per_step = sum(times) / len(times)
+    V = V * len(builders)
     return dict(value=V * N_SAMPLES / per_step, ms_per_step=per_step * 1e3, cores=cores, voices=V,
                 sample=f"{V} voices x {N_SAMPLES} samples per step ({V} of the workload's voices; "
                        f"block-based execute(), buffer_size 1024, one patch instance per voice, {cores} threads)")
@@ -152,7 +158,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="cfg2", choices=sorted(BYTES_PER_VOICE_SAMPLE))
+    ap.add_argument("--config", default="cfg2", choices=sorted(BYTES_PER_VOICE_SAMPLE) + ["cfg5"])
     ap.add_argument("--voices-per-gpu", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -163,7 +169,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     import srack_b200 as srk
 
-    desc = srk.patches.CONFIGS[args.config][2]
+    desc = srk.patches.CONFIGS[args.config][2] if args.config in srk.patches.CONFIGS else "mixed batch: 8 distinct patch graphs x 32768 voices each"
     metric = "voice-samples/sec @48 kHz offline render"
     unit = "voice-samples/s"
 
@@ -202,6 +208,8 @@ def main():
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
+    if args.config == "cfg5":
+        return run_cfg5(args, srk, torch, dist, rank, local_rank, world, dev, metric, unit)
     V_gpu = args.voices_per_gpu or (min(srk.patches.CONFIGS[args.config][1], 65536) if world == 1
                                     else {"cfg4": 32768}.get(args.config, min(srk.patches.CONFIGS[args.config][1], 65536)))
     V_total = V_gpu * world
@@ -378,6 +386,112 @@ def main():
             "clocks": clocks,
         }
         print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_cfg5(args, srk, torch, dist, rank, local_rank, world, dev, metric, unit):
+    """BASELINE configs[4]: 8 distinct patch graphs x 32768 voices each, one graph per GPU at N = 8; with fewer
+    ranks every rank renders graphs rank, rank + N, ... one after the other (the job stays the same: strong
+    scaling).  One NCCL sum of the mix per step.  Stems stay in HBM (one graph's 12.6 GB buffer, reused)."""
+    graphs = srk.patches.CFG5_GRAPHS
+    V = args.voices_per_gpu or srk.patches.CFG5_VOICES
+    mine = list(range(rank, len(graphs), world))
+    C = 2
+    patches = []
+    for g in mine:
+        p = srk.Patch(device=local_rank)
+        graphs[g](p, V)
+        p.plan()
+        patches.append((g, p, p.program_info(V)))
+    stems = torch.empty((C, N_SAMPLES, V), dtype=torch.float32, device=dev)
+    mixes = [torch.empty((C, N_SAMPLES), dtype=torch.float32, device=dev) for _ in mine]
+    total = torch.zeros((C, N_SAMPLES), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        for (g, p, _), mx in zip(patches, mixes):
+            p.render_into(V, N_SAMPLES, 0, stems.data_ptr(), mx.data_ptr(), device_out=True, async_=True, stream=stream)
+        torch.sum(torch.stack(mixes), dim=0, out=total)
+        if world > 1:
+            srk.shard.reduce_mix(total)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = sum(p.launch_count() for _, p, _ in patches)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = sum(p.launch_count() for _, p, _ in patches) - launches0
+    per_graph = {}
+    for g, p, info in patches:  # kernel time per graph (CUDA events inside the library)
+        p.render_into(V, N_SAMPLES, 0, stems.data_ptr(), mixes[0].data_ptr(), device_out=True, stream=stream)
+        torch.cuda.synchronize()
+        per_graph[graphs[g].__name__] = {"kernel_ms": p.last_render_ms()[0], "warps_per_voice_group": info["n_warps"],
+                                         "step_samples": info["step_samples"], "voice_groups_per_block": info["groups_per_block"]}
+    # e2e: host per-voice parameters in, mix out to pinned host memory, every step
+    mix_host = torch.empty((C, N_SAMPLES), dtype=torch.float32).pin_memory()
+    pv = [(p, list(p.per_voice.items())) for _, p, _ in patches]
+    h2d = sum(info["param_words"] for _, _, info in patches) * V * 4
+
+    def step_e2e():
+        for (p, items), mx in zip(pv, mixes):
+            for (m, pid), arr in items:
+                m.set_param_per_voice(pid, arr)
+            p.render_into(V, N_SAMPLES, 0, None, mx.data_ptr(), device_out=True, async_=True, stream=stream)
+        torch.sum(torch.stack(mixes), dim=0, out=total)
+        if world > 1:
+            srk.shard.reduce_mix(total)
+        mix_host.copy_(total, non_blocking=False)
+        return float(mix_host[0, -1])
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(2, min(args.steps, 5))
+    for _ in range(n_e2e):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / n_e2e
+    if world > 1:
+        t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0].item()), float(t[1].item()) * 1e-3
+        gathered = [None] * world
+        dist.all_gather_object(gathered, per_graph)
+        per_graph = {k: v for d in gathered for k, v in d.items()}
+    if rank == 0:
+        n_vs = len(graphs) * V * N_SAMPLES
+        peak, peak_src = measured_peak_hbm()
+        k_sum = sum(v["kernel_ms"] for v in per_graph.values())
+        algo = sum((16 if name == "cfg3b" else 8) * V * N_SAMPLES for name in per_graph)
+        print(json.dumps({
+            "metric": metric, "value": n_vs / (ms * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 (+f64 oscillator phase)", "data": "synthetic",
+            "config": {"workload": "cfg5: mixed batch, 8 distinct patch graphs x %d voices each, 48 kHz x 1 s" % V,
+                       "graphs": [g.__name__ for g in graphs], "graphs_per_gpu": len(graphs) / world, "voices_total": len(graphs) * V,
+                       "n_samples": N_SAMPLES, "parallelism": f"graph-shard x{world}",
+                       "l2": "every graph writes 12583 MB of stems per step (> 126 MB L2), no flush needed"},
+            "roofline": {"bound": "hbm", "achieved": algo / (k_sum * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": algo / (k_sum * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "render_voices_kernel (sum over the 8 graphs' launches)", "per_graph": per_graph},
+            "cpu_baseline": None,
+            "e2e": {"value": n_vs / e2e_s, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": C * N_SAMPLES * 4,
+                    "ms_per_step": e2e_s * 1e3, "what": "per-voice params from host + render + mix to pinned host"},
+            "gpu_launches": int(launches)}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
