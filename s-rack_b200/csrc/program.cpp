@@ -313,6 +313,17 @@ int compile_program(const srk_patch& patch, int max_warps, Program& prog, std::s
     // chunk % n == i, so the slowest pipeline stage shrinks from phase + shape to
     // phase + shape / n.  Copy 0 alone stores the state back.
     int spare = std::min(max_warps, kMaxWarps) - (int)code.size();
+    // SRK_MOOG_SPLIT=1 (experiment, see below): the coefficient warps are reserved BEFORE the oscillators take
+    // the spare warps, and one more warp is left unused so that the ladder keeps sub-partition 0 to itself.
+    const char* split_env = std::getenv("SRK_MOOG_SPLIT");
+    const bool split_coef = split_env && split_env[0] == '1';
+    int reserved_coef = 0;
+    if (split_coef) {
+      for (const Pending& p : code)
+        if (p.ins.op == OP_MOOG && p.in_vw[1] >= 0 && spare > 0) { ++reserved_coef; --spare; }
+      const int isolate_cap = 1 + 3 * (std::min(max_warps, kMaxWarps) / 4);
+      spare = std::min(spare, std::max(0, isolate_cap - (int)code.size() - reserved_coef));
+    }
     // First take the V/oct conversion out of CV-driven oscillators: delta = 440 * 2^(cv + val) / sr
     // (oscillator.rs:43-48,132) is an f64 exp2 and an f64 division per sample, stateless, and four
     // times the cost of the phase recurrence it feeds.  It becomes an OP_OSC_DELTA instruction of its
@@ -361,11 +372,9 @@ int compile_program(const srk_patch& patch, int max_warps, Program& prog, std::s
     // Measured on B200 (profiles/r01o): 4.09 ms vs 4.13 ms per step at equal chunk length -- the
     // ladder is bound by its dependency chain, not by issue slots -- and the three extra wires
     // halve the chunk that fits in shared memory, so it is off unless SRK_MOOG_SPLIT=1.
-    const char* split_env = std::getenv("SRK_MOOG_SPLIT");
-    const bool split_coef = split_env && split_env[0] == '1';
     std::vector<int> coef_of(code.size(), 0);
-    for (size_t i = 0; split_coef && i < code.size() && spare > 0; ++i)
-      if (code[i].ins.op == OP_MOOG && code[i].in_vw[1] >= 0) { coef_of[i] = 1; --spare; }
+    for (size_t i = 0; split_coef && i < code.size() && reserved_coef > 0; ++i)
+      if (code[i].ins.op == OP_MOOG && code[i].in_vw[1] >= 0) { coef_of[i] = 1; --reserved_coef; }
     std::vector<Pending> split;
     for (size_t i = 0; i < code.size(); ++i)
       for (int c = 0; c < copies[i]; ++c) {
