@@ -289,7 +289,7 @@ typedef struct srk_instr_info {
                       8 mixer, 9 math, 10 output (stems), 11 mix, 12 moog coefficients,
                       13 grid sequencer, 14 pattern sequencer (three output ports per instruction),
                       15 oscillator V/oct conversion (delta = 440 * 2^cv / sr on a wire pair),
-                      16 sample player */
+                      16 sample player, 17 / 18 oscillator phase recurrence / stateless shaping (experimental split) */
   uint8_t flags;   /* math: operation; oscillator: (copies << 4) | copy index when time-split, bit 3 = antialiasing off;
                       VCA: bit 0 = negative */
   uint8_t warp;    /* warp of the 32-voice group that executes it */

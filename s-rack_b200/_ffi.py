@@ -33,7 +33,7 @@ class srk_wire_info(C.Structure):
 
 
 OPS = ["END", "RING_LOAD", "RING_STORE", "OSC", "NOISE", "MOOG", "ADSR", "VCA", "MIXER", "MATH", "OUTPUT", "MIX",
-       "MOOG_COEF", "GRIDSEQ", "PATSEQ", "OSC_DELTA", "SAMPLE"]
+       "MOOG_COEF", "GRIDSEQ", "PATSEQ", "OSC_DELTA", "SAMPLE", "OSC_PHASE", "OSC_SHAPE"]
 SEQ_NONE = -1
 
 

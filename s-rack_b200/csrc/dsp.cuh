@@ -415,6 +415,201 @@ struct OscDeltaOp {
   }
 };
 
+// ---- The oscillator split in two (program.cpp, SRK_OSC_PHASE_SPLIT=1, pipelined schedule only) ----
+// OscPhaseOp runs what is sequential -- sync reset, `pos += delta; pos %= 1.0` (:125-131, :151-152) --
+// once per oscillator and publishes the phase every sample is shaped at as the two halves of the f64
+// on a wire pair; OscShapeOp (time-split like OscDeltaOp) turns phases into sine / square / saw with
+// exactly OscOp's arithmetic.  Without this every time-split OscOp copy repeats the whole recurrence.
+struct OscPhaseOp {
+  uint32_t* s;
+  double pos, delta_const;
+  bool last, ext;
+  Port p_sync, p_dlo, p_dhi, p_lo, p_hi;
+  __device__ __forceinline__ void load(const Instr& ins, const Lane& ln) {
+    s = ln.st + ins.state * L;
+    pos = __hiloint2double((int)s[L], (int)s[0]);
+    last = s[2 * L] != 0u;
+    const uint32_t* p = ln.pr + ins.param * L;
+    delta_const = __hiloint2double((int)p[2 * L], (int)p[L]);
+    ext = ins.n_ch != 0;
+    p_sync = port(ln, ins.in[1]);
+    p_dlo = port(ln, ext ? ins.in[2] : -1); p_dhi = port(ln, ext ? ins.in[3] : -1);
+    p_lo = port(ln, ins.out[0]); p_hi = port(ln, ins.out[1]);
+  }
+  __device__ __forceinline__ void store() {
+    s[0] = (uint32_t)__double2loint(pos);
+    s[L] = (uint32_t)__double2hiint(pos);
+    s[2 * L] = last ? 1u : 0u;
+  }
+  template <bool EXT, bool HAS_SYNC>
+  __device__ __forceinline__ void run_t(const Lane& ln, int kk) {
+    const float* dlo = p_dlo.at(ln);
+    const float* dhi = p_dhi.at(ln);
+    const float* sync = p_sync.at(ln);
+    float* lo = p_lo.at(ln);
+    float* hi = p_hi.at(ln);
+    double pos = this->pos;
+    bool last = this->last;
+    const double delta_const = this->delta_const;
+    for_groups(kk, [&](auto u, int k0) {
+      constexpr int U = decltype(u)::value;
+      bool edge[U];
+      double ps[U], dl[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) edge[j] = false;
+      if (HAS_SYNC) {
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const bool above = sync[(k0 + j) * L] > 0.0f;
+          edge[j] = above & !last;
+          last = above;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j)
+        dl[j] = EXT ? __hiloint2double(__float_as_int(dhi[(k0 + j) * L]), __float_as_int(dlo[(k0 + j) * L])) : delta_const;
+      const double pos0 = pos;
+      bool odd = false;
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        if (HAS_SYNC) pos = edge[j] ? 0.0 : pos;
+        ps[j] = pos;
+        const double x = dadd(pos, dl[j]);
+        odd |= !(x < 2.0);
+        pos = wrap01(x);
+      }
+      if (odd) {
+        pos = pos0;
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          if (HAS_SYNC) pos = edge[j] ? 0.0 : pos;
+          ps[j] = pos;
+          pos = fmod1_exact(dadd(pos, dl[j]));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        lo[(k0 + j) * L] = __int_as_float(__double2loint(ps[j]));
+        hi[(k0 + j) * L] = __int_as_float(__double2hiint(ps[j]));
+      }
+    });
+    if (!HAS_SYNC && kk > 0) last = false;
+    this->pos = pos;
+    this->last = last;
+  }
+  __device__ __forceinline__ void run(const Instr&, const Lane& ln, int kk) {
+    const bool sync = p_sync.base != nullptr;
+    if (ext) { if (sync) run_t<true, true>(ln, kk); else run_t<true, false>(ln, kk); }
+    else { if (sync) run_t<false, true>(ln, kk); else run_t<false, false>(ln, kk); }
+  }
+};
+
+struct OscShapeOp {
+  double delta_const;
+  bool aa, ext;
+  Port p_plo, p_phi, p_dlo, p_dhi, p_sine, p_square, p_saw;
+  __device__ __forceinline__ void load(const Instr& ins, const Lane& ln) {
+    const uint32_t* p = ln.pr + ins.param * L;
+    delta_const = __hiloint2double((int)p[2 * L], (int)p[L]);
+    aa = !(ins.flags & F_OSC_NO_ANTIALIASING);
+    ext = ins.n_ch != 0;
+    p_plo = port(ln, ins.in[0]); p_phi = port(ln, ins.in[1]);
+    p_dlo = port(ln, ext ? ins.in[2] : -1); p_dhi = port(ln, ext ? ins.in[3] : -1);
+    p_sine = port(ln, ins.out[0]); p_square = port(ln, ins.out[1]); p_saw = port(ln, ins.out[2]);
+  }
+  __device__ __forceinline__ void store() {}
+  template <bool EXT, int OUTS>
+  __device__ __forceinline__ void run_t(const Lane& ln, int kb, int ke) {
+    constexpr bool SINE = OUTS & 1, SQUARE = OUTS & 2, SAW = OUTS & 4;
+    const float* plo = p_plo.at(ln);
+    const float* phi = p_phi.at(ln);
+    const float* dlo = p_dlo.at(ln);
+    const float* dhi = p_dhi.at(ln);
+    float* sine = p_sine.at(ln);
+    float* square = p_square.at(ln);
+    float* saw = p_saw.at(ln);
+    const double delta_const = this->delta_const;
+    const bool aa = this->aa;
+    for_groups(kb, ke, [&](auto u, int k0) {
+      constexpr int U = decltype(u)::value;
+      double ps[U], dl[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        ps[j] = __hiloint2double(__float_as_int(phi[(k0 + j) * L]), __float_as_int(plo[(k0 + j) * L]));
+        dl[j] = EXT ? __hiloint2double(__float_as_int(dhi[(k0 + j) * L]), __float_as_int(dlo[(k0 + j) * L])) : delta_const;
+      }
+      if (SINE) {  // (:133)
+#pragma unroll
+        for (int j = 0; j < U; ++j)
+          sine[(k0 + j) * L] = __double2float_rn(sin(dmul(dmul(ps[j], 3.14159265358979323846), 2.0)));
+      }
+      if (SQUARE || SAW) {  // (:135-149), as OscOp::run_t
+        double om[U], p2[U];
+        bool near = false;
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          om[j] = dsub(1.0, dl[j]);
+          near |= (ps[j] < dl[j]) | (ps[j] > om[j]);
+          if (SQUARE) {
+            p2[j] = wrap01(dadd(ps[j], 0.5));
+            near |= (p2[j] < dl[j]) | (p2[j] > om[j]);
+          }
+        }
+        if (aa & near) {
+          double pb0[U];
+#pragma unroll
+          for (int j = 0; j < U; ++j) pb0[j] = blep_eval(ps[j], dl[j], om[j]);
+          if (SQUARE) {
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+              const float base = ps[j] < 0.5 ? -1.0f : 1.0f;
+              square[(k0 + j) * L] = fsub(base, __double2float_rn(dsub(pb0[j], blep_eval(p2[j], dl[j], om[j]))));
+            }
+          }
+          if (SAW) {
+#pragma unroll
+            for (int j = 0; j < U; ++j)
+              saw[(k0 + j) * L] = fsub(fsub(fmul(__double2float_rn(ps[j]), 2.0f), 1.0f), __double2float_rn(pb0[j]));
+          }
+        } else {
+          if (SQUARE) {
+#pragma unroll
+            for (int j = 0; j < U; ++j) square[(k0 + j) * L] = ps[j] < 0.5 ? -1.0f : 1.0f;
+          }
+          if (SAW) {
+#pragma unroll
+            for (int j = 0; j < U; ++j) saw[(k0 + j) * L] = fsub(fmul(__double2float_rn(ps[j]), 2.0f), 1.0f);
+          }
+        }
+      }
+    });
+  }
+  template <bool EXT>
+  __device__ __forceinline__ void run_outs(const Lane& ln, int kb, int ke) {
+    const int outs = (p_sine.base ? 1 : 0) | (p_square.base ? 2 : 0) | (p_saw.base ? 4 : 0);
+    switch (outs) {
+      case 1: run_t<EXT, 1>(ln, kb, ke); break;
+      case 2: run_t<EXT, 2>(ln, kb, ke); break;
+      case 3: run_t<EXT, 3>(ln, kb, ke); break;
+      case 4: run_t<EXT, 4>(ln, kb, ke); break;
+      case 5: run_t<EXT, 5>(ln, kb, ke); break;
+      case 6: run_t<EXT, 6>(ln, kb, ke); break;
+      case 7: run_t<EXT, 7>(ln, kb, ke); break;
+      default: break;
+    }
+  }
+  __device__ __forceinline__ void run(const Instr& ins, const Lane& ln, int kk) {
+    const uint32_t n = ins.flags >> 4;
+    int kb = 0, ke = kk;
+    if (n > 1) {
+      const int span = (int)(ln.tile_elems / L / n);
+      kb = min(kk, (int)(ins.flags & 7u) * span);
+      ke = min(kk, kb + span);
+    }
+    if (ext) run_outs<true>(ln, kb, ke); else run_outs<false>(ln, kb, ke);
+  }
+};
+
 // ---- NoiseModule::calc, src/synth/oscillator.rs:381-388 (seeded generator) ----
 struct NoiseOp {
   uint32_t* s;

@@ -34,11 +34,13 @@ struct Pending {
 // profiles/r01j): used to balance warps over the 4 SM sub-partitions and to decide
 // which oscillators to time-split.
 int osc_phase_cost(const Pending& p) {  // the recurrence (+ 2^cv / sr when the CV is converted here)
-  if (p.ins.op == OP_OSC_DELTA) return 0;
+  if (p.ins.op == OP_OSC_DELTA || p.ins.op == OP_OSC_SHAPE) return 0;
+  if (p.ins.op == OP_OSC_PHASE) return 30 + (p.ins.n_ch ? 10 : 0);
   return 25 + (p.in_vw[0] >= 0 ? 100 : 0) + (p.ins.n_ch ? 10 : 0);
 }
 int osc_shape_cost(const Pending& p) {  // the stateless part a time-split copy shares
   if (p.ins.op == OP_OSC_DELTA) return 125;
+  if (p.ins.op == OP_OSC_PHASE) return 0;
   return (p.out_vw[0] >= 0 ? 90 : 0) + (p.out_vw[1] >= 0 ? 90 : 0) + (p.out_vw[2] >= 0 ? 100 : 0);
 }
 
@@ -48,7 +50,7 @@ int op_cost(const Pending& p) {
     case OP_MOOG_COEF: return 45;
     case OP_GRIDSEQ: case OP_PATSEQ: return 20;
     case OP_SAMPLE: return p.in_vw[1] >= 0 ? 70 : 40;
-    case OP_OSC: case OP_OSC_DELTA: {
+    case OP_OSC: case OP_OSC_DELTA: case OP_OSC_PHASE: case OP_OSC_SHAPE: {
       const int n = std::max(1, p.ins.flags >> 4);  // time-split copies share the shaping work
       return osc_phase_cost(p) + osc_shape_cost(p) / n;
     }
@@ -352,14 +354,47 @@ int compile_program(const srk_patch& patch, int max_warps, Program& prog, std::s
       }
       code.swap(with_delta);
     }
+    // SRK_OSC_PHASE_SPLIT=1 (experiment): an oscillator that would be time-split becomes OP_OSC_PHASE (the
+    // recurrence, once) + OP_OSC_SHAPE (stateless, time-split below) joined by a wire pair carrying the f64 phase,
+    // instead of n copies that each repeat the whole recurrence.
+    {
+      const char* ph_env = std::getenv("SRK_OSC_PHASE_SPLIT");
+      std::vector<Pending> with_phase;
+      for (Pending& p : code) {
+        if (ph_env && ph_env[0] == '1' && p.ins.op == OP_OSC && p.in_vw[0] < 0 && spare > 0 &&
+            (p.out_vw[0] >= 0 || p.out_vw[1] >= 0 || p.out_vw[2] >= 0)) {
+          --spare;
+          Pending ph = p;
+          ph.ins.op = OP_OSC_PHASE;
+          for (int j = 0; j < 3; ++j) ph.out_vw[j] = -1;
+          p.ins.op = OP_OSC_SHAPE;
+          for (int j = 0; j < 2; ++j) {
+            vw.push_back(VWire());
+            vw.back().last_use = 0;  // read by the shaper below
+            ph.out_vw[j] = (int)vw.size() - 1;
+            p.in_vw[j] = ph.out_vw[j];  // (the sync input stays with the phase instruction)
+          }
+          with_phase.push_back(ph);
+        }
+        with_phase.push_back(p);
+      }
+      code.swap(with_phase);
+    }
     std::vector<int> copies(code.size(), 1);
+    const char* sc_env = std::getenv("SRK_SHAPE_COST_SCALE");  // experiment knobs
+    const int shape_scale = sc_env && *sc_env ? std::max(1, std::atoi(sc_env)) : 1;
+    const char* mc_env = std::getenv("SRK_MAX_COPIES");
+    const int env_copies = mc_env && *mc_env ? std::min(8, std::max(1, std::atoi(mc_env))) : 4;
     for (;;) {  // double the copies of the currently slowest splittable oscillator while warps last
       int best = -1, best_cost = 60;  // per-copy cost under which splitting further is pointless
       for (size_t i = 0; i < code.size(); ++i) {
         const Pending& p = code[i];
-        const bool splittable = (p.ins.op == OP_OSC && p.in_vw[0] < 0) || p.ins.op == OP_OSC_DELTA;
-        if (!splittable || copies[i] >= 4 || spare < copies[i]) continue;
-        const int c = osc_phase_cost(p) + osc_shape_cost(p) / copies[i];
+        const bool splittable = (p.ins.op == OP_OSC && p.in_vw[0] < 0) || p.ins.op == OP_OSC_DELTA || p.ins.op == OP_OSC_SHAPE;
+        // stateless pieces may go to 8 copies (K / 8 is still a multiple of the sample group); an OP_OSC copy
+        // repeats the recurrence, so 4 is where that stops paying
+        const int max_copies = p.ins.op == OP_OSC ? 4 : env_copies;
+        if (!splittable || copies[i] >= max_copies || spare < copies[i]) continue;
+        const int c = osc_phase_cost(p) + shape_scale * osc_shape_cost(p) / copies[i];
         if (c > best_cost) { best = (int)i; best_cost = c; }
       }
       if (best < 0) break;

@@ -35,6 +35,9 @@ enum Op : uint8_t {
   OP_PATSEQ,      // pattern sequencer: in step, sync; out ports flags..flags+2 of its 9; table at aux
   OP_OSC_DELTA,   // out[0..1] <- lo / hi words of delta = 440 * 2^(cv + val) / sample_rate per sample (f64)
   OP_SAMPLE,      // sample player: in gate, cv; out[0]; descriptor (WaveDesc) at tables[aux]
+  OP_OSC_PHASE,   // the oscillator's phase recurrence alone: in[1] sync, in[2..3] delta (n_ch = 1); out[0..1] <- lo / hi
+                  // words of the phase each sample is shaped at (f64); owns the oscillator's state
+  OP_OSC_SHAPE,   // the stateless rest: in[0..1] phase, in[2..3] delta (n_ch = 1, else the voice's constant); out sine, square, saw
 };
 
 // Instr::flags

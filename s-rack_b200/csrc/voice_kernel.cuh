@@ -235,6 +235,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) render_voices_kernel(const Ren
       case OP_MOOG_COEF: run_resident<dsp::MoogCoefOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_GRIDSEQ: run_resident<dsp::GridSeqOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_OSC_DELTA: run_resident<dsp::OscDeltaOp>(ins, ln, a, n_chunks, n_iter); break;
+      case OP_OSC_PHASE: run_resident<dsp::OscPhaseOp>(ins, ln, a, n_chunks, n_iter); break;
+      case OP_OSC_SHAPE: run_resident<dsp::OscShapeOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_PATSEQ: run_resident<dsp::PatSeqOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_SAMPLE: run_resident<dsp::SampleOp>(ins, ln, a, n_chunks, n_iter); break;
       case OP_ADSR: run_resident<dsp::AdsrOp>(ins, ln, a, n_chunks, n_iter); break;
@@ -261,6 +263,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) render_voices_kernel(const Ren
           case OP_MOOG: run_once<dsp::MoogOp>(ins, ln, kk); break;
           case OP_MOOG_COEF: if constexpr (!SOLO) run_once<dsp::MoogCoefOp>(ins, ln, kk); break;
           case OP_OSC_DELTA: if constexpr (!SOLO) run_once<dsp::OscDeltaOp>(ins, ln, kk); break;
+          case OP_OSC_PHASE: if constexpr (!SOLO) run_once<dsp::OscPhaseOp>(ins, ln, kk); break;
+          case OP_OSC_SHAPE: if constexpr (!SOLO) run_once<dsp::OscShapeOp>(ins, ln, kk); break;
           case OP_GRIDSEQ: if constexpr (FULL) run_once<dsp::GridSeqOp>(ins, ln, kk); break;
           case OP_PATSEQ: if constexpr (FULL) run_once<dsp::PatSeqOp>(ins, ln, kk); break;
           case OP_SAMPLE: if constexpr (FULL) run_once<dsp::SampleOp>(ins, ln, kk); break;
