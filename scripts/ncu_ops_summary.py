@@ -21,6 +21,24 @@ def fn_of(line_no):
             name = n
     return name
 
+# voice_kernel.cuh: the output / mix / ring helpers are regions of their own; the rest of that file (resident
+# loops, barriers, the interpreter) stays with the op whose body precedes it in the SASS
+vk = os.path.join(os.path.dirname(dsp), "voice_kernel.cuh")
+vk_starts = []
+if os.path.exists(vk):
+    for i, line in enumerate(open(vk), 1):
+        m = re.match(r"__device__ __forceinline__ void (run_output|run_mix|run_ring_load|run_ring_store)\(", line)
+        if m:
+            vk_starts.append((i, m.group(1)))
+        elif re.match(r"(template|// A warp that owns ONE instruction)", line) and vk_starts and vk_starts[-1][1] != "":
+            vk_starts.append((i, ""))
+def vk_fn_of(line_no):
+    name = ""
+    for s_, n in vk_starts:
+        if s_ <= line_no:
+            name = n
+    return name
+
 rows = list(csv.reader(open(dump, errors="replace")))
 cur_file, hdr, cur_line = None, None, None
 insts = []  # (addr, file, line, sass, samples, barrier, executed)
@@ -53,6 +71,10 @@ for addr, f, line, sass, samp, bar, ex in insts:
     if f == "dsp.cuh":
         fn = fn_of(line)
         if fn not in LEAF:
+            region = fn
+    elif f == "voice_kernel.cuh":
+        fn = vk_fn_of(line)
+        if fn:
             region = fn
     elif f == "engine.cu":
         region = "engine.cu"
