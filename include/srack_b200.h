@@ -223,8 +223,11 @@ SRK_API int srk_write_wav(const char* path, const float* planar, unsigned channe
  * Load empties the patch and rebuilds it: module list in the order the reference ends up with (the
  * file's reversed, ui.rs:652-660), ids, parameters, sequencer tables, Sample tables, connections
  * (entries naming unknown ids or bad ports are skipped like the reference's `let _ = set_input(..)`,
- * ui.rs:662-681; their count goes to *n_skipped_connections when non-NULL).  Serialized port buffers
- * and DSP state are not imported: every voice starts from X::new() state.  A file that contains a
+ * ui.rs:662-681; their count goes to *n_skipped_connections when non-NULL) and the DSP state the
+ * modules were saved with (phase, filter memory, envelope stage, step counters, play position,
+ * detectors): every voice starts from it and srk_reset() returns to it, like the reference's
+ * deserialized modules carry on from where they were saved.  Serialized port buffers are not imported
+ * (a wire the cycle breaker cut starts with an empty history).  A file that contains a
  * Freeverb module is refused with SRK_ERR_UNSUPPORTED and the patch is left as it was; a malformed file
  * gives SRK_ERR_ARG.  Per-voice parameter arrays are dropped (the file has one value per field).
  * Call srk_plan() afterwards (the reference plans at the end of deserialize). ------------------- */
@@ -259,7 +262,8 @@ SRK_API int srk_render(srk_patch* patch, size_t n_voices, size_t voice_offset, s
 SRK_API int srk_render_on_stream(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t n_samples,
                                  unsigned flags, float* stems, float* mix, void* cuda_stream);
 SRK_API int srk_sync(srk_patch* patch);
-/* Back to X::new() state for every module of every voice (and empty feedback history). */
+/* Back to X::new() state -- or the state a loaded .srk file carried -- for every module of every voice
+ * (and empty feedback history). */
 SRK_API int srk_reset(srk_patch* patch);
 
 /* ---- instrumentation ---------------------------------------------------- */

@@ -50,6 +50,7 @@ def lib():
         L.orc_set_sample.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_float]
         L.orc_exp2f.restype = C.c_float
         L.orc_exp2f.argtypes = [C.c_float]
+        L.orc_set_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
         L.orc_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_reset.argtypes = [C.c_void_p]
         L.orc_render.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
@@ -135,6 +136,13 @@ class OraclePatch:
         samples, rate = wav.load(data)
         self.set_sample(module, samples, rate)
 
+    def set_state(self, module, words):
+        """Deserialized DSP state of one module as device state words (uint32), see srk_file.state_words."""
+        w = np.ascontiguousarray(words, dtype=np.uint32)
+        rc = lib().orc_set_state(self._h, module, w.ctypes.data, w.size)
+        if rc:
+            raise ValueError(f"set_state failed rc={rc}")
+
     def set_adsr_sample_rate(self, module, sample_rate):
         """The `sample_rate` field an ADSR carries through a .srk file (set_audio_config never updates it)."""
         self.set_param(module, 100, sample_rate)
@@ -147,6 +155,9 @@ class OraclePatch:
         for variant, m in ff["modules"]:
             if variant == "ADSRModuleV0":
                 self.set_adsr_sample_rate(handles[m["id"]], m["sample_rate"])
+            words = srk_file.state_words(variant, m)
+            if words is not None:
+                self.set_state(handles[m["id"]], words)
         return handles
 
     def set_module_order(self, order):

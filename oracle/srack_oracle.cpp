@@ -72,6 +72,8 @@ struct TransitionDetector {
   }
 };
 
+inline float word_f32(uint32_t w) { float f; std::memcpy(&f, &w, 4); return f; }
+
 // ---- Philox4x32-10 (Salmon et al., SC'11), our seeded stand-in for rand::random
 inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
   for (int r = 0; r < 10; ++r) {
@@ -103,6 +105,8 @@ struct Module {
   virtual void calc() = 0;
   virtual void reset() = 0;
   virtual bool set_param(int pid, float v) = 0;
+  // DSP state from a deserialized module, as the device's state words (s-rack_b200/csrc/program.hpp)
+  virtual bool set_state(const uint32_t*, size_t) { return false; }
   // resolve_input, src/synth.rs:249-254: None -> AudioBuffer(None)
   const float* resolve(int i) const {
     if (!inputs[i]) return nullptr;
@@ -124,6 +128,13 @@ struct Oscillator : Module {
     if (pid == 0) { val = v; return true; }
     if (pid == 1) { antialiasing = v != 0.0f; return true; }
     return false;
+  }
+  bool set_state(const uint32_t* w, size_t n) override {  // pos (f64 lo, hi), sync detector
+    if (n != 3) return false;
+    const uint64_t b = (uint64_t)w[0] | ((uint64_t)w[1] << 32);
+    std::memcpy(&pos, &b, 8);
+    sync_detector.last = w[2] != 0;
+    return true;
   }
   // :43-48.  2.0_f64.powf(x): LLVM folds pow(2.0, x) to exp2(x) in optimised builds.
   double freq_hz(const float* cv, size_t i) const {
@@ -202,6 +213,13 @@ struct MoogFilter : Module {
     if (pid == 2) { exp_amt = v; return true; }
     return false;
   }
+  bool set_state(const uint32_t* w, size_t n) override {  // f, p, q, b[0..4], freq, res
+    if (n != 10) return false;
+    st.f = word_f32(w[0]); st.p = word_f32(w[1]); st.q = word_f32(w[2]);
+    for (int k = 0; k < 5; ++k) st.b[k] = word_f32(w[3 + k]);
+    st.freq = word_f32(w[8]); st.res = word_f32(w[9]);
+    return true;
+  }
   // :60-83; returns (b4, in - b4, 3*(b3-b4))
   void state_calc(float input, float frequency, float resonance, float& r0, float& r1, float& r2) {
     if (frequency != st.freq || resonance != st.res) {
@@ -266,6 +284,13 @@ struct ADSR : Module {
       case 100: sample_rate = v; return true;  // a deserialized ADSR keeps the rate it was saved with (adsr.rs:17,69-71)
     }
     return false;
+  }
+  bool set_state(const uint32_t* w, size_t n) override {  // phase, r_val, from_a_val, mode | gate_last << 8
+    if (n != 4 || (w[3] & 0xFF) > 4) return false;
+    phase = word_f32(w[0]); r_val = word_f32(w[1]); from_a_val = word_f32(w[2]);
+    mode = (Mode)(w[3] & 0xFF);
+    det.last = (w[3] >> 8) & 1;
+    return true;
   }
   void calc() override {
     const float* gate = resolve(0);
@@ -391,6 +416,12 @@ struct GridSequencer : Module {
     for (auto& o : outs) std::fill(o.begin(), o.end(), 0.0f);
   }
   bool set_param(int pid, float v) override { if (pid == 0) { steps_per_octave = (uint16_t)v; return true; } return false; }
+  bool set_state(const uint32_t* w, size_t n) override {  // step | step_last << 16 | sync_last << 17, last cv
+    if (n != 2) return false;
+    current_step = (uint16_t)(w[0] & 0xFFFF); det.last = (w[0] >> 16) & 1; sync_det.last = (w[0] >> 17) & 1;
+    last = word_f32(w[1]);
+    return true;
+  }
   void calc() override {
     const float* step_buf = resolve(0);
     const float* sync_buf = resolve(1);
@@ -429,6 +460,11 @@ struct PatternSequencer : Module {
     for (auto& o : outs) std::fill(o.begin(), o.end(), 0.0f);
   }
   bool set_param(int, float) override { return false; }
+  bool set_state(const uint32_t* w, size_t n) override {
+    if (n != 1) return false;
+    current_step = (uint16_t)(w[0] & 0xFFFF); det.last = (w[0] >> 16) & 1; sync_det.last = (w[0] >> 17) & 1;
+    return true;
+  }
   void calc() override {
     const float* step_buf = resolve(0);
     const float* sync_buf = resolve(1);
@@ -479,6 +515,11 @@ struct Sample : Module {
     std::fill(outs[0].begin(), outs[0].end(), 0.0f);
   }
   bool set_param(int, float) override { return false; }
+  bool set_state(const uint32_t* w, size_t n) override {  // pos, playing | gate_last << 1
+    if (n != 2) return false;
+    pos = word_f32(w[0]); playing = w[1] & 1; det.last = (w[1] >> 1) & 1;
+    return true;
+  }
   void calc() override {
     const float* gate_in = resolve(0);
     const float* cv_in = resolve(1);
@@ -642,6 +683,7 @@ struct Patch {
   std::vector<ParamSetting> params;  // applied in order
   std::unordered_map<int, std::vector<int32_t>> sequences;  // module -> cells (rows x steps for the pattern sequencer)
   std::unordered_map<int, std::shared_ptr<const WaveBox>> waves;  // Sample module -> its WaveBox
+  std::unordered_map<int, std::vector<uint32_t>> states;          // module -> deserialized DSP state (device words)
   std::vector<int> order;            // all_modules order (module indices); empty = creation order
   // voice bank
   std::vector<Instance> voices;
@@ -681,6 +723,7 @@ struct Patch {
         if (wiring[m][i])
           inst.modules[m]->inputs[i] = std::make_pair(inst.modules[wiring[m][i]->first].get(), (uint8_t)wiring[m][i]->second);
     apply_params(inst, voice);
+    for (const auto& kv : states) inst.modules[kv.first]->set_state(kv.second.data(), kv.second.size());
     inst.output = nullptr;
     std::vector<Module*> all;
     if (order.empty())
@@ -860,8 +903,22 @@ int orc_plan(void* h, int* out_plan, int* out_n, int* out_cuts, int* out_n_cuts)
 
 void orc_reset(void* h) {
   auto* p = static_cast<Patch*>(h);
-  for (auto& inst : p->voices)
+  for (auto& inst : p->voices) {
     for (auto& m : inst.modules) m->reset();
+    for (const auto& kv : p->states) inst.modules[kv.first]->set_state(kv.second.data(), kv.second.size());  // back to the loaded state
+  }
+}
+
+// The DSP state a deserialized module carries (enum_to_sharedsynthmodule, synth.rs:325-348, keeps it), given as
+// the device's per-voice state words; every voice starts from it.
+int orc_set_state(void* h, int module, const uint32_t* words, size_t n) {
+  auto* p = static_cast<Patch*>(h);
+  if (module < 0 || module >= (int)p->kinds.size()) return 1;
+  auto probe = make_module(p->kinds[module], p->cfg);
+  if (!probe->set_state(words, n)) return 2;
+  p->states[module] = std::vector<uint32_t>(words, words + n);
+  p->bank_dirty = true;
+  return 0;
 }
 
 // Render n_samples for voices [voice_offset, voice_offset + n_voices).  Runs

@@ -295,11 +295,39 @@ _N_INPUTS = {"OUTPUT": None, "OSCILLATOR": 2, "NOISE": 0, "GRID_SEQUENCER": 2, "
 _N_OUTPUTS = {"OUTPUT": 0, "OSCILLATOR": 3, "MOOG_FILTER": 3, "GRID_SEQUENCER": 3, "PATTERN_SEQUENCER": 9}
 
 
+def _f32(x):
+    return struct.unpack("<I", struct.pack("<f", x))[0]
+
+
+def state_words(variant, m):
+    """The DSP state a serialized module carries, in the device's per-voice state-word layout
+    (s-rack_b200/csrc/program.hpp): what a voice starts from after a load.  None = the kind has none."""
+    det = lambda d: 1 if d["last"] else 0
+    if variant == "OscillatorModuleV0":
+        b = struct.unpack("<Q", struct.pack("<d", m["pos"]))[0]
+        return [b & 0xFFFFFFFF, b >> 32, det(m["sync_detector"])]
+    if variant in ("MoogFilterModuleV0", "MoogFilterModuleV1"):
+        st = m["state"]
+        return [_f32(st["f"]), _f32(st["p"]), _f32(st["q"])] + [_f32(x) for x in st["b"]] + [_f32(st["freq"]), _f32(st["res"])]
+    if variant == "ADSRModuleV0":
+        mode = ["Attack", "Decay", "Sustain", "Release", "None"].index(m["mode"])
+        return [_f32(m["phase"]), _f32(m["r_val"]), _f32(m["from_a_val"]), mode | (det(m["transition_detector"]) << 8)]
+    if variant in ("GridSequencerModuleV0", "GridSequencerModuleV1"):
+        return [m["current_step"] | (det(m["transition_detector"]) << 16) | (det(m["sync_transition_detector"]) << 17),
+                _f32(m["last"])]
+    if variant == "PatternSequencerModuleV0":
+        return [m["current_step"] | (det(m["transition_detector"]) << 16) | (det(m["sync_transition_detector"]) << 17)]
+    if variant == "SampleModuleV0":
+        pos, playing = (0.0, False) if m["wavebox"]["new"] else (m["pos"], m["playing"])  # sample.rs:212-216
+        return [_f32(pos), (1 if playing else 0) | (det(m["transition_detector"]) << 1)]
+    return None
+
+
 def build(backend, file_format, channels=2):
     """Apply a decoded file to any backend with the patch verbs (module_create, connect, set_param,
     set_sequence, set_sample) -> {id: handle}.  Module list = the file's reversed (unpack_modules pops
     from the back, ui.rs:652-660); connections back to front, unknown ids / bad ports skipped
-    (ui.rs:662-681).  DSP state and port buffers in the file are not applied."""
+    (ui.rs:662-681).  The DSP state in the file is applied by the caller (state_words); port buffers are not."""
     import numpy as np
     handles, kinds = {}, {}
     for variant, m in reversed(file_format["modules"]):

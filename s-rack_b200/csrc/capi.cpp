@@ -354,6 +354,7 @@ int srk_patch_load_srk(srk_patch* p, const void* bytes, size_t n_bytes, size_t* 
       m->wave_new = false;  // a fresh voice starts rewound anyway
     }
     if (fm.has_adsr_rate) m->adsr_sample_rate = fm.adsr_sample_rate;  // set_audio_config leaves it alone (adsr.rs:69-71)
+    m->init_state = fm.state;  // phase, filter memory, envelope stage, step counters, play position
   }
   // unpack_connections pops from the back too (ui.rs:673): of two entries for one input the EARLIER wins
   size_t skipped = 0;

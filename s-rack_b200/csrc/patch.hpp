@@ -49,6 +49,9 @@ struct srk_module {
   std::vector<float> wave;
   float wave_rate = 0.0f;
   bool wave_new = false;
+  // DSP state a loaded .srk file carried (device state words, program.hpp); empty = X::new().  Every voice starts
+  // from it and srk_reset() returns to it.
+  std::vector<uint32_t> init_state;
   uint16_t osc_sample_rate = 0;  // Oscillator / Sample: follows set_audio_config (oscillator.rs:83-84, sample.rs:120-123)
   float adsr_sample_rate = 0;    // ADSR: fixed at construction (adsr.rs:47,69-71)
   int n_outputs() const;

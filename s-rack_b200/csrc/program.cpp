@@ -148,10 +148,12 @@ int compile_program(const srk_patch& patch, int max_warps, Program& prog, std::s
     p.out_vw[0] = ring_load_wire[kv.second];
     code.push_back(p);
   }
+  const srk_module* state_owner = nullptr;  // module being emitted: a loaded file's state overrides X::new()
   auto alloc_state = [&](int words, std::initializer_list<uint32_t> init) {
     uint16_t first = (uint16_t)prog.state_init.size();
     std::vector<uint32_t> v(init);
     v.resize(words, 0u);
+    if (state_owner && (int)state_owner->init_state.size() == words) v = state_owner->init_state;
     prog.state_init.insert(prog.state_init.end(), v.begin(), v.end());
     return first;
   };
@@ -162,6 +164,7 @@ int compile_program(const srk_patch& patch, int max_warps, Program& prog, std::s
   };
   for (const srk_module* mod : patch.plan) {
     const int m = patch.index_of(mod);
+    state_owner = mod;
     Pending p = blank();
     for (size_t i = 0; i < mod->inputs.size() && i < 4; ++i) p.in_vw[i] = in_wire[m][i];
     for (int port = 0; port < mod->n_outputs() && port < 3; ++port) {

@@ -19,9 +19,11 @@
 // What a load keeps: the module list (in the order the reference ends up with: unpack_modules pops
 // from the back, ui.rs:652-660, so the list is the file's REVERSED), ids, parameters, sequencer
 // tables, the Sample module's WaveBox, the connections (applied back to front like
-// unpack_connections, ui.rs:662-681: unknown ids and bad sink ports are skipped silently) and the
-// GUI positions (kept only to be written back).  What it drops: the serialized port buffers and DSP
-// state (phase, filter memory, envelope stage ...): every voice starts from X::new() state.
+// unpack_connections, ui.rs:662-681: unknown ids and bad sink ports are skipped silently), the DSP
+// state the modules were saved with (oscillator phase, filter memory, envelope stage, step counters,
+// play position, detectors: every voice starts from it, as the reference's deserialized modules do)
+// and the GUI positions (kept only to be written back).  What it drops: the serialized port buffers
+// (they only matter as the first block of history of a wire the cycle breaker cut).
 #include "srkfile.hpp"
 
 #include <cstring>
@@ -201,10 +203,37 @@ int variant_index(const Val& key) {
   return -1;
 }
 
+uint32_t f32_bits(double x) {
+  const float f = (float)x;
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  return u;
+}
+// TransitionDetector { last } (synth.rs:277): [bool] or {"last": bool}
+bool get_detector(const Val* v, bool& last) { return v && get_bool(field(*v, 0, "last"), last); }
+
 #define SRK_FIELD(expr, what)                                 \
   do {                                                        \
     if (!(expr)) { err = std::string("bad field: ") + what; return false; } \
   } while (0)
+
+// InternalMoogFilterState { f, p, q, b: [f32; 5], freq, res } (filter.rs:49-56) -> the ten device words
+bool decode_moog_state(const Val* sv, std::vector<uint32_t>& out) {
+  if (!sv) return false;
+  double f, p, q, fr, rs, b;
+  const Val* bv = field(*sv, 3, "b");
+  if (!get_num(field(*sv, 0, "f"), f) || !get_num(field(*sv, 1, "p"), p) || !get_num(field(*sv, 2, "q"), q) || !bv ||
+      !bv->is_seq() || bv->size() != 5 || !get_num(field(*sv, 4, "freq"), fr) || !get_num(field(*sv, 5, "res"), rs))
+    return false;
+  out = {f32_bits(f), f32_bits(p), f32_bits(q)};
+  for (size_t k = 0; k < 5; ++k) {
+    if (!seq_num(*bv, k, b)) return false;
+    out.push_back(f32_bits(b));
+  }
+  out.push_back(f32_bits(fr));
+  out.push_back(f32_bits(rs));
+  return true;
+}
 
 bool decode_module(int variant, const Val& st, SrkModule& m, std::string& err) {
   double x = 0;
@@ -225,6 +254,11 @@ bool decode_module(int variant, const Val& st, SrkModule& m, std::string& err) {
       bool aa = true;
       SRK_FIELD(get_bool(field(st, 7, "antialiasing"), aa), "Oscillator.antialiasing");
       m.param[SRK_OSC_ANTIALIASING] = aa ? 1.0f : 0.0f;
+      bool last = true;
+      SRK_FIELD(get_num(field(st, 6, "pos"), x) && get_detector(field(st, 8, "sync_detector"), last), "Oscillator state");
+      uint64_t pb;
+      std::memcpy(&pb, &x, 8);
+      m.state = {(uint32_t)pb, (uint32_t)(pb >> 32), last ? 1u : 0u};
       return true;
     }
     case 2:  // NoiseModule { id, out }
@@ -249,6 +283,13 @@ bool decode_module(int variant, const Val& st, SrkModule& m, std::string& err) {
       }
       m.seq_steps = m.sequence.size();
       SRK_FIELD(num(6, "steps_per_octave", m.param[SRK_GRIDSEQ_STEPS_PER_OCTAVE]), "GridSequencer.steps_per_octave");
+      bool l1 = true, l2 = true;
+      double step = 0, lastcv = 0;
+      SRK_FIELD(get_num(field(st, 7, "current_step"), step) && step >= 0 && step <= 65535 &&
+                    get_detector(field(st, 8, "transition_detector"), l1) &&
+                    get_detector(field(st, 9, "sync_transition_detector"), l2) && get_num(field(st, 10, "last"), lastcv),
+                "GridSequencer state");
+      m.state = {(uint32_t)step | (l1 ? 1u << 16 : 0u) | (l2 ? 1u << 17 : 0u), f32_bits(lastcv)};
       return true;
     }
     case 5: {  // PatternSequencerModule { id, gate_outs, sync_out, sequence: Vec<Vec<Option<bool>>>, ... }
@@ -265,6 +306,12 @@ bool decode_module(int variant, const Val& st, SrkModule& m, std::string& err) {
         }
       }
       m.seq_steps = steps;
+      bool l1 = true, l2 = true;
+      double step = 0;
+      SRK_FIELD(get_num(field(st, 4, "current_step"), step) && step >= 0 && step <= 65535 &&
+                    get_detector(field(st, 5, "transition_detector"), l1) &&
+                    get_detector(field(st, 6, "sync_transition_detector"), l2), "PatternSequencer state");
+      m.state = {(uint32_t)step | (l1 ? 1u << 16 : 0u) | (l2 ? 1u << 17 : 0u)};
       return true;
     }
     case 6:  // ADSRModule { id, a_sec, d_sec, s_val, r_sec, phase, mode, r_val, from_a_val, sample_rate, ... }
@@ -273,6 +320,23 @@ bool decode_module(int variant, const Val& st, SrkModule& m, std::string& err) {
                     num(3, "s_val", m.param[SRK_ADSR_S_VAL]) && num(4, "r_sec", m.param[SRK_ADSR_R_SEC]), "ADSR times");
       SRK_FIELD(num(9, "sample_rate", m.adsr_sample_rate), "ADSR.sample_rate");  // kept: adsr.rs:69-71 never updates it
       m.has_adsr_rate = true;
+      {
+        double phase = 0, r_val = 0, from_a = 0;
+        bool last = true;
+        const Val* mode = field(st, 6, "mode");
+        int mi = -1;  // ADSRMode (adsr.rs:27-33) in declaration order == the device encoding
+        if (mode && mode->type == Val::STR) {
+          static const char* const names[] = {"Attack", "Decay", "Sustain", "Release", "None"};
+          for (int k = 0; k < 5; ++k)
+            if (mode->s == names[k]) mi = k;
+        } else if (mode && mode->type == Val::INT) {
+          mi = (int)mode->i;
+        }
+        SRK_FIELD(mi >= 0 && mi <= 4 && get_num(field(st, 5, "phase"), phase) && get_num(field(st, 7, "r_val"), r_val) &&
+                      get_num(field(st, 8, "from_a_val"), from_a) && get_detector(field(st, 10, "transition_detector"), last),
+                  "ADSR state");
+        m.state = {f32_bits(phase), f32_bits(r_val), f32_bits(from_a), (uint32_t)mi | (last ? 1u << 8 : 0u)};
+      }
       return true;
     case 7: {  // VCAModule { id, buf, negative }
       m.kind = SRK_KIND_VCA;
@@ -285,11 +349,13 @@ bool decode_module(int variant, const Val& st, SrkModule& m, std::string& err) {
       m.kind = SRK_KIND_MOOG_FILTER;
       SRK_FIELD(num(2, "freq", m.param[SRK_MOOG_FREQ]) && num(3, "res", m.param[SRK_MOOG_RES]) &&
                     num(4, "exp_amt", m.param[SRK_MOOG_EXP_AMT]), "MoogFilterV0 parameters");
+      SRK_FIELD(decode_moog_state(field(st, 5, "state"), m.state), "MoogFilterV0 state");
       return true;
     case 9:  // MoogFilterModule { id, lowpass, bandpass, highpass, freq, res, exp_amt, state }
       m.kind = SRK_KIND_MOOG_FILTER;
       SRK_FIELD(num(4, "freq", m.param[SRK_MOOG_FREQ]) && num(5, "res", m.param[SRK_MOOG_RES]) &&
                     num(6, "exp_amt", m.param[SRK_MOOG_EXP_AMT]), "MoogFilter parameters");
+      SRK_FIELD(decode_moog_state(field(st, 7, "state"), m.state), "MoogFilter state");
       return true;
     case 10: {  // MonoMixerModule { id, gain: Vec<f32>, buf }
       m.kind = SRK_KIND_MONO_MIXER;
@@ -317,6 +383,12 @@ bool decode_module(int variant, const Val& st, SrkModule& m, std::string& err) {
       }
       SRK_FIELD(get_num(field(*wb, 1, "sample_rate"), x), "Sample.wavebox.sample_rate");
       m.wave_rate = (float)x;
+      bool is_new = false, playing = false, last = true;
+      double pos = 0;
+      SRK_FIELD(get_bool(field(*wb, 2, "new"), is_new) && get_detector(field(st, 1, "transition_detector"), last) &&
+                    get_num(field(st, 2, "pos"), pos) && get_bool(field(st, 5, "playing"), playing), "Sample state");
+      if (is_new) { pos = 0; playing = false; }  // the first calc() after the load rewinds (sample.rs:212-216)
+      m.state = {f32_bits(pos), (playing ? 1u : 0u) | (last ? 2u : 0u)};
       return true;
     }
     case 12: {  // MathModule { id, buf, constant, operation }

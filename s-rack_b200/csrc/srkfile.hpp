@@ -20,6 +20,8 @@ struct SrkModule {
   float wave_rate = 0.0f;
   float adsr_sample_rate = 0.0f;  // ADSR: the rate it was built with travels with the file (adsr.rs:17,69-71)
   bool has_adsr_rate = false;
+  // The DSP state the file carries, as device state words (program.hpp "Per-voice state words"); empty = X::new()
+  std::vector<uint32_t> state;
 };
 struct SrkConnection {
   std::string src_id, sink_id;

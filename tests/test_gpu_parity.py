@@ -440,8 +440,9 @@ def test_sampler_patch_is_bit_exact(srk, orc, cuda_device):
 
 def test_loaded_srk_files_render_like_the_oracle(srk, orc, cuda_device):
     """a .srk file goes through the product's C++ loader on one side and through the
-    schema-driven restatement onto the oracle on the other; the renders must agree (the serialized DSP
-    state and port buffers in the file are ignored by both)."""
+    schema-driven restatement onto the oracle on the other; the renders must agree.  The files carry
+    mid-performance DSP state (oscillator phase, filter memory, an envelope in Decay, step counters, a
+    playing sample): every voice starts from it; the port buffers in the file are ignored by both."""
     from oracle import srk_file as sf
     from test_srk_file import sequenced_file, subtractive_file
     for make, B, exact_ch in ((subtractive_file, 1024, ()), (sequenced_file, 512, (1,))):
@@ -459,14 +460,28 @@ def test_loaded_srk_files_render_like_the_oracle(srk, orc, cuda_device):
         for c in exact_ch:
             assert_parity(g[c], o[c], exact=True, what=f"{make.__name__} ch{c}")
         assert s["bit_identical"] > 0.98
-        # save -> load -> render gives the same bits (list order reversed twice = plan unchanged? no: compare to itself)
+        gp.reset()                                        # reset() returns to the loaded state
+        assert (gp.render(V, N, stems=True, mix=False)[0].view(np.uint32) == g.view(np.uint32)).all()
+        # save writes new() state: after save -> load -> save -> load (the list reversed twice = the same order)
+        # the same graph starts from scratch and must NOT sound like the file's mid-performance state
         gp2 = srk.Patch(srk.AudioConfig(48000, B, 2))
         gp2.load_srk(gp.save_srk())
-        gp3 = srk.Patch(srk.AudioConfig(48000, B, 2))
-        gp3.load_srk(gp2.save_srk())
-        gp3.plan()
-        g3, _ = gp3.render(V, N, stems=True, mix=False)
-        assert (g3.view(np.uint32) == g.view(np.uint32)).all()
+        fresh = srk.Patch(srk.AudioConfig(48000, B, 2))
+        fresh.load_srk(gp2.save_srk())
+        assert [m.get_id() for m in fresh.modules] == [m.get_id() for m in gp.modules]
+        fresh.plan()
+        f0 = fresh.render(V, 2 * B, stems=True, mix=False)[0]
+        assert not (f0 == g[:, :2 * B]).all(), "the file's state was not applied"
+        assert_parity(f0, orc_render_same_order(orc, sf, fresh, B, V, 2 * B), what=f"{make.__name__} from new() state")
+
+
+def orc_render_same_order(orc, sf, patch, B, V, N):
+    """The oracle on the file `patch` would load from: save twice so the module order survives the reversal."""
+    tmp = type(patch)(patch.audio_config)
+    tmp.load_srk(patch.save_srk())
+    op = orc.OraclePatch(48000, B, 2)
+    op.load_srk(tmp.save_srk())
+    return op.render(V, N)[0]
 
 
 def test_sample_reload_rewinds_and_keeps_the_detector(srk, orc, cuda_device):
