@@ -232,8 +232,9 @@ SRK_API int srk_write_wav(const char* path, const float* planar, unsigned channe
  * gives SRK_ERR_ARG.  Per-voice parameter arrays are dropped (the file has one value per field).
  * Call srk_plan() afterwards (the reference plans at the end of deserialize). ------------------- */
 SRK_API int srk_patch_load_srk(srk_patch* patch, const void* bytes, size_t n_bytes, size_t* n_skipped_connections);
-/* The patch as the reference would save it with freshly constructed modules (zeroed port buffers of
- * buffer_size samples, X::new() DSP state).  *bytes stays valid until the next save or patch destroy. */
+/* The patch as the reference would save it: zeroed port buffers of buffer_size samples, X::new() DSP state
+ * for modules built through this ABI, the loaded state for modules that came from a file (the device state
+ * of a render is per voice and is not written back).  *bytes stays valid until the next save or patch destroy. */
 SRK_API int srk_patch_save_srk(srk_patch* patch, const void** bytes, size_t* n_bytes);
 
 /* ---- planning: plan_execution(output, &all_modules, &mut plan), src/synth.rs:128-212,

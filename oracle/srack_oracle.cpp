@@ -518,6 +518,7 @@ struct Sample : Module {
   bool set_state(const uint32_t* w, size_t n) override {  // pos, playing | gate_last << 1
     if (n != 2) return false;
     pos = word_f32(w[0]); playing = w[1] & 1; det.last = (w[1] >> 1) & 1;
+    is_new = false;  // (a file whose WaveBox.new was set arrives here already rewound, srk_file.state_words)
     return true;
   }
   void calc() override {

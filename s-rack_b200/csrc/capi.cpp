@@ -387,6 +387,7 @@ int srk_patch_save_srk(srk_patch* p, const void** bytes, size_t* n_bytes) {
     fm.wave = m->wave;
     fm.wave_rate = m->wave_rate;
     fm.adsr_sample_rate = m->adsr_sample_rate;
+    fm.state = m->init_state;  // a loaded file's state is written back; modules built through the ABI save new() state
     f.modules.push_back(std::move(fm));
   }
   for (const srk_module* m : p->modules)  // capture_connections: per module, inputs in index order

@@ -444,7 +444,7 @@ struct Writer {
   }
   void variant(const char* name) { o.push_back(0x81); str(name); }
   void buffer(size_t n) { array(n); for (size_t k = 0; k < n; ++k) f32(0.0f); }  // AudioBuffer::new(Some(n)): zeros
-  void detector() { array(1); boolean(true); }                                    // TransitionDetector::new()
+  void detector(bool last = true) { array(1); boolean(last); }                    // TransitionDetector { last }; new(): true
 };
 
 }  // namespace
@@ -501,6 +501,7 @@ bool srk_file_decode(const void* bytes, size_t n_bytes, SrkFile& out, std::strin
 void srk_file_encode(const SrkFile& f, size_t buffer_size, uint16_t sample_rate, uint8_t channels,
                      std::vector<unsigned char>& o) {
   Writer w{o};
+  auto wf = [](uint32_t u) { float x; std::memcpy(&x, &u, 4); return x; };  // state word -> f32
   const size_t B = buffer_size;
   w.array(3);
   w.array(f.modules.size());
@@ -512,7 +513,17 @@ void srk_file_encode(const SrkFile& f, size_t buffer_size, uint16_t sample_rate,
         break;
       case SRK_KIND_OSCILLATOR:
         w.variant("OscillatorModuleV0"); w.array(9); w.str(m.id); w.f32(m.param[SRK_OSC_VAL]); w.uint(sample_rate);
-        w.buffer(B); w.buffer(B); w.buffer(B); w.f64(0.0); w.boolean(m.param[SRK_OSC_ANTIALIASING] != 0.0f); w.detector();
+        w.buffer(B); w.buffer(B); w.buffer(B);
+        {
+          double pos = 0.0;
+          bool last = true;
+          if (m.state.size() == 3) {
+            const uint64_t b = (uint64_t)m.state[0] | ((uint64_t)m.state[1] << 32);
+            std::memcpy(&pos, &b, 8);
+            last = m.state[2] != 0;
+          }
+          w.f64(pos); w.boolean(m.param[SRK_OSC_ANTIALIASING] != 0.0f); w.detector(last);
+        }
         break;
       case SRK_KIND_NOISE:
         w.variant("NoiseModuleV0"); w.array(2); w.str(m.id); w.buffer(B);
@@ -526,7 +537,12 @@ void srk_file_encode(const SrkFile& f, size_t buffer_size, uint16_t sample_rate,
         }
         w.uint(2);  // octaves (sequencer.rs:39; GUI only)
         w.uint((uint16_t)m.param[SRK_GRIDSEQ_STEPS_PER_OCTAVE]);
-        w.uint(0); w.detector(); w.detector(); w.f32(0.0f); w.boolean(true);  // current_step, detectors, last, ui_dirty
+        if (m.state.size() == 2) {  // current_step, detectors, last, ui_dirty
+          w.uint(m.state[0] & 0xFFFF); w.detector((m.state[0] >> 16) & 1); w.detector((m.state[0] >> 17) & 1); w.f32(wf(m.state[1]));
+        } else {
+          w.uint(0); w.detector(); w.detector(); w.f32(0.0f);
+        }
+        w.boolean(true);
         break;
       case SRK_KIND_PATTERN_SEQUENCER:
         w.variant("PatternSequencerModuleV0"); w.array(8); w.str(m.id);
@@ -540,13 +556,24 @@ void srk_file_encode(const SrkFile& f, size_t buffer_size, uint16_t sample_rate,
             if (c < 0) w.nil(); else w.boolean(c != 0);
           }
         }
-        w.uint(0); w.detector(); w.detector(); w.boolean(true);
+        if (m.state.size() == 1) {
+          w.uint(m.state[0] & 0xFFFF); w.detector((m.state[0] >> 16) & 1); w.detector((m.state[0] >> 17) & 1);
+        } else {
+          w.uint(0); w.detector(); w.detector();
+        }
+        w.boolean(true);
         break;
       case SRK_KIND_ADSR:
         w.variant("ADSRModuleV0"); w.array(13); w.str(m.id);
         for (int k = 0; k < 4; ++k) w.f32(m.param[k]);
-        w.f32(0.0f); w.str("None"); w.f32(0.0f); w.f32(0.0f); w.f32(m.adsr_sample_rate);  // phase, mode, r_val, from_a_val
-        w.detector(); w.buffer(B); w.boolean(true);
+        if (m.state.size() == 4) {  // phase, mode, r_val, from_a_val
+          static const char* const modes[] = {"Attack", "Decay", "Sustain", "Release", "None"};
+          w.f32(wf(m.state[0])); w.str(modes[(m.state[3] & 0xFF) <= 4 ? (m.state[3] & 0xFF) : 4]); w.f32(wf(m.state[1])); w.f32(wf(m.state[2]));
+          w.f32(m.adsr_sample_rate); w.detector((m.state[3] >> 8) & 1);
+        } else {
+          w.f32(0.0f); w.str("None"); w.f32(0.0f); w.f32(0.0f); w.f32(m.adsr_sample_rate); w.detector();
+        }
+        w.buffer(B); w.boolean(true);
         break;
       case SRK_KIND_VCA:
         w.variant("VCAModuleV0"); w.array(3); w.str(m.id); w.buffer(B); w.boolean(m.param[SRK_VCA_NEGATIVE] != 0.0f);
@@ -554,7 +581,14 @@ void srk_file_encode(const SrkFile& f, size_t buffer_size, uint16_t sample_rate,
       case SRK_KIND_MOOG_FILTER:
         w.variant("MoogFilterModuleV1"); w.array(8); w.str(m.id); w.buffer(B); w.buffer(B); w.buffer(B);
         for (int k = 0; k < 3; ++k) w.f32(m.param[k]);
-        w.array(6); w.f32(0); w.f32(0); w.f32(0); w.array(5); for (int k = 0; k < 5; ++k) w.f32(0); w.f32(0); w.f32(0);
+        w.array(6);
+        if (m.state.size() == 10) {
+          w.f32(wf(m.state[0])); w.f32(wf(m.state[1])); w.f32(wf(m.state[2]));
+          w.array(5); for (int k = 0; k < 5; ++k) w.f32(wf(m.state[3 + k]));
+          w.f32(wf(m.state[8])); w.f32(wf(m.state[9]));
+        } else {
+          w.f32(0); w.f32(0); w.f32(0); w.array(5); for (int k = 0; k < 5; ++k) w.f32(0); w.f32(0); w.f32(0);
+        }
         break;
       case SRK_KIND_MONO_MIXER:
         w.variant("MonoMixerModuleV0"); w.array(3); w.str(m.id);
@@ -562,10 +596,14 @@ void srk_file_encode(const SrkFile& f, size_t buffer_size, uint16_t sample_rate,
         w.buffer(B);
         break;
       case SRK_KIND_SAMPLE:
-        w.variant("SampleModuleV0"); w.array(7); w.str(m.id); w.detector(); w.f32(0.0f); w.buffer(B);
-        w.array(3); w.array(m.wave.size()); for (float x : m.wave) w.f32(x);
-        w.f32(m.wave_rate); w.boolean(!m.wave.empty());  // new: the loader rewinds at its first calc()
-        w.boolean(false); w.f32((float)sample_rate);
+        {
+          const bool st = m.state.size() == 2;  // pos, playing | gate_last << 1
+          w.variant("SampleModuleV0"); w.array(7); w.str(m.id); w.detector(st ? (m.state[1] >> 1) & 1 : true);
+          w.f32(st ? wf(m.state[0]) : 0.0f); w.buffer(B);
+          w.array(3); w.array(m.wave.size()); for (float x : m.wave) w.f32(x);
+          w.f32(m.wave_rate); w.boolean(!st && !m.wave.empty());  // new: a fresh table rewinds at its first calc()
+          w.boolean(st ? m.state[1] & 1 : false); w.f32((float)sample_rate);
+        }
         break;
       case SRK_KIND_ADD: case SRK_KIND_SUBTRACT: case SRK_KIND_MULTIPLY: {
         static const char* const names[] = {"Add", "Subtract", "Multiply"};

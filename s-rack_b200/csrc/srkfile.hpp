@@ -38,8 +38,8 @@ struct SrkFile {
 };
 
 bool srk_file_decode(const void* bytes, size_t n_bytes, SrkFile& out, std::string& err);
-// Writes what the reference would save for freshly constructed modules with these settings
-// (zeroed port buffers of `buffer_size`, X::new() DSP state).
+// Writes what the reference would save for modules with these settings: zeroed port buffers of `buffer_size`,
+// and the DSP state in SrkModule::state (X::new() state when that is empty).
 void srk_file_encode(const SrkFile& f, size_t buffer_size, uint16_t sample_rate, uint8_t channels,
                      std::vector<unsigned char>& out);
 

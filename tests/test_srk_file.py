@@ -130,19 +130,22 @@ def test_save_matches_the_schema_encoder_byte_for_byte(srk):
         p.load_srk(sf.dumps(ff))
         saved = p.save_srk()
         got = sf.loads(saved)  # strict decode: layout is exactly rmp-serde's
-        # expected: the loaded patch as fresh modules (new() state, zero buffers), list order = reversed file order
+        # expected: the loaded modules with zeroed port buffers and the state they came with, list order = reversed file order
         want_mods = []
         for variant, m in reversed(ff["modules"]):
             over = {k: v for k, v in m.items() if k in ("val", "antialiasing", "a_sec", "d_sec", "s_val", "r_sec", "negative",
                                                         "freq", "res", "exp_amt", "gain", "constant", "operation",
-                                                        "steps_per_octave")}
+                                                        "steps_per_octave",
+                                                        # the DSP state a loaded module carries is written back
+                                                        "pos", "sync_detector", "phase", "mode", "r_val", "from_a_val",
+                                                        "transition_detector", "sync_transition_detector", "state",
+                                                        "current_step", "last", "playing")}
             v_out = {"GridSequencerModuleV0": "GridSequencerModuleV1", "MoogFilterModuleV0": "MoogFilterModuleV1"}.get(variant, variant)
             if "Sequencer" in variant:
                 seq = m["sequence"]
                 over["sequence"] = [None if c is None else (c, False) for c in seq] if variant == "GridSequencerModuleV0" else seq
             if variant == "SampleModuleV0":
-                over["wavebox"] = dict(samples=m["wavebox"]["samples"], sample_rate=m["wavebox"]["sample_rate"],
-                                       new=bool(m["wavebox"]["samples"]))
+                over["wavebox"] = dict(samples=m["wavebox"]["samples"], sample_rate=m["wavebox"]["sample_rate"], new=False)
             want_mods.append(sf.new_module(v_out, m["id"], buffer_size=B, **over))
         ids = [m["id"] for _, m in want_mods]
         n_in = lambda mid: {v: k for k, v in enumerate(ids)}[mid]
