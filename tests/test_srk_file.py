@@ -196,3 +196,26 @@ def test_oracle_loads_the_same_graph(srk, orc):
         rev = {h: i for i, h in handles.items()}
         oplan, _ = op.plan()
         assert [rev[h] for h in oplan] == plan_ids
+
+
+def test_committed_srk_fixture(srk):
+    """tests/golden/subtractive_b16.srk (tests/golden/make_srk_golden.py): both codecs still read the bytes the
+    way they did when the fixture was written, state included."""
+    import os
+    data = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "subtractive_b16.srk"), "rb").read()
+    assert data == sf.dumps(subtractive_file(B=16))          # the encoder has not drifted
+    ff = sf.loads(data)
+    p = srk.Patch(srk.AudioConfig(48000, 16, 2))
+    assert p.load_srk(data) == 0
+    back = sf.loads(p.save_srk())
+    by_id = {m["id"]: (v, m) for v, m in back["modules"]}
+    for variant, m in ff["modules"]:
+        v2, m2 = by_id[m["id"]]
+        assert v2 == {"MoogFilterModuleV0": "MoogFilterModuleV1"}.get(variant, variant)
+        for key in ("val", "pos", "sync_detector", "antialiasing", "a_sec", "d_sec", "s_val", "r_sec", "phase", "mode", "r_val",
+                    "from_a_val", "transition_detector", "freq", "res", "exp_amt", "state", "negative", "constant",
+                    "operation", "gain"):
+            if key in m:
+                assert m2[key] == m[key], (variant, key)
+    adsr = by_id[IDS[2]][1]
+    assert adsr["mode"] == "Decay" and abs(adsr["phase"] - 0.4) < 1e-7 and by_id[IDS[0]][1]["pos"] == 0.3125
