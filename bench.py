@@ -394,11 +394,20 @@ def main():
 
 def run_cfg5(args, srk, torch, dist, rank, local_rank, world, dev, metric, unit):
     """BASELINE configs[4]: 8 distinct patch graphs x 32768 voices each, one graph per GPU at N = 8; with fewer
-    ranks every rank renders graphs rank, rank + N, ... one after the other (the job stays the same: strong
-    scaling).  One NCCL sum of the mix per step.  Stems stay in HBM (one graph's 12.6 GB buffer, reused)."""
+    ranks every rank renders its share of the graphs one after the other (the job stays the same: strong
+    scaling; shares balanced by measured kernel time).  One NCCL sum of the mix per step.  Stems stay in HBM (one graph's 12.6 GB buffer, reused)."""
     graphs = srk.patches.CFG5_GRAPHS
     V = args.voices_per_gpu or srk.patches.CFG5_VOICES
-    mine = list(range(rank, len(graphs), world))
+    # graphs -> ranks: longest-processing-time first, with the kernel times measured at 32768 voices
+    # (profiles/r03s_bench_cfg5_1gpu.json) as weights; every rank computes the same assignment
+    weight = {"cfg2": 20.3, "cfg3": 29.2, "cfg3b": 41.7, "cfg4": 57.4, "cfg5_bandpass": 20.4, "cfg5_two_osc": 31.5,
+              "cfg5_no_noise": 54.8, "cfg5_gated_sine": 19.6}
+    load, owner = [0.0] * world, {}
+    for g in sorted(range(len(graphs)), key=lambda i: (-weight.get(graphs[i].__name__, 30.0), i)):
+        r = min(range(world), key=lambda k: (load[k], k))
+        owner[g] = r
+        load[r] += weight.get(graphs[g].__name__, 30.0)
+    mine = [g for g in range(len(graphs)) if owner[g] == rank]
     C = 2
     patches = []
     for g in mine:
