@@ -155,3 +155,27 @@ def test_wide_output_is_chunked_by_four_channels(srk):
     outs = [i for i in code if i["op"] == "OUTPUT"]
     assert [(i["aux"], i["n_ch"]) for i in outs] == [(0, 4), (4, 2)]
     assert [(i["aux"], i["n_ch"]) for i in code if i["op"] == "MIX"] == [(0, 4), (4, 2)]
+
+
+def test_one_warp_schedule_block_shape(srk):
+    """One-warp schedule (no device needed: the sm_100 limits are assumed): a block holds all the groups its SM gets,
+    the chunk is the longest that still fits 227 KB of shared memory, and never shorter than 16 samples."""
+    limit, n_sm = 227 * 1024, 148
+    for name, V, want in (("cfg2", 65536, (14, 32)), ("cfg2", 32768, (7, 64)), ("cfg3", 65536, (14, 32)),
+                          ("cfg4", 32768, (7, 32)), ("cfg1", 65536, (14, 64)), ("cfg2", 262144, (14, 32))):
+        p = srk.Patch()
+        srk.patches.CONFIGS[name][0](p, 8)
+        p.plan()
+        info = p.program_info(V)
+        assert info["n_warps"] == 1 and info["n_stages"] == 1, (name, V)
+        assert (info["groups_per_block"], info["step_samples"]) == want, (name, V, info)
+        assert info["smem_bytes"] <= limit and info["block_threads"] == 32 * info["groups_per_block"]
+        groups = -(-V // 32)
+        per_sm = -(-groups // n_sm)
+        blocks_per_sm = -(-per_sm // 16)
+        assert info["groups_per_block"] == -(-per_sm // blocks_per_sm)
+        # the next longer chunk would not have fitted with that many groups
+        if info["step_samples"] < 128:
+            per_group = (info["smem_bytes"] - 2048) // info["groups_per_block"]  # minus (at most) the program image
+            tiles = info["n_tiles"] * 32 * 4
+            assert info["smem_bytes"] + info["groups_per_block"] * tiles * info["step_samples"] > limit, (name, V, per_group)
