@@ -126,7 +126,12 @@ __device__ __forceinline__ Port port(const Lane& ln, int slot) {
 template <int U>
 using UC = std::integral_constant<int, U>;
 
-constexpr int kGroup = 4;
+// Samples per straight-line group.  A translation unit may set SRK_SAMPLE_GROUP before including this header
+// (each kernel image is its own translation unit; nothing here is linked across them).
+#ifndef SRK_SAMPLE_GROUP
+#define SRK_SAMPLE_GROUP 4
+#endif
+constexpr int kGroup = SRK_SAMPLE_GROUP;
 
 // Runs body(UC<kGroup>, k) over full groups of samples in [k0, k1), body(UC<1>, k) over the tail.
 template <class Body>

@@ -1,5 +1,8 @@
 // SOLO instantiation of the voice kernel: one warp per 32-voice group (several groups per block) runs the whole program chunk
 // by chunk (the throughput schedule), for programs made of the BASELINE modules only.  sm_100a only.
+#ifdef SRK_SOLO_SAMPLE_GROUP
+#define SRK_SAMPLE_GROUP SRK_SOLO_SAMPLE_GROUP
+#endif
 #include "voice_kernel.cuh"
 
 namespace srk {

@@ -1,5 +1,8 @@
 // SOLO instantiation of the voice kernel with every module kind in the interpreter (sequencers,
 // sample player): one warp per 32-voice group, plan order.  sm_100a only.
+#ifdef SRK_SOLO_SAMPLE_GROUP
+#define SRK_SAMPLE_GROUP SRK_SOLO_SAMPLE_GROUP
+#endif
 #include "voice_kernel.cuh"
 
 namespace srk {
