@@ -281,8 +281,19 @@ typedef struct srk_program_info {
   uint32_t n_instr, step_samples, block_threads, smem_bytes;
   uint32_t n_wires, state_words, param_words, n_rings;
   uint32_t n_warps, n_stages, n_tiles, groups_per_block;
+  /* fused = 1: the launch uses the patch-specialised kernel (wires in registers, step_samples = the 32-sample
+   * output tile, groups_per_block = independent warps per block); registers per thread and local (spill) bytes
+   * are known once the kernel has been loaded by a render on this patch, else 0. */
+  uint32_t fused, fused_group, fused_regs, fused_local_bytes;
 } srk_program_info;
 SRK_API int srk_get_program_info(srk_patch* patch, size_t n_voices, srk_program_info* out);
+/* The CUDA C++ translation unit generated for this patch (the wiring; the DSP is csrc/fused_ops.cuh) when a
+ * render of n_voices would use a fused kernel, else an empty string.  Valid until the next call on the patch. */
+SRK_API int srk_fused_source(srk_patch* patch, size_t n_voices, const char** source, size_t* n_bytes);
+/* Compiles that kernel for sm_100a into the on-disk cubin cache (kernel_cache/ next to the library, or
+ * $SRK_KERNEL_CACHE) so that the first render does not pay for NVRTC.  Needs no GPU.  *compiled = 1 when a
+ * compilation happened, 0 when the cubin was cached already or the launch would not use a fused kernel. */
+SRK_API int srk_precompile(srk_patch* patch, size_t n_voices, int* compiled);
 /* The compiled, scheduled device program itself (what execute() becomes for n_voices voices):
  * one entry per instruction -- the modules of the plan in plan order (src/synth.rs:97-101), plus
  * ring loads/stores for the wires the cycle breaker cut (synth.rs:168-192), the stems / mixdown

@@ -19,7 +19,8 @@ class srk_audio_config(C.Structure):
 class srk_program_info(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("n_instr", "step_samples", "block_threads", "smem_bytes",
                                           "n_wires", "state_words", "param_words", "n_rings",
-                                          "n_warps", "n_stages", "n_tiles", "groups_per_block")]
+                                          "n_warps", "n_stages", "n_tiles", "groups_per_block",
+                                          "fused", "fused_group", "fused_regs", "fused_local_bytes")]
 
 
 class srk_instr_info(C.Structure):
@@ -105,6 +106,8 @@ _SIGNATURES = {
     "srk_last_render_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "srk_launch_count": (C.c_uint64, [_P]),
     "srk_get_program_info": (C.c_int, [_P, C.c_size_t, C.POINTER(srk_program_info)]),
+    "srk_fused_source": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t)]),
+    "srk_precompile": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_int)]),
     "srk_get_program": (C.c_int, [_P, C.c_size_t, C.POINTER(srk_instr_info), C.c_size_t, C.POINTER(C.c_size_t),
                                   C.POINTER(srk_wire_info), C.c_size_t, C.POINTER(C.c_size_t)]),
 }

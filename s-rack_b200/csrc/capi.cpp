@@ -487,6 +487,20 @@ int srk_get_program_info(srk_patch* p, size_t n_voices, srk_program_info* out) {
   return srk::engine_program_info(p, n_voices, out);
 }
 
+int srk_fused_source(srk_patch* p, size_t n_voices, const char** source, size_t* n_bytes) {
+  if (!p || !source) return SRK_ERR_ARG;
+  int rc = srk::engine_fused_source(p, n_voices, p->fused_source);
+  if (rc != SRK_OK) return rc;
+  *source = p->fused_source.c_str();
+  if (n_bytes) *n_bytes = p->fused_source.size();
+  return SRK_OK;
+}
+
+int srk_precompile(srk_patch* p, size_t n_voices, int* compiled) {
+  if (!p) return SRK_ERR_ARG;
+  return srk::engine_precompile(p, n_voices, compiled);
+}
+
 int srk_get_program(srk_patch* p, size_t n_voices, srk_instr_info* instrs, size_t instr_cap, size_t* n_instr,
                     srk_wire_info* wires, size_t wire_cap, size_t* n_wires) {
   if (!p) return SRK_ERR_ARG;

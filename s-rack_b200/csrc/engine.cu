@@ -27,6 +27,7 @@
 #include <cstring>
 #include <vector>
 
+#include "fused.hpp"
 #include "voice_args.hpp"
 
 namespace srk {
@@ -102,6 +103,12 @@ struct Engine {
   // geometry of the last launch
   int block_threads = 0, step = 0, n_warps = 0, n_stages = 0;
   size_t smem_bytes = 0;
+  // fused (patch-specialised) kernel of the compiled program, when that is the schedule in use
+  bool fused = false, last_fused = false;
+  FusedSpec fspec;
+  const FusedKernel* fkernel = nullptr;
+  std::string fused_note;  // why the interpreter is used instead, if it is
+  std::vector<uint32_t> uniform_words;  // parameter word w for voice 0 of the range (read by fused kernels for uniform words)
 
   ~Engine() {
     if (device >= 0) {
@@ -269,6 +276,40 @@ static int chunk_for_length(const Program& prog, int K, size_t n_samples) {
   return K;
 }
 
+// SRK_FUSED: 1 = every launch uses the fused kernel, 0 = never, unset = wherever the one-warp schedule would run
+// (more voice groups than a pipeline per group pays for).
+static int fused_mode() { return env_int("SRK_FUSED", -1); }
+
+// Compiles the planned patch for n_voices: pipelined program, one-warp program or one-warp program + fused
+// kernel source.  `e` supplies the device limits (a probe without a device assumes sm_100).
+static int schedule_program(const srk_patch& patch, const Engine& e, size_t n_voices, Program& prog, std::vector<uint4>& blob,
+                            int& K, bool& fused, FusedSpec& spec, std::string& note, std::string& err) {
+  fused = false;
+  note.clear();
+  const int mode = fused_mode();
+  int rc = compile_program(patch, mode == 1 ? 1 : choose_max_warps(e, n_voices), prog, err);
+  if (rc != SRK_OK) return rc;
+  build_blob(prog, blob);
+  K = prog.n_warps > 1 && !pipelined_pays(e, prog, n_voices) ? 0 : choose_chunk(e, prog, blob.size(), n_voices);
+  if (K == 0 && prog.n_warps > 1) {  // does not fit or does not pay as a pipeline: one warp, plan order
+    rc = compile_program(patch, 1, prog, err);
+    if (rc != SRK_OK) return rc;
+    build_blob(prog, blob);
+    K = choose_chunk(e, prog, blob.size(), n_voices);
+  }
+  if (prog.n_warps == 1 && mode != 0) {
+    std::string why;
+    if (fused_generate(patch, prog, env_int("SRK_FUSED_GROUP", 4), env_int("SRK_FUSED_MINB", 4), spec, why) == SRK_OK) {
+      fused = true;
+      K = SRK_FUSED_TILE;
+    } else {
+      note = why;
+    }
+  }
+  if (K == 0) { err = "patch needs more shared memory than one block can have"; return SRK_ERR_LIMIT; }
+  return SRK_OK;
+}
+
 static int build_param_table(srk_patch* patch, Engine& e) {
   const size_t P = e.prog.param_src.size(), V = e.V;
   const size_t bytes = std::max<size_t>(P * V, 1) * sizeof(uint32_t);
@@ -317,6 +358,8 @@ static int build_param_table(srk_patch* patch, Engine& e) {
       }
     }
   }
+  e.uniform_words.assign(P, 0u);
+  for (size_t w = 0; w < P && V; ++w) e.uniform_words[w] = e.h_params[w * V];  // what a fused kernel reads for a uniform word
   SRK_CUDA(e.d_params.ensure(bytes));
   SRK_CUDA(cudaMemcpyAsync(e.d_params.p, e.h_params, P * V * sizeof(uint32_t), cudaMemcpyHostToDevice, e.stream));
   return SRK_OK;
@@ -349,17 +392,20 @@ static int engine_prepare(srk_patch* patch, size_t n_voices, size_t voice_offset
     // (a sequence-table edit alone rebuilds the program image but keeps the voice state: the state
     // layout depends on the wiring only)
     std::string err;
-    int rc = compile_program(*patch, want_warps, e.prog, err);
+    int rc = schedule_program(*patch, e, n_voices, e.prog, e.blob, e.chunk, e.fused, e.fspec, e.fused_note, err);
     if (rc != SRK_OK) { patch->last_error = err; return rc; }
-    build_blob(e.prog, e.blob);
-    e.chunk = e.prog.n_warps > 1 && !pipelined_pays(e, e.prog, n_voices) ? 0 : choose_chunk(e, e.prog, e.blob.size(), n_voices);
-    if (e.chunk == 0 && e.prog.n_warps > 1) {  // does not fit or does not pay as a pipeline: one warp, plan order
-      rc = compile_program(*patch, 1, e.prog, err);
-      if (rc != SRK_OK) { patch->last_error = err; return rc; }
-      build_blob(e.prog, e.blob);
-      e.chunk = choose_chunk(e, e.prog, e.blob.size(), n_voices);
+    e.fkernel = nullptr;
+    if (e.fused) {
+      std::string why;
+      if (fused_kernel(e.fspec, &e.fkernel, why) != SRK_OK) {
+        // no NVRTC here, or the generated source did not compile: the interpreter runs the same one-warp program
+        e.fused = false;
+        e.fused_note = why;
+        e.chunk = choose_chunk(e, e.prog, e.blob.size(), n_voices);
+        if (fused_mode() == 1) { patch->last_error = why; return SRK_ERR_UNSUPPORTED; }
+        if (e.chunk == 0) { patch->last_error = "patch needs more shared memory than one block can have"; return SRK_ERR_LIMIT; }
+      }
     }
-    if (e.chunk == 0) { patch->last_error = "patch needs more shared memory than one block can have"; return SRK_ERR_LIMIT; }
     SRK_CUDA(e.d_prog.ensure(e.blob.size() * sizeof(uint4)));
     SRK_CUDA(cudaMemcpyAsync(e.d_prog.p, e.blob.data(), e.blob.size() * sizeof(uint4), cudaMemcpyHostToDevice, e.stream));
     SRK_CUDA(e.d_state_init.ensure(std::max<size_t>(e.prog.state_init.size(), 1) * sizeof(uint32_t)));
@@ -398,6 +444,24 @@ static int engine_prepare(srk_patch* patch, size_t n_voices, size_t voice_offset
     e.uploaded_param_epoch = 0;
   }
   if (e.uploaded_param_epoch != patch->param_epoch) {
+    if (e.fused) {
+      // which parameter words are uniform over voices is part of a fused kernel's source: a parameter that became
+      // per-voice (or uniform again) selects another kernel
+      FusedSpec spec;
+      std::string why;
+      if (fused_generate(*patch, e.prog, e.fspec.group, e.fspec.min_blocks, spec, why) == SRK_OK && spec.source != e.fspec.source) {
+        const FusedKernel* k = nullptr;
+        if (fused_kernel(spec, &k, why) == SRK_OK) {
+          e.fspec = std::move(spec);
+          e.fkernel = k;
+        } else {
+          e.fused = false;
+          e.fused_note = why;
+          e.chunk = choose_chunk(e, e.prog, e.blob.size(), n_voices);
+          if (e.chunk == 0) { patch->last_error = "patch needs more shared memory than one block can have"; return SRK_ERR_LIMIT; }
+        }
+      }
+    }
     int rc = build_param_table(patch, e);
     if (rc != SRK_OK) return rc;
     SRK_CUDA(cudaStreamSynchronize(e.stream));  // staging buffer is reused by the next upload
@@ -430,12 +494,7 @@ int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t
 
   const Program& prog = e.prog;
   const size_t C = prog.channels;
-  const int K = chunk_for_length(prog, e.chunk, n_samples);  // <= e.chunk, which fitted
-  const int T = (int)prog.n_warps * 32;
   const unsigned n_groups = (unsigned)((n_voices + kVoicesPerGroup - 1) / kVoicesPerGroup);
-  const int G = prog.n_warps == 1 ? choose_solo_groups(e, prog, e.blob.size(), K, n_voices) : 1;
-  const size_t smem = smem_bytes_for(prog, e.blob.size(), K, G);
-  const unsigned grid = (n_groups + G - 1) / G;
   const bool device_out = flags & SRK_RENDER_DEVICE_OUT;
 
   float* d_stems = nullptr;
@@ -449,6 +508,56 @@ int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t
     else { SRK_CUDA(e.d_mix.ensure(C * n_samples * sizeof(float))); d_mix = (float*)e.d_mix.p; }
     SRK_CUDA(e.d_partial.ensure((size_t)n_groups * C * n_samples * sizeof(float)));
   }
+
+  int K = 0, G = 1, T = 0;
+  size_t smem = 0;
+  if (e.fused) {
+    // ---- fused kernel: one warp per voice group, blocks of `wpb` independent warps, everything in registers
+    const int wpb = std::max(1, std::min(env_int("SRK_FUSED_WPB", 1), kFusedMaxThreads / 32));
+    SrkFusedArgs args{};
+    args.state = (unsigned*)e.d_state.p;
+    args.params = (const unsigned*)e.d_params.p;
+    args.rings = (float*)e.d_rings.p;
+    args.stems = d_stems;
+    args.partial = mix ? (float*)e.d_partial.p : nullptr;
+    args.waves = (const float*)e.d_waves.p;
+    args.tables = reinterpret_cast<const int*>(reinterpret_cast<const unsigned char*>(e.d_prog.p) + blob_table_offset(prog));
+    args.V = (unsigned)n_voices;
+    args.voice_offset = (unsigned)voice_offset;
+    args.n_samples = (unsigned)n_samples;
+    args.C = (unsigned)C;
+    args.B = std::max<uint32_t>(prog.ring_len, 1);
+    args.ring_phase = (unsigned)(e.n_abs % args.B);
+    args.n_abs = (unsigned)e.n_abs;
+    args.seed_lo = (unsigned)patch->seed;
+    args.seed_hi = (unsigned)(patch->seed >> 32);
+    SrkTensorMap tmap{};
+    args.use_tma = 0;
+    if (d_stems && n_voices % 4 == 0 && env_int("SRK_FUSED_TMA", 1)) {
+      std::string why;
+      if (fused_stems_map(&tmap, d_stems, C, n_samples, n_voices, why) == SRK_OK) args.use_tma = 1;
+    }
+    for (size_t w = 0; w < e.uniform_words.size() && w < SRK_FUSED_MAX_UNIFORM; ++w) args.u[w] = e.uniform_words[w];
+    smem = e.fspec.smem_per_warp * wpb;
+    FusedKernel* fk = const_cast<FusedKernel*>(e.fkernel);
+    if (smem > fk->max_smem_set) {
+      SRK_CUDA(cudaFuncSetAttribute((const void*)fk->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SRK_CUDA(cudaFuncSetAttribute((const void*)fk->kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      fk->max_smem_set = smem;
+    }
+    void* kargs[] = {&args, &tmap};
+    const unsigned grid = (n_groups + wpb - 1) / wpb;
+    SRK_CUDA(cudaEventRecord(e.ev[1], work));
+    SRK_CUDA(cudaLaunchKernel((const void*)fk->kernel, dim3(grid), dim3(32u * wpb), kargs, smem, work));
+    K = SRK_FUSED_TILE;
+    G = wpb;
+    T = 32;
+  } else {
+  K = chunk_for_length(prog, e.chunk, n_samples);  // <= e.chunk, which fitted
+  T = (int)prog.n_warps * 32;
+  G = prog.n_warps == 1 ? choose_solo_groups(e, prog, e.blob.size(), K, n_voices) : 1;
+  smem = smem_bytes_for(prog, e.blob.size(), K, G);
+  const unsigned grid = (n_groups + G - 1) / G;
 
   RenderArgs a{};
   a.blob = (const uint4*)e.d_prog.p;
@@ -486,6 +595,7 @@ int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t
   SRK_CUDA(prog.n_warps > 1 ? launch_voices_pipelined(a, grid, (unsigned)T, smem, work)
            : beyond_baseline ? launch_voices_solo_full(a, grid, 32u * G, smem, work)
                              : launch_voices_solo(a, grid, 32u * G, smem, work));
+  }
   SRK_CUDA(cudaGetLastError());
   ++e.launches;
   SRK_CUDA(cudaEventRecord(e.ev[2], work));
@@ -507,6 +617,7 @@ int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t
   for (int mi : prog.wave_modules)
     if (patch->modules[mi]->wave_new) { patch->modules[mi]->wave_new = false; ++patch->table_epoch; }
   e.block_threads = prog.n_warps == 1 ? 32 * G : T;
+  e.last_fused = e.fused;
   e.step = K;
   e.n_warps = (int)prog.n_warps;
   e.n_stages = (int)prog.n_stages;
@@ -549,25 +660,25 @@ uint64_t engine_launches(const srk_patch* patch) { return patch->engine ? patch-
 
 // Compiles the planned patch the way a render of n_voices would (no device needed: the sm_100
 // limits are assumed when the patch has no engine yet).
-static int probe_program(srk_patch* patch, size_t n_voices, Program& prog, std::vector<uint4>& blob, int& K, int* solo_groups = nullptr) {
+static int probe_program(srk_patch* patch, size_t n_voices, Program& prog, std::vector<uint4>& blob, int& K, int* solo_groups = nullptr,
+                         bool* fused = nullptr, FusedSpec* spec = nullptr) {
   if (!patch->planned) { patch->last_error = "not planned"; return SRK_ERR_NOT_PLANNED; }
   Engine probe;
   probe.smem_optin = patch->engine ? patch->engine->smem_optin : 227 * 1024;
   probe.n_sm = patch->engine ? patch->engine->n_sm : 148;
   probe.smem_sm = patch->engine ? patch->engine->smem_sm : 228 * 1024;
-  std::string err;
-  int rc = compile_program(*patch, choose_max_warps(probe, n_voices), prog, err);
+  std::string err, note;
+  bool is_fused = false;
+  FusedSpec local;
+  int rc = schedule_program(*patch, probe, n_voices, prog, blob, K, is_fused, spec ? *spec : local, note, err);
   if (rc != SRK_OK) { patch->last_error = err; return rc; }
-  build_blob(prog, blob);
-  K = prog.n_warps > 1 && !pipelined_pays(probe, prog, n_voices) ? 0 : choose_chunk(probe, prog, blob.size(), n_voices);
-  if (K == 0 && prog.n_warps > 1) {
-    rc = compile_program(*patch, 1, prog, err);
-    if (rc != SRK_OK) { patch->last_error = err; return rc; }
-    build_blob(prog, blob);
+  if (is_fused && !fused) {  // the caller wants the interpreter's view of the one-warp program
+    is_fused = false;
     K = choose_chunk(probe, prog, blob.size(), n_voices);
+    if (K == 0) { patch->last_error = "patch needs more shared memory than one block can have"; return SRK_ERR_LIMIT; }
   }
-  if (K == 0) { patch->last_error = "patch needs more shared memory than one block can have"; return SRK_ERR_LIMIT; }
-  if (solo_groups) *solo_groups = prog.n_warps == 1 ? choose_solo_groups(probe, prog, blob.size(), K, n_voices) : 1;
+  if (fused) *fused = is_fused;
+  if (solo_groups) *solo_groups = prog.n_warps == 1 && !is_fused ? choose_solo_groups(probe, prog, blob.size(), K, n_voices) : 1;
   return SRK_OK;
 }
 
@@ -575,12 +686,13 @@ int engine_program_info(srk_patch* patch, size_t n_voices, srk_program_info* out
   Program prog;
   std::vector<uint4> blob;
   int K = 0, G = 1;
-  int rc = probe_program(patch, n_voices, prog, blob, K, &G);
+  bool fused = false;
+  FusedSpec spec;
+  int rc = probe_program(patch, n_voices, prog, blob, K, &G, &fused, &spec);
   if (rc != SRK_OK) return rc;
+  std::memset(out, 0, sizeof *out);
   out->n_instr = (uint32_t)prog.code.size();
   out->step_samples = (uint32_t)K;
-  out->block_threads = prog.n_warps * 32 * G;  // one-warp schedule: G voice groups (warps) per block
-  out->smem_bytes = (uint32_t)smem_bytes_for(prog, blob.size(), K, G);
   out->n_wires = (uint32_t)prog.wires.size();
   out->state_words = (uint32_t)prog.state_init.size();
   out->param_words = (uint32_t)prog.param_src.size();
@@ -588,7 +700,56 @@ int engine_program_info(srk_patch* patch, size_t n_voices, srk_program_info* out
   out->n_warps = prog.n_warps;
   out->n_stages = prog.n_stages;
   out->n_tiles = prog.n_tiles;
-  out->groups_per_block = (uint32_t)G;
+  if (fused) {
+    const int wpb = std::max(1, std::min(env_int("SRK_FUSED_WPB", 1), kFusedMaxThreads / 32));
+    out->fused = 1;
+    out->fused_group = (uint32_t)spec.group;
+    out->block_threads = 32u * wpb;
+    out->smem_bytes = (uint32_t)(spec.smem_per_warp * wpb);
+    out->groups_per_block = (uint32_t)wpb;
+    const Engine* e = patch->engine.get();
+    if (e && e->fused && e->fkernel && e->fspec.source == spec.source) {  // the kernel is loaded: what ptxas made of it
+      out->fused_regs = (uint32_t)e->fkernel->regs;
+      out->fused_local_bytes = (uint32_t)e->fkernel->local_bytes;
+    }
+  } else {
+    out->block_threads = prog.n_warps * 32 * G;  // one-warp schedule: G voice groups (warps) per block
+    out->smem_bytes = (uint32_t)smem_bytes_for(prog, blob.size(), K, G);
+    out->groups_per_block = (uint32_t)G;
+  }
+  return SRK_OK;
+}
+
+// The generated source of the fused kernel a render of n_voices would use (empty when it would not use one).
+int engine_fused_source(srk_patch* patch, size_t n_voices, std::string& source) {
+  Program prog;
+  std::vector<uint4> blob;
+  int K = 0;
+  bool fused = false;
+  FusedSpec spec;
+  int rc = probe_program(patch, n_voices, prog, blob, K, nullptr, &fused, &spec);
+  if (rc != SRK_OK) return rc;
+  source = fused ? spec.source : std::string();
+  return SRK_OK;
+}
+
+// Compiles that kernel into the on-disk cache (NVRTC; needs no GPU).  *compiled: 1 compiled now, 0 already cached
+// or no fused kernel for this launch shape.
+int engine_precompile(srk_patch* patch, size_t n_voices, int* compiled) {
+  Program prog;
+  std::vector<uint4> blob;
+  int K = 0;
+  bool fused = false;
+  FusedSpec spec;
+  if (compiled) *compiled = 0;
+  int rc = probe_program(patch, n_voices, prog, blob, K, nullptr, &fused, &spec);
+  if (rc != SRK_OK || !fused) return rc;
+  std::vector<char> cubin;
+  std::string key, err;
+  bool from_disk = false;
+  rc = fused_cubin(spec, cubin, key, &from_disk, nullptr, err);
+  if (rc != SRK_OK) { patch->last_error = err; return rc; }
+  if (compiled) *compiled = from_disk ? 0 : 1;
   return SRK_OK;
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <string>
 
 #include "patch.hpp"
 #include "program.hpp"
@@ -17,6 +18,8 @@ void engine_invalidate_state(srk_patch* patch);  // next render starts from X::n
 int engine_last_ms(srk_patch* patch, float* kernel_ms, float* total_ms);
 uint64_t engine_launches(const srk_patch* patch);
 int engine_program_info(srk_patch* patch, size_t n_voices, srk_program_info* out);
+int engine_fused_source(srk_patch* patch, size_t n_voices, std::string& source);
+int engine_precompile(srk_patch* patch, size_t n_voices, int* compiled);
 int engine_program_dump(srk_patch* patch, size_t n_voices, srk_instr_info* instrs, size_t instr_cap, size_t* n_instr,
                         srk_wire_info* wires, size_t wire_cap, size_t* n_wires);
 

@@ -1,0 +1,55 @@
+// Fused (patch-specialised) voice kernels: generation (fused_gen.cpp) and the runtime that turns the
+// generated source into a loaded kernel (fused_rt.cpp: in-memory cache -> cubin cache on disk -> NVRTC).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "fused_args.h"
+#include "patch.hpp"
+#include "program.hpp"
+
+namespace srk {
+
+constexpr int kFusedMaxThreads = 128;  // __launch_bounds__ of every fused kernel; blocks of 1..4 warps are launched
+
+struct FusedSpec {
+  std::string source;            // the generated translation unit (#includes "fused_ops.cuh")
+  std::vector<uint8_t> uniform;  // per parameter word: 1 = the kernel reads args.u[w], 0 = params[w][voice]
+  int n_distinct = 0;            // distinct wires feeding the Output module (one shared-memory tile pair each)
+  int channels = 0;
+  int group = 4;                 // samples per straight-line group
+  int min_blocks = 4;            // second __launch_bounds__ argument (register cap = 65536 / (128 * min_blocks))
+  size_t smem_per_warp = 0;
+};
+
+// `prog` must be the one-warp program of the planned patch (compile_program(patch, 1, ...)).
+int fused_generate(const srk_patch& patch, const Program& prog, int group, int min_blocks, FusedSpec& out, std::string& err);
+
+std::string fused_hash(const std::string& text, const std::string& salt);
+
+struct FusedKernel {
+  void* library = nullptr;  // cudaLibrary_t
+  void* kernel = nullptr;   // cudaKernel_t (accepted by cudaLaunchKernel / cudaFuncSetAttribute as is)
+  std::string key;
+  int regs = 0;
+  size_t local_bytes = 0;   // spills show up here
+  size_t max_smem_set = 0;
+  bool from_disk = false;
+  double compile_ms = 0.0;
+};
+
+// cubin for `spec` (cache key included): from the disk cache, else compiled with NVRTC for sm_100a and stored.
+// Needs no GPU.  SRK_OK or SRK_ERR_UNSUPPORTED (no NVRTC on this machine) / SRK_ERR_LIMIT (compile error: log in err).
+int fused_cubin(const FusedSpec& spec, std::vector<char>& cubin, std::string& key, bool* from_disk, double* compile_ms, std::string& err);
+
+// The loaded kernel for `spec` on the current device (cached per process by key).
+int fused_kernel(const FusedSpec& spec, const FusedKernel** out, std::string& err);
+
+// cuTensorMapEncodeTiled for the f32 [C][N][V] stems tensor with a {32, 32, 1} box.
+int fused_stems_map(SrkTensorMap* map, float* stems, uint64_t C, uint64_t N, uint64_t V, std::string& err);
+
+std::string fused_cache_dir();
+
+}  // namespace srk

@@ -74,6 +74,7 @@ struct srk_patch {
   std::string last_error;
   std::vector<std::pair<std::string, std::pair<float, float>>> positions;  // GUI positions of a loaded .srk, written back on save
   std::vector<unsigned char> saved;  // last srk_patch_save_srk() image
+  std::string fused_source;          // last srk_fused_source() text
   std::unique_ptr<srk::Engine, void (*)(srk::Engine*)> engine{nullptr, nullptr};
 
   int index_of(const srk_module* m) const {

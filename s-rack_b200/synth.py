@@ -311,6 +311,18 @@ class Patch:
         self._check(lib.srk_get_program_info(self._h, n_voices, C.byref(info)))
         return {f: getattr(info, f) for f, _ in info._fields_}
 
+    def fused_source(self, n_voices=0):
+        """CUDA C++ generated for this patch when a render of n_voices would use a fused kernel, else ''."""
+        src, n = C.c_char_p(), C.c_size_t()
+        self._check(lib.srk_fused_source(self._h, n_voices, C.byref(src), C.byref(n)))
+        return (src.value or b"").decode()
+
+    def precompile(self, n_voices=0):
+        """Compile that kernel into the on-disk cubin cache (NVRTC, no GPU needed) -> True when it compiled now."""
+        done = C.c_int()
+        self._check(lib.srk_precompile(self._h, n_voices, C.byref(done)))
+        return bool(done.value)
+
     def program(self, n_voices=0):
         """The compiled, scheduled device program for n_voices voices -> (instrs, wires): lists of
         dicts (op name, flags, warp, stage, in/out wire slots, ...) and (first_tile, n_tiles)."""

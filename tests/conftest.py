@@ -13,6 +13,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_generate_tests(metafunc):
+    """Every GPU test runs twice: with the schedule the engine picks on its own ("auto": pipelined warps for few
+    voices, the fused kernel for many) and with the fused kernel forced for every launch ("fused")."""
+    if "schedule" in metafunc.fixturenames:
+        gpu = metafunc.definition.get_closest_marker("gpu") is not None
+        metafunc.parametrize("schedule", ["auto", "fused"] if gpu else ["auto"], indirect=True)
+
+
+@pytest.fixture(autouse=True)
+def schedule(request, monkeypatch):
+    mode = getattr(request, "param", "auto")
+    if mode == "fused":
+        monkeypatch.setenv("SRK_FUSED", "1")
+    return mode
+
+
 @pytest.fixture(scope="session")
 def orc():
     """The CPU oracle (test infrastructure), built on demand with oracle/Makefile."""

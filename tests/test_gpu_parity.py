@@ -529,22 +529,35 @@ def test_schedule_invariance(srk, orc, cuda_device, monkeypatch, name, B):
     V, N = 77, 5003
     builder = getattr(srk.patches, name)
     results = []
-    for warps, step in [(1, 8), (1, 32), (1, 1), (4, 16), (16, 32), (16, 8), (2, 32)]:
-        monkeypatch.setenv("SRK_WARPS", str(warps))
-        monkeypatch.setenv("SRK_STEP", str(step))
+    # (fused, warps, chunk | samples per straight-line group): the interpreter's schedules, then the fused kernel
+    for fused, warps, step in [(0, 1, 8), (0, 1, 32), (0, 1, 1), (0, 4, 16), (0, 16, 32), (0, 16, 8), (0, 2, 32),
+                               (1, 1, 4), (1, 1, 1), (1, 1, 2), (1, 1, 8)]:
+        monkeypatch.setenv("SRK_FUSED", str(fused))
+        if fused:
+            monkeypatch.delenv("SRK_WARPS", raising=False)
+            monkeypatch.delenv("SRK_STEP", raising=False)
+            monkeypatch.setenv("SRK_FUSED_GROUP", str(step))
+        else:
+            monkeypatch.setenv("SRK_WARPS", str(warps))
+            monkeypatch.setenv("SRK_STEP", str(step))
         p = srk.Patch(srk.AudioConfig(48000, B, 2))
         builder(p, V)
         p.plan()
         info = p.program_info(V)
-        assert info["n_warps"] <= max(warps, 1) and info["step_samples"] <= step
+        assert info["fused"] == fused
+        if fused:
+            assert info["fused_group"] == step and info["n_warps"] == 1
+        else:
+            assert info["n_warps"] <= max(warps, 1) and info["step_samples"] <= step
         assert (info["n_warps"] > 1) == (info["n_stages"] > 1)
         st, mx = p.render(V, N, stems=True, mix=True)
         # a second call continues from the persisted state under the same schedule
         st2, _ = p.render(V, 997, stems=True, mix=True)
         results.append((info, np.concatenate([st, st2], axis=1), mx))
-    monkeypatch.delenv("SRK_WARPS")
-    monkeypatch.delenv("SRK_STEP")
+    for k in ("SRK_WARPS", "SRK_STEP", "SRK_FUSED_GROUP"):
+        monkeypatch.delenv(k, raising=False)
     assert any(r[0]["n_warps"] > 1 for r in results) and any(r[0]["n_warps"] == 1 for r in results)
+    assert any(r[0]["fused"] for r in results)
     for info, st, mx in results[1:]:
         assert (st.view(np.uint32) == results[0][1].view(np.uint32)).all(), info
         assert np.abs(mx - results[0][2]).max() <= 1e-5 * np.sqrt(V), info
@@ -561,6 +574,7 @@ def test_one_warp_schedule_groups_per_block(srk, orc, cuda_device, monkeypatch, 
     V, N = 333, 3001
     builder = getattr(srk.patches, name)
     monkeypatch.setenv("SRK_WARPS", "1")
+    monkeypatch.setenv("SRK_FUSED", "0")  # the interpreter's one-warp schedule is what this test is about
     results = []
     for groups, op_barrier in [(1, 0), (3, 0), (4, 1), (16, 0), (16, 1), (5, 0)]:
         monkeypatch.setenv("SRK_SOLO_GROUPS", str(groups))

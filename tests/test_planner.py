@@ -81,8 +81,9 @@ def test_no_output_gives_an_empty_plan(srk):
     assert e.value.status == srk.STATUS["ERR_NO_OUTPUT"]
 
 
-def test_compiled_program_marks_delayed_wires(srk):
+def test_compiled_program_marks_delayed_wires(srk, monkeypatch):
     """A wire whose source runs after its reader becomes a ring (one-block delay)."""
+    monkeypatch.setenv("SRK_FUSED", "0")  # the interpreter's chunk length is what is checked at the end
     p = srk.Patch()
     srk.patches.cfg3b(p, 4)
     p.plan()

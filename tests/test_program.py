@@ -11,6 +11,13 @@ from test_gpu_parity import _fuzz_patch
 PIPELINED_V, SOLO_V = 4096, 65536
 
 
+@pytest.fixture(autouse=True)
+def interpreter_schedules(monkeypatch):
+    """This module checks the two INTERPRETER schedules (pipelined warps / one warp per group); the fused kernel
+    that replaces the one-warp schedule by default has its own tests (tests/test_fused.py)."""
+    monkeypatch.setenv("SRK_FUSED", "0")
+
+
 def _build(srk, builder, B=1024, channels=2):
     p = srk.Patch(srk.AudioConfig(48000, B, channels))
     builder(p, 8)
