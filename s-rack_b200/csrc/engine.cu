@@ -276,18 +276,51 @@ static int chunk_for_length(const Program& prog, int K, size_t n_samples) {
   return K;
 }
 
-// SRK_FUSED: 1 = every launch uses the fused kernel, 0 = never, unset = wherever the one-warp schedule would run
-// (more voice groups than a pipeline per group pays for).
+// SRK_FUSED: 0 = never use the fused (patch-specialised) kernel, 1 = fail when it cannot be used, unset = use it
+// whenever it can be generated and compiled, the interpreter kernels otherwise.
 static int fused_mode() { return env_int("SRK_FUSED", -1); }
+
+// Build options of the fused kernel for a launch of n_voices.  With few voice groups per SM a group is cut into
+// stages (one warp each, a tile apart): the render is then bound by dependent-instruction latency and more warps per
+// SM are what hides it (cfg2 @ 4096 voices: 6.7 ms as one warp per group, profiles/r04c).
+static FusedOptions fused_options(const Engine& e, size_t n_voices) {
+  FusedOptions o;
+  o.group = env_int("SRK_FUSED_GROUP", 4);
+  o.min_blocks = env_int("SRK_FUSED_MINB", 4);
+  const size_t groups = (n_voices + kVoicesPerGroup - 1) / kVoicesPerGroup;
+  const size_t n_sm = (size_t)std::max(e.n_sm, 1);
+  const size_t per_sm = std::max<size_t>((groups + n_sm - 1) / n_sm, 1);
+  // up to 16 warps per SM (128 registers each); with more than 4 groups per SM one warp per group is faster
+  // (cfg4 @ 32768 voices: 25.4 ms against 30.1 ms as two stages, profiles/r04g)
+  o.stages = per_sm <= 4 ? (int)std::min<size_t>(8, 16 / per_sm) : 1;
+  if (env_int("SRK_FUSED_STAGES", 0) > 0) { o.stages = env_int("SRK_FUSED_STAGES", 1); o.exact_stages = true; }
+  o.tile = env_int("SRK_FUSED_TILE_ROWS", 32);
+  return o;
+}
+// ... and the variant that fits: every group an SM gets must be resident at once (the launch is one wave)
+static int fused_generate_fitting(const srk_patch& patch, const Engine& e, const Program& prog, size_t n_voices, FusedSpec& spec, std::string& why) {
+  FusedOptions o = fused_options(e, n_voices);
+  const size_t groups = (n_voices + kVoicesPerGroup - 1) / kVoicesPerGroup;
+  const size_t n_sm = (size_t)std::max(e.n_sm, 1);
+  const size_t per_sm = std::max<size_t>((groups + n_sm - 1) / n_sm, 1);
+  const size_t budget = (size_t)e.smem_sm - 1024 * std::min<size_t>(per_sm, 32);  // (1 KB per block is the system's)
+  for (;;) {
+    int rc = fused_generate(patch, prog, o, spec, why);
+    if (rc != SRK_OK) return rc;
+    if (env_int("SRK_DEBUG", 0))
+      std::fprintf(stderr, "[srk] fused: stages %d tile %d cross wires %d smem/group %zu x %zu groups/SM (budget %zu)\n", spec.stages, spec.tile,
+                   spec.n_cross, spec.smem_per_group, per_sm, budget);
+    if (spec.stages == 1 || spec.smem_per_group * per_sm <= budget) return SRK_OK;
+    if (o.tile == 32) o.tile = 16;  // shorter tiles first, then fewer stages
+    else { o.stages = spec.stages - 1; o.exact_stages = false; o.tile = 32; }
+  }
+}
 
 // Compiles the planned patch for n_voices: pipelined program, one-warp program or one-warp program + fused
 // kernel source.  `e` supplies the device limits (a probe without a device assumes sm_100).
-static int schedule_program(const srk_patch& patch, const Engine& e, size_t n_voices, Program& prog, std::vector<uint4>& blob,
-                            int& K, bool& fused, FusedSpec& spec, std::string& note, std::string& err) {
-  fused = false;
-  note.clear();
-  const int mode = fused_mode();
-  int rc = compile_program(patch, mode == 1 ? 1 : choose_max_warps(e, n_voices), prog, err);
+static int schedule_interpreter(const srk_patch& patch, const Engine& e, size_t n_voices, Program& prog, std::vector<uint4>& blob, int& K,
+                                std::string& err) {
+  int rc = compile_program(patch, choose_max_warps(e, n_voices), prog, err);
   if (rc != SRK_OK) return rc;
   build_blob(prog, blob);
   K = prog.n_warps > 1 && !pipelined_pays(e, prog, n_voices) ? 0 : choose_chunk(e, prog, blob.size(), n_voices);
@@ -297,17 +330,48 @@ static int schedule_program(const srk_patch& patch, const Engine& e, size_t n_vo
     build_blob(prog, blob);
     K = choose_chunk(e, prog, blob.size(), n_voices);
   }
-  if (prog.n_warps == 1 && mode != 0) {
-    std::string why;
-    if (fused_generate(patch, prog, env_int("SRK_FUSED_GROUP", 4), env_int("SRK_FUSED_MINB", 4), spec, why) == SRK_OK) {
-      fused = true;
-      K = SRK_FUSED_TILE;
-    } else {
-      note = why;
-    }
-  }
   if (K == 0) { err = "patch needs more shared memory than one block can have"; return SRK_ERR_LIMIT; }
   return SRK_OK;
+}
+
+static int schedule_program(const srk_patch& patch, const Engine& e, size_t n_voices, Program& prog, std::vector<uint4>& blob,
+                            int& K, bool& fused, FusedSpec& spec, std::string& note, std::string& err) {
+  fused = false;
+  note.clear();
+  const int mode = fused_mode();
+  int rc = SRK_OK;
+  if (mode != 0) {  // the fused kernel is generated from the one-warp program
+    rc = compile_program(patch, 1, prog, err);
+    if (rc != SRK_OK) return rc;
+    std::string why;
+    if (fused_generate_fitting(patch, e, prog, n_voices, spec, why) == SRK_OK) {
+      // Few voice groups per SM and a slowest stage that is one long module (a CV-driven oscillator: exp2, division
+      // and sin in one warp): the interpreter's pipeline splits such a module over several warps and wins
+      // (cfg3 @ 4096 voices: 4.2 ms against 14.7 ms, profiles/r04g).
+      const size_t groups = (n_voices + kVoicesPerGroup - 1) / kVoicesPerGroup;
+      const size_t per_sm = std::max<size_t>((groups + std::max(e.n_sm, 1) - 1) / std::max(e.n_sm, 1), 1);
+      bool use = true;
+      if (mode != 1 && per_sm <= 2 && spec.max_stage_cost > 90.0) {
+        Program pp;
+        std::vector<uint4> pb;
+        int pk = 0;
+        std::string perr;
+        if (schedule_interpreter(patch, e, n_voices, pp, pb, pk, perr) == SRK_OK && pp.n_warps > 1) {
+          prog = std::move(pp); blob = std::move(pb); K = pk;
+          note = "slowest fused stage too long: interpreter pipeline";
+          return SRK_OK;
+        }
+      }
+      if (use) {
+        build_blob(prog, blob);
+        fused = true;
+        K = spec.tile;
+        return SRK_OK;
+      }
+    }
+    note = why;
+  }
+  return schedule_interpreter(patch, e, n_voices, prog, blob, K, err);
 }
 
 static int build_param_table(srk_patch* patch, Engine& e) {
@@ -398,12 +462,12 @@ static int engine_prepare(srk_patch* patch, size_t n_voices, size_t voice_offset
     if (e.fused) {
       std::string why;
       if (fused_kernel(e.fspec, &e.fkernel, why) != SRK_OK) {
-        // no NVRTC here, or the generated source did not compile: the interpreter runs the same one-warp program
+        // no NVRTC here, or the generated source did not compile: the interpreter kernels take over
+        if (fused_mode() == 1) { patch->last_error = why; return SRK_ERR_UNSUPPORTED; }
+        rc = schedule_interpreter(*patch, e, n_voices, e.prog, e.blob, e.chunk, err);
+        if (rc != SRK_OK) { patch->last_error = err; return rc; }
         e.fused = false;
         e.fused_note = why;
-        e.chunk = choose_chunk(e, e.prog, e.blob.size(), n_voices);
-        if (fused_mode() == 1) { patch->last_error = why; return SRK_ERR_UNSUPPORTED; }
-        if (e.chunk == 0) { patch->last_error = "patch needs more shared memory than one block can have"; return SRK_ERR_LIMIT; }
       }
     }
     SRK_CUDA(e.d_prog.ensure(e.blob.size() * sizeof(uint4)));
@@ -449,16 +513,14 @@ static int engine_prepare(srk_patch* patch, size_t n_voices, size_t voice_offset
       // per-voice (or uniform again) selects another kernel
       FusedSpec spec;
       std::string why;
-      if (fused_generate(*patch, e.prog, e.fspec.group, e.fspec.min_blocks, spec, why) == SRK_OK && spec.source != e.fspec.source) {
+      if (fused_generate_fitting(*patch, e, e.prog, n_voices, spec, why) == SRK_OK && spec.source != e.fspec.source) {
         const FusedKernel* k = nullptr;
         if (fused_kernel(spec, &k, why) == SRK_OK) {
           e.fspec = std::move(spec);
           e.fkernel = k;
         } else {
-          e.fused = false;
-          e.fused_note = why;
-          e.chunk = choose_chunk(e, e.prog, e.blob.size(), n_voices);
-          if (e.chunk == 0) { patch->last_error = "patch needs more shared memory than one block can have"; return SRK_ERR_LIMIT; }
+          patch->last_error = why;  // (the state layout is the same, but the interpreter's program may be a pipelined one: replan)
+          return SRK_ERR_UNSUPPORTED;
         }
       }
     }
@@ -512,8 +574,9 @@ int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t
   int K = 0, G = 1, T = 0;
   size_t smem = 0;
   if (e.fused) {
-    // ---- fused kernel: one warp per voice group, blocks of `wpb` independent warps, everything in registers
-    const int wpb = std::max(1, std::min(env_int("SRK_FUSED_WPB", 1), kFusedMaxThreads / 32));
+    // ---- fused kernel: S warps (stages) per voice group, everything in registers; single-stage groups may share a block
+    const int S = std::max(1, e.fspec.stages);
+    const int wpb = S > 1 ? 1 : std::max(1, std::min(env_int("SRK_FUSED_WPB", 1), kFusedMaxThreads / 32));  // groups per block
     SrkFusedArgs args{};
     args.state = (unsigned*)e.d_state.p;
     args.params = (const unsigned*)e.d_params.p;
@@ -535,10 +598,10 @@ int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t
     args.use_tma = 0;
     if (d_stems && n_voices % 4 == 0 && env_int("SRK_FUSED_TMA", 1)) {
       std::string why;
-      if (fused_stems_map(&tmap, d_stems, C, n_samples, n_voices, why) == SRK_OK) args.use_tma = 1;
+      if (fused_stems_map(&tmap, d_stems, C, n_samples, n_voices, (unsigned)e.fspec.tile, why) == SRK_OK) args.use_tma = 1;
     }
     for (size_t w = 0; w < e.uniform_words.size() && w < SRK_FUSED_MAX_UNIFORM; ++w) args.u[w] = e.uniform_words[w];
-    smem = e.fspec.smem_per_warp * wpb;
+    smem = e.fspec.smem_per_group * wpb;
     FusedKernel* fk = const_cast<FusedKernel*>(e.fkernel);
     if (smem > fk->max_smem_set) {
       SRK_CUDA(cudaFuncSetAttribute((const void*)fk->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -548,10 +611,10 @@ int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t
     void* kargs[] = {&args, &tmap};
     const unsigned grid = (n_groups + wpb - 1) / wpb;
     SRK_CUDA(cudaEventRecord(e.ev[1], work));
-    SRK_CUDA(cudaLaunchKernel((const void*)fk->kernel, dim3(grid), dim3(32u * wpb), kargs, smem, work));
-    K = SRK_FUSED_TILE;
+    SRK_CUDA(cudaLaunchKernel((const void*)fk->kernel, dim3(grid), dim3(32u * S * wpb), kargs, smem, work));
+    K = e.fspec.tile;
     G = wpb;
-    T = 32;
+    T = 32 * S;
   } else {
   K = chunk_for_length(prog, e.chunk, n_samples);  // <= e.chunk, which fitted
   T = (int)prog.n_warps * 32;
@@ -616,11 +679,11 @@ int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t
   // the next render carries is_new = 0 again
   for (int mi : prog.wave_modules)
     if (patch->modules[mi]->wave_new) { patch->modules[mi]->wave_new = false; ++patch->table_epoch; }
-  e.block_threads = prog.n_warps == 1 ? 32 * G : T;
+  e.block_threads = e.fused ? T * G : prog.n_warps == 1 ? 32 * G : T;
   e.last_fused = e.fused;
   e.step = K;
-  e.n_warps = (int)prog.n_warps;
-  e.n_stages = (int)prog.n_stages;
+  e.n_warps = e.fused ? e.fspec.stages : (int)prog.n_warps;
+  e.n_stages = e.fused ? e.fspec.stages : (int)prog.n_stages;
   e.smem_bytes = smem;
   if (foreign) SRK_CUDA(cudaStreamWaitEvent(caller, e.ev[3], 0));  // caller's stream sees the results
   if (!(flags & SRK_RENDER_ASYNC)) SRK_CUDA(cudaStreamSynchronize(work));
@@ -672,10 +735,10 @@ static int probe_program(srk_patch* patch, size_t n_voices, Program& prog, std::
   FusedSpec local;
   int rc = schedule_program(*patch, probe, n_voices, prog, blob, K, is_fused, spec ? *spec : local, note, err);
   if (rc != SRK_OK) { patch->last_error = err; return rc; }
-  if (is_fused && !fused) {  // the caller wants the interpreter's view of the one-warp program
+  if (is_fused && !fused) {  // the caller wants the interpreter's program (srk_get_program)
     is_fused = false;
-    K = choose_chunk(probe, prog, blob.size(), n_voices);
-    if (K == 0) { patch->last_error = "patch needs more shared memory than one block can have"; return SRK_ERR_LIMIT; }
+    rc = schedule_interpreter(*patch, probe, n_voices, prog, blob, K, err);
+    if (rc != SRK_OK) { patch->last_error = err; return rc; }
   }
   if (fused) *fused = is_fused;
   if (solo_groups) *solo_groups = prog.n_warps == 1 && !is_fused ? choose_solo_groups(probe, prog, blob.size(), K, n_voices) : 1;
@@ -701,11 +764,13 @@ int engine_program_info(srk_patch* patch, size_t n_voices, srk_program_info* out
   out->n_stages = prog.n_stages;
   out->n_tiles = prog.n_tiles;
   if (fused) {
-    const int wpb = std::max(1, std::min(env_int("SRK_FUSED_WPB", 1), kFusedMaxThreads / 32));
+    const int wpb = spec.stages > 1 ? 1 : std::max(1, std::min(env_int("SRK_FUSED_WPB", 1), kFusedMaxThreads / 32));
     out->fused = 1;
     out->fused_group = (uint32_t)spec.group;
-    out->block_threads = 32u * wpb;
-    out->smem_bytes = (uint32_t)(spec.smem_per_warp * wpb);
+    out->n_warps = out->n_stages = (uint32_t)spec.stages;  // warps per voice group = pipeline stages
+    out->n_tiles = (uint32_t)(spec.n_cross_tiles + 2 * spec.n_distinct);
+    out->block_threads = 32u * spec.stages * wpb;
+    out->smem_bytes = (uint32_t)(spec.smem_per_group * wpb);
     out->groups_per_block = (uint32_t)wpb;
     const Engine* e = patch->engine.get();
     if (e && e->fused && e->fkernel && e->fspec.source == spec.source) {  // the kernel is loaded: what ptxas made of it

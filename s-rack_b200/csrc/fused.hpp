@@ -19,13 +19,27 @@ struct FusedSpec {
   std::vector<uint8_t> uniform;  // per parameter word: 1 = the kernel reads args.u[w], 0 = params[w][voice]
   int n_distinct = 0;            // distinct wires feeding the Output module (one shared-memory tile pair each)
   int channels = 0;
+  int n_ssa = 0;                 // wires (one local array each)
   int group = 4;                 // samples per straight-line group
   int min_blocks = 4;            // second __launch_bounds__ argument (register cap = 65536 / (128 * min_blocks))
-  size_t smem_per_warp = 0;
+  int stages = 1;                // warps per voice group: consecutive slices of the patch, one tile apart
+  int tile = 32;                 // samples per output / cross-stage tile
+  double max_stage_cost = 0.0;   // cost model: instructions per voice-sample of the slowest stage
+  int n_cross = 0;               // wires that cross a stage boundary
+  int n_cross_tiles = 0;         // ... and the tiles of their rings (stages spanned + 1 each)
+  size_t smem_per_group = 0;
+};
+
+struct FusedOptions {
+  int group = 4;       // samples per straight-line group
+  int min_blocks = 4;
+  int stages = 1;      // at most; the generator picks the count whose slowest stage is cheapest
+  bool exact_stages = false;  // ... unless told to use exactly that many (experiments, tests)
+  int tile = 32;
 };
 
 // `prog` must be the one-warp program of the planned patch (compile_program(patch, 1, ...)).
-int fused_generate(const srk_patch& patch, const Program& prog, int group, int min_blocks, FusedSpec& out, std::string& err);
+int fused_generate(const srk_patch& patch, const Program& prog, const FusedOptions& opt, FusedSpec& out, std::string& err);
 
 std::string fused_hash(const std::string& text, const std::string& salt);
 
@@ -48,7 +62,7 @@ int fused_cubin(const FusedSpec& spec, std::vector<char>& cubin, std::string& ke
 int fused_kernel(const FusedSpec& spec, const FusedKernel** out, std::string& err);
 
 // cuTensorMapEncodeTiled for the f32 [C][N][V] stems tensor with a {32, 32, 1} box.
-int fused_stems_map(SrkTensorMap* map, float* stems, uint64_t C, uint64_t N, uint64_t V, std::string& err);
+int fused_stems_map(SrkTensorMap* map, float* stems, uint64_t C, uint64_t N, uint64_t V, unsigned tile_rows, std::string& err);
 
 std::string fused_cache_dir();
 

@@ -24,12 +24,14 @@ typedef unsigned long long u64;
 
 #define FZ_DEV __device__ __forceinline__
 
-FZ_DEV float fadd(float a, float b) { return __fadd_rn(a, b); }
-FZ_DEV float fsub(float a, float b) { return __fsub_rn(a, b); }
-FZ_DEV float fmul(float a, float b) { return __fmul_rn(a, b); }
-FZ_DEV double dadd(double a, double b) { return __dadd_rn(a, b); }
-FZ_DEV double dsub(double a, double b) { return __dsub_rn(a, b); }
-FZ_DEV double dmul(double a, double b) { return __dmul_rn(a, b); }
+// (macros, not functions: with -lineinfo an inlined helper's instructions carry the HELPER's line, and the per-op
+// attribution of an ncu capture -- scripts/ncu_fused_summary.py -- needs the line of the op body that used it)
+#define fadd(a, b) __fadd_rn((a), (b))
+#define fsub(a, b) __fsub_rn((a), (b))
+#define fmul(a, b) __fmul_rn((a), (b))
+#define dadd(a, b) __dadd_rn((a), (b))
+#define dsub(a, b) __dsub_rn((a), (b))
+#define dmul(a, b) __dmul_rn((a), (b))
 // A value the compiler must treat as unknown.  Ops whose output is the same for every sample of a group (a Math
 // module with no inputs is how a patch spells a constant) write it through this: nvcc 12.9 mis-folds nested selects
 // over complementary predicates of ONE value at -O2 and above (select(x > 0, select(x <= 0, a, b), c) came out as
@@ -46,7 +48,9 @@ struct Ctx {
   const SrkFusedArgs* a;
   u32 v;         // voice inside this launch (idle lanes shadow the last voice and never store)
   u32 lane;
-  u32 group;     // voice group of 32 = this warp
+  u32 group;     // voice group of 32: this warp (single-stage kernels) or this warp and its S - 1 siblings
+  u32 stage;     // pipeline stage this warp runs (0 in single-stage kernels)
+  u32 gib;       // group index inside the thread block
   u32 n_active;  // voices of the group that exist
   bool active;
   FZ_DEV u32 ld_state(u32 w) const { return a->state[(size_t)w * a->V + v]; }
@@ -95,7 +99,11 @@ FZ_DEV double blep_eval_const(double t, double dt, double one_minus_dt, double r
   return lo ? r_lo : (hi ? r_hi : 0.0);
 }
 
-template <bool HAS_CV, bool HAS_SYNC, int OUTS, bool AA>
+// RATE = 1 ("audio rate", chosen by the host, which knows every voice's delta): constant delta with 2^-200 <= delta <
+// 1/8 for EVERY voice and large enough that most groups have some lane next to a discontinuity anyway -- the group
+// test is dropped and every group runs the branch-free path, so that the oscillator shares one basic block with
+// the modules around it (what limits a fused kernel is dependent-instruction latency: profiles/r04b).
+template <bool HAS_CV, bool HAS_SYNC, int OUTS, bool AA, int RATE>
 struct Osc {
   double pos, d0, val, sr;
   double om0, h1, h2, rd0;  // fast-path bounds and RN(1 / d0) for a constant delta (see run)
@@ -122,6 +130,7 @@ struct Osc {
     c.st_state(sw + 1, (u32)__double2hiint(pos));
     c.st_state(sw + 2, last ? 1u : 0u);
   }
+  FZ_DEV bool needs_generic() const { return false; }
 
   template <int U>
   FZ_DEV void shape(const double (&ps)[U], const double (&dl)[U], float* sine, float* square, float* saw) {
@@ -171,11 +180,59 @@ struct Osc {
     }
   }
 
+  // Constant delta in [2^-200, 1/8), no sync: straight-line code, per-sample wrap (pos + d0 < 1.125), polyBLEP through
+  // the constant-divisor division.  No vote, no call, no branch.
   template <int U>
+  FZ_DEV void run_small(float* sine, float* square, float* saw) {
+    constexpr bool SINE = OUTS & 1, SQUARE = OUTS & 2, SAW = OUTS & 4;
+    double ps[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      ps[j] = pos;
+      pos = wrap01(dadd(pos, d0));
+    }
+    if (SINE) {
+#pragma unroll
+      for (int j = 0; j < U; ++j) sine[j] = __double2float_rn(sin(dmul(dmul(ps[j], 3.14159265358979323846), 2.0)));
+    }
+    if (SQUARE || SAW) {
+      double pb0[U];
+      if (AA) {
+#pragma unroll
+        for (int j = 0; j < U; ++j) pb0[j] = blep_eval_const(ps[j], d0, om0, rd0);
+      }
+      if (SQUARE) {
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const float base = ps[j] < 0.5 ? -1.0f : 1.0f;
+          if (AA) {
+            const double p2 = wrap01(dadd(ps[j], 0.5));
+            square[j] = fsub(base, __double2float_rn(dsub(pb0[j], blep_eval_const(p2, d0, om0, rd0))));
+          } else {
+            square[j] = base;
+          }
+        }
+      }
+      if (SAW) {
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const float ramp = fsub(fmul(__double2float_rn(ps[j]), 2.0f), 1.0f);
+          saw[j] = AA ? fsub(ramp, __double2float_rn(pb0[j])) : ramp;
+        }
+      }
+    }
+  }
+
+  template <int U, bool FAST>
   FZ_DEV void run(const float* cv, const float* sync, float* sine, float* square, float* saw) {
     constexpr bool SINE = OUTS & 1, SQUARE = OUTS & 2, SAW = OUTS & 4;
     constexpr bool NEAR = AA && (SQUARE || SAW);
     double ps[U], dl[U];
+    if (!HAS_CV && !HAS_SYNC && RATE == 1) {
+      last = false;
+      run_small<U>(sine, square, saw);
+      return;
+    }
     if (!HAS_CV && !HAS_SYNC) {
       // Constant delta, no sync: the phases of the group are pos, pos + d, ... as long as none of them wraps,
       // and when in addition no sample sits within d of a discontinuity every polyBLEP term is 0.0.  One
@@ -209,43 +266,7 @@ struct Osc {
         return;
       }
       if (__all_sync(0xFFFFFFFFu, small)) {
-        // Somebody is near a discontinuity: straight-line code, per-sample wrap (pos + d0 < 1.125), polyBLEP through
-        // the constant-divisor division.  No vote, no call, no branch below this line.
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-          ps[j] = pos;
-          pos = wrap01(dadd(pos, d0));
-        }
-        if (SINE) {
-#pragma unroll
-          for (int j = 0; j < U; ++j) sine[j] = __double2float_rn(sin(dmul(dmul(ps[j], 3.14159265358979323846), 2.0)));
-        }
-        if (SQUARE || SAW) {
-          double pb0[U];
-          if (AA) {
-#pragma unroll
-            for (int j = 0; j < U; ++j) pb0[j] = blep_eval_const(ps[j], d0, om0, rd0);
-          }
-          if (SQUARE) {
-#pragma unroll
-            for (int j = 0; j < U; ++j) {
-              const float base = ps[j] < 0.5 ? -1.0f : 1.0f;
-              if (AA) {
-                const double p2 = wrap01(dadd(ps[j], 0.5));
-                square[j] = fsub(base, __double2float_rn(dsub(pb0[j], blep_eval_const(p2, d0, om0, rd0))));
-              } else {
-                square[j] = base;
-              }
-            }
-          }
-          if (SAW) {
-#pragma unroll
-            for (int j = 0; j < U; ++j) {
-              const float ramp = fsub(fmul(__double2float_rn(ps[j]), 2.0f), 1.0f);
-              saw[j] = AA ? fsub(ramp, __double2float_rn(pb0[j])) : ramp;
-            }
-          }
-        }
+        run_small<U>(sine, square, saw);
         return;
       }
     }
@@ -317,6 +338,7 @@ struct Noise {
     c.st_state(sw, (u32)n);
     c.st_state(sw + 1, (u32)(n >> 32));
   }
+  FZ_DEV bool needs_generic() const { return (n & 3u) != 0u; }  // (the same for every voice)
   FZ_DEV static float shape(u32 r) {
     const float u = fmul((float)(r >> 8), 1.0f / 16777216.0f);  // rand 0.8.5 Standard f32
     return fmul(fsub(u, 0.5f), 2.0f);
@@ -325,14 +347,16 @@ struct Noise {
     c[0] = (u32)blk; c[1] = (u32)(blk >> 32); c[2] = voice; c[3] = module;
     philox4x32_10(c, k0, k1);
   }
-  template <int U>
+  template <int U, bool FAST>
   FZ_DEV void run(float* out) {
     if (out) {
       u32 c[4];
-      if (U == 4 && (n & 3u) == 0u) {  // one Philox block per 4 samples (uniform over the warp: every voice has the same count)
-        draw(n >> 2, c);
+      if (FAST && U % 4 == 0) {  // one Philox block per 4 samples: the FAST body runs only while the counter is a multiple of 4
 #pragma unroll
-        for (int j = 0; j < U; ++j) out[j] = shape(c[j & 3]);
+        for (int j = 0; j < U; j += 4) {
+          draw((n + j) >> 2, c);
+          out[j] = shape(c[0]); out[j + 1] = shape(c[1]); out[j + 2] = shape(c[2]); out[j + 3] = shape(c[3]);
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < U; ++j) {
@@ -388,7 +412,8 @@ struct Moog {
     c.st_state(sw + 8, asu(c_freq)); c.st_state(sw + 9, asu(c_res));
   }
 
-  template <int U>
+  FZ_DEV bool needs_generic() const { return HAS_CV && __any_sync(0xFFFFFFFFu, virgin); }
+  template <int U, bool FAST>
   FZ_DEV void run(const float* audio, const float* cv, float* lowpass, float* bandpass, float* highpass) {
     float fj[U], pj[U], qj[U], in_[U], o3[U], o4[U];
     if (HAS_CV) {
@@ -397,14 +422,14 @@ struct Moog {
       for (int j = 0; j < U; ++j) fc[j] = fminf(fmaxf(fadd(freq, fmul(cv[j], exp_amt)), 0.0f), 0.9f);  // :213
 #pragma unroll
       for (int j = 0; j < U; ++j) moog_coef(fc[j], r, fj[j], pj[j], qj[j]);
-      if (__any_sync(0xFFFFFFFFu, virgin)) {  // only until (fc, r) first leaves (0, 0)
+      if (!FAST && __any_sync(0xFFFFFFFFu, virgin)) {  // only until (fc, r) first leaves (0, 0); FAST tiles have no virgin lane
 #pragma unroll
         for (int j = 0; j < U; ++j) {
           virgin = virgin & (fc[j] == 0.0f) & (r == 0.0f);
           if (virgin) { fj[j] = 0.0f; pj[j] = 0.0f; qj[j] = 0.0f; }
         }
       }
-      if (!virgin) { c_freq = fc[U - 1]; c_res = r; }
+      if (FAST || !virgin) { c_freq = fc[U - 1]; c_res = r; }
       f = fj[U - 1]; p = pj[U - 1]; q = qj[U - 1];
     } else {
 #pragma unroll
@@ -577,7 +602,7 @@ struct Adsr {
     return true;
   }
 
-  template <int U>
+  template <int U, bool FAST>
   FZ_DEV void run(const float* gate, float* out) {
     float g[U], o[U];
 #pragma unroll
@@ -596,7 +621,7 @@ struct Adsr {
 // ---- VCAModule::calc, src/synth/vca.rs:117-148 ---------------------------------------------------
 template <bool BOTH, bool NEGATIVE>
 struct Vca {
-  template <int U>
+  template <int U, bool FAST>
   FZ_DEV void run(const float* audio, const float* cv, float* out) const {
     if (!out) return;
 #pragma unroll
@@ -612,7 +637,7 @@ template <int CONNECTED>  // bit k: input k is connected
 struct Mixer {
   float gain[4];
   FZ_DEV void load(u32 g0, u32 g1, u32 g2, u32 g3) { gain[0] = asf(g0); gain[1] = asf(g1); gain[2] = asf(g2); gain[3] = asf(g3); }
-  template <int U>
+  template <int U, bool FAST>
   FZ_DEV void run(const float* in0, const float* in1, const float* in2, const float* in3, float* out) const {
     if (!out) return;
     float o[U];  // output.fill(0.0) then `*dst += src * gain` per connected input, in order
@@ -647,7 +672,7 @@ template <int WHICH /*0 add 1 sub 2 mul 3 non-linear*/, bool HAS_A, bool HAS_B>
 struct Math {
   float constant;
   FZ_DEV void load(u32 bits) { constant = asf(bits); }
-  template <int U>
+  template <int U, bool FAST>
   FZ_DEV void run(const float* i1, const float* i2, float* out) const {
     if (!out) return;
 #pragma unroll
@@ -680,7 +705,7 @@ struct GridSeq {
     c.st_state(sw, step | (last_step ? 1u << 16 : 0u) | (last_sync ? 1u << 17 : 0u));
     c.st_state(sw + 1, asu(last_cv));
   }
-  template <int U>
+  template <int U, bool FAST>
   FZ_DEV void run(const float* step_in, const float* sync_in, float* cv, float* gate, float* sync_out) {
 #pragma unroll
     for (int j = 0; j < U; ++j) {
@@ -721,7 +746,7 @@ struct PatSeq {
   FZ_DEV void store(const Ctx& c, u32 sw) const {
     c.st_state(sw, step | (last_step ? 1u << 16 : 0u) | (last_sync ? 1u << 17 : 0u));
   }
-  template <int U>
+  template <int U, bool FAST>
   FZ_DEV void run(const float* step_in, const float* sync_in, float* o0, float* o1, float* o2) {
     float* out[3] = {o0, o1, o2};
 #pragma unroll
@@ -803,7 +828,7 @@ struct Sample {
     c.st_state(sw, asu(pos));
     c.st_state(sw + 1, (playing ? 1u : 0u) | (last ? 2u : 0u));
   }
-  template <int U>
+  template <int U, bool FAST>
   FZ_DEV void run(const float* gate, const float* cv, float* out) {
 #pragma unroll
     for (int j = 0; j < U; ++j) {
@@ -864,9 +889,7 @@ struct Rings {
 // memory (one STS per sample).  When a tile is full: (a) stems -- lane 0 issues one TMA bulk tensor store per
 // channel, box {32 voices, 32 samples, 1 channel} of the [C][N][V] tensor (the box is clipped at N and V, so
 // ragged tails need no special case); tiles are double-buffered and the buffer is reused only after
-// cp.async.bulk.wait_group.read; (b) mix -- lane r sums sample row r over the 32 voices, starting at column
-// (absolute sample index) mod 32 so that the 32 lanes hit 32 different banks; the order therefore depends
-// only on the absolute sample index: renders are bit-identical however they are cut into calls.
+// cp.async.bulk.wait_group.read; (b) mix -- lane r sums sample row r over the 32 voices (see flush).
 FZ_DEV u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
 FZ_DEV void tma_store_3d(const SrkTensorMap* map, const float* tile, int x, int y, int z) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -878,18 +901,23 @@ FZ_DEV void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :
 FZ_DEV void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 FZ_DEV void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-constexpr int kTile = SRK_FUSED_TILE;
+#ifndef SRK_TILE
+#define SRK_TILE SRK_FUSED_TILE
+#endif
+constexpr int kTile = SRK_TILE;  // samples per output / cross-stage tile: 32, or 16 when shared memory is short
 constexpr int kTileElems = kTile * 32;
 
 // D distinct wires, C channels; chan_wire[c] = index of the distinct wire feeding channel c, or -1 (None: zeros).
 template <int D, int C>
 struct Out {
   float* tiles;  // this warp's [2][D][32][32]
+  float* cur;    // this lane's column of the buffer being filled
   u32 buf;
   bool want_tile;
 
-  FZ_DEV void init(const Ctx& c, float* smem_base, u32 warp_in_block) {
-    tiles = smem_base + (size_t)warp_in_block * 2 * D * kTileElems;
+  FZ_DEV void init(const Ctx& c, float* group_smem) {
+    tiles = group_smem;
+    cur = tiles + c.lane;
     buf = 0;
     want_tile = (c.a->stems != nullptr) | (c.a->partial != nullptr);
   }
@@ -901,9 +929,9 @@ struct Out {
     }
   }
   template <int U>
-  FZ_DEV void put(const Ctx& c, int d, u32 row, const float* w) {
+  FZ_DEV void put(const Ctx&, int d, u32 row, const float* w) {
     if (!want_tile) return;
-    float* t = tiles + ((size_t)buf * D + d) * kTileElems + row * 32 + c.lane;
+    float* t = cur + d * kTileElems + row * 32;
 #pragma unroll
     for (int j = 0; j < U; ++j) t[j * 32] = w[j];
   }
@@ -943,32 +971,38 @@ struct Out {
       }
     }
     if (a.partial) {
+      // lane r sums sample row r over the 32 voices, four voices per LDS.128, starting at the chunk (absolute sample
+      // index) mod 8: the eight lanes of a quarter warp read eight different chunks (no bank conflict), and the order
+      // of the additions is a function of the absolute sample index alone (chunked renders are bit-identical)
       __syncwarp();
-      const u32 r = c.lane;
-      const u32 start = (a.n_abs + n0 + r) & 31u;
+      const u32 r = c.lane & (kTile - 1);  // (kTile = 16: the upper half warp repeats the lower one and stores nothing)
+      const u32 s8 = (a.n_abs + n0 + r) & 7u;
       float sums[D];
 #pragma unroll
       for (int d = 0; d < D; ++d) {
-        const float* row = t0 + d * kTileElems + r * 32;
+        const float4* row4 = reinterpret_cast<const float4*>(t0 + d * kTileElems + r * 32);
         float acc = 0.0f;
         if (c.n_active == 32u) {
-          u32 col = start;
-#pragma unroll 8
-          for (int q = 0; q < 32; ++q) {
-            acc = fadd(acc, row[col]);
-            col = (col + 1) & 31u;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float4 x = row4[(s8 + k) & 7u];
+            acc = fadd(fadd(fadd(fadd(acc, x.x), x.y), x.z), x.w);
           }
         } else {
-          u32 col = start;
-          for (int q = 0; q < 32; ++q) {
-            const float x = row[col];
-            acc = fadd(acc, col < c.n_active ? x : 0.0f);
-            col = (col + 1) & 31u;
+#pragma unroll 1
+          for (int k = 0; k < 8; ++k) {
+            const u32 ch4 = (s8 + k) & 7u;
+            const float4 x = row4[ch4];
+            const u32 v0 = ch4 * 4u;
+            acc = fadd(acc, v0 < c.n_active ? x.x : 0.0f);
+            acc = fadd(acc, v0 + 1u < c.n_active ? x.y : 0.0f);
+            acc = fadd(acc, v0 + 2u < c.n_active ? x.z : 0.0f);
+            acc = fadd(acc, v0 + 3u < c.n_active ? x.w : 0.0f);
           }
         }
         sums[d] = acc;
       }
-      if (r < rows) {
+      if (c.lane < rows) {  // (rows <= kTile)
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) {
           float s = 0.0f;
@@ -979,19 +1013,80 @@ struct Out {
       }
       __syncwarp();
     }
-    if (a.use_tma && a.stems) buf ^= 1u;
+    if (a.use_tma && a.stems) {
+      buf ^= 1u;
+      cur = tiles + (size_t)buf * D * kTileElems + c.lane;
+    }
   }
   FZ_DEV void finish(const Ctx& c) {
     if (c.a->use_tma && c.a->stems && c.lane == 0) tma_wait_all();
   }
 };
 
+// ---- pipelined fused kernels: the S warps of a voice group run consecutive slices ("stages") of the patch, one tile
+//      apart; a wire that crosses stages is a ring of XD [kTile][32] tiles in shared memory; done[s] counts the tiles
+//      stage s has finished.  A stage waits until its producers have finished the tile it is about to read and until the
+//      consumers of its own wires have finished the tile whose ring slot it is about to overwrite.
+struct Pipe {
+  volatile u32* done;
+  float* xbase;  // this lane's column of cross tile 0
+  u32 lane;
+  FZ_DEV void init(const Ctx& c, float* group_smem, u32 out_floats, u32 cross_floats) {
+    xbase = group_smem + out_floats + c.lane;
+    done = reinterpret_cast<volatile u32*>(group_smem + out_floats + cross_floats);
+    lane = c.lane;
+  }
+  // Flag protocol: the producer's tile stores, then (after __syncwarp, which orders the warp's lanes) lane 0's release
+  // store of the count; the consumer's lane 0 spins with acquire loads, then __syncwarp.  CTA scope: every stage of a
+  // group lives in the same thread block.  (No __threadfence_block(): it compiles to MEMBAR.SC.CTA, which waits for
+  // the warp's outstanding global stores -- the stems -- on every tile.)
+  FZ_DEV void wait_ge(u32 stage, int need) const {
+    // EVERY lane polls (one broadcast LDS): a lane-0-only spin loop leaves the warp split into two divergent halves for
+    // the rest of the tile, and every instruction of the tile then issues twice (profiles/r04f: 8.7 ms instead of 7.0)
+    const u32 addr = smem_u32(const_cast<u32*>(done + stage));
+    u32 v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    while ((int)v < need) {
+      __nanosleep(40);  // (a polling warp shares its scheduler with working warps when an SM holds several groups)
+      asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    }
+    __syncwarp();
+  }
+  // a delayed (feedback) wire stored by a later stage: every sample up to (t + 1) * kTile - 1 - B must be in HBM
+  FZ_DEV void wait_ring(u32 stage, u32 t, u32 B) const {
+    const int last = (int)((t + 1u) * kTile) - 1 - (int)B;  // last delayed sample index this tile reads
+    if (last >= 0) wait_ge(stage, last / kTile + 1);
+  }
+  FZ_DEV void publish(u32 stage, u32 tiles_done) const {
+    __syncwarp();
+    if (lane == 0) {
+      const u32 addr = smem_u32(const_cast<u32*>(done + stage));
+      asm volatile("st.release.cta.shared.u32 [%0], %1;" :: "r"(addr), "r"(tiles_done) : "memory");
+    }
+  }
+  template <int U>
+  FZ_DEV void put(u32 tile_index, u32 row, const float* w) const {  // tile_index = x * XD + slot
+    float* t = xbase + tile_index * kTileElems + row * 32;
+#pragma unroll
+    for (int j = 0; j < U; ++j) t[j * 32] = w[j];
+  }
+  template <int U>
+  FZ_DEV void get(u32 tile_index, u32 row, float* w) const {
+    const float* t = xbase + tile_index * kTileElems + row * 32;
+#pragma unroll
+    for (int j = 0; j < U; ++j) w[j] = t[j * 32];
+  }
+};
+
 // Sets up this lane's voice; false when the whole warp has no voice (it may then simply return: warps of a
 // fused kernel never synchronise with each other).
-FZ_DEV bool ctx_init(Ctx& c, const SrkFusedArgs* a) {
+FZ_DEV bool ctx_init(Ctx& c, const SrkFusedArgs* a, u32 n_stages) {
   c.a = a;
   c.lane = threadIdx.x & 31u;
-  c.group = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 warp = threadIdx.x >> 5;
+  c.stage = warp % n_stages;
+  c.gib = warp / n_stages;
+  c.group = blockIdx.x * ((blockDim.x >> 5) / n_stages) + c.gib;
   const u32 v0 = c.group * 32u;
   if (v0 >= a->V) return false;
   c.n_active = min(32u, a->V - v0);

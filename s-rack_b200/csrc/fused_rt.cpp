@@ -202,7 +202,7 @@ int fused_kernel(const FusedSpec& spec, const FusedKernel** out, std::string& er
   return SRK_OK;
 }
 
-int fused_stems_map(SrkTensorMap* map, float* stems, uint64_t C, uint64_t N, uint64_t V, std::string& err) {
+int fused_stems_map(SrkTensorMap* map, float* stems, uint64_t C, uint64_t N, uint64_t V, unsigned tile_rows, std::string& err) {
   using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -217,7 +217,7 @@ int fused_stems_map(SrkTensorMap* map, float* stems, uint64_t C, uint64_t N, uin
   static_assert(sizeof(SrkTensorMap) == sizeof(CUtensorMap), "tensor map size");
   const cuuint64_t dims[3] = {V, N, C};
   const cuuint64_t strides[2] = {V * sizeof(float), N * V * sizeof(float)};
-  const cuuint32_t box[3] = {32, SRK_FUSED_TILE, 1};
+  const cuuint32_t box[3] = {32, tile_rows, 1};
   const cuuint32_t elem[3] = {1, 1, 1};
   const CUresult r = encode(reinterpret_cast<CUtensorMap*>(map), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, stems, dims, strides, box, elem,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,

@@ -14,18 +14,22 @@ def pytest_configure(config):
 
 
 def pytest_generate_tests(metafunc):
-    """Every GPU test runs twice: with the schedule the engine picks on its own ("auto": pipelined warps for few
-    voices, the fused kernel for many) and with the fused kernel forced for every launch ("fused")."""
+    """Every GPU test runs three times: with the schedule the engine picks on its own ("auto": the fused kernel, cut
+    into pipeline stages when an SM holds few voice groups), with the fused kernel as one warp per voice group
+    ("fused1") and with the interpreter kernels ("interp": what runs when NVRTC is missing)."""
     if "schedule" in metafunc.fixturenames:
         gpu = metafunc.definition.get_closest_marker("gpu") is not None
-        metafunc.parametrize("schedule", ["auto", "fused"] if gpu else ["auto"], indirect=True)
+        metafunc.parametrize("schedule", ["auto", "fused1", "interp"] if gpu else ["auto"], indirect=True)
 
 
 @pytest.fixture(autouse=True)
 def schedule(request, monkeypatch):
     mode = getattr(request, "param", "auto")
-    if mode == "fused":
+    if mode == "fused1":
         monkeypatch.setenv("SRK_FUSED", "1")
+        monkeypatch.setenv("SRK_FUSED_STAGES", "1")
+    elif mode == "interp":
+        monkeypatch.setenv("SRK_FUSED", "0")
     return mode
 
 

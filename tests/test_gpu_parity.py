@@ -530,13 +530,15 @@ def test_schedule_invariance(srk, orc, cuda_device, monkeypatch, name, B):
     builder = getattr(srk.patches, name)
     results = []
     # (fused, warps, chunk | samples per straight-line group): the interpreter's schedules, then the fused kernel
+    # (fused, warps | stages, chunk | samples per straight-line group): the interpreter's schedules, then the fused kernel
     for fused, warps, step in [(0, 1, 8), (0, 1, 32), (0, 1, 1), (0, 4, 16), (0, 16, 32), (0, 16, 8), (0, 2, 32),
-                               (1, 1, 4), (1, 1, 1), (1, 1, 2), (1, 1, 8)]:
+                               (1, 1, 4), (1, 1, 1), (1, 1, 2), (1, 1, 8), (1, 2, 4), (1, 3, 4), (1, 5, 8), (1, 8, 1)]:
         monkeypatch.setenv("SRK_FUSED", str(fused))
         if fused:
             monkeypatch.delenv("SRK_WARPS", raising=False)
             monkeypatch.delenv("SRK_STEP", raising=False)
             monkeypatch.setenv("SRK_FUSED_GROUP", str(step))
+            monkeypatch.setenv("SRK_FUSED_STAGES", str(warps))
         else:
             monkeypatch.setenv("SRK_WARPS", str(warps))
             monkeypatch.setenv("SRK_STEP", str(step))
@@ -546,7 +548,7 @@ def test_schedule_invariance(srk, orc, cuda_device, monkeypatch, name, B):
         info = p.program_info(V)
         assert info["fused"] == fused
         if fused:
-            assert info["fused_group"] == step and info["n_warps"] == 1
+            assert info["fused_group"] == (step if B >= step else 1) and 1 <= info["n_warps"] <= warps
         else:
             assert info["n_warps"] <= max(warps, 1) and info["step_samples"] <= step
         assert (info["n_warps"] > 1) == (info["n_stages"] > 1)
@@ -554,10 +556,10 @@ def test_schedule_invariance(srk, orc, cuda_device, monkeypatch, name, B):
         # a second call continues from the persisted state under the same schedule
         st2, _ = p.render(V, 997, stems=True, mix=True)
         results.append((info, np.concatenate([st, st2], axis=1), mx))
-    for k in ("SRK_WARPS", "SRK_STEP", "SRK_FUSED_GROUP"):
+    for k in ("SRK_WARPS", "SRK_STEP", "SRK_FUSED_GROUP", "SRK_FUSED_STAGES"):
         monkeypatch.delenv(k, raising=False)
     assert any(r[0]["n_warps"] > 1 for r in results) and any(r[0]["n_warps"] == 1 for r in results)
-    assert any(r[0]["fused"] for r in results)
+    assert any(r[0]["fused"] and r[0]["n_warps"] > 1 for r in results) and any(r[0]["fused"] and r[0]["n_warps"] == 1 for r in results)
     for info, st, mx in results[1:]:
         assert (st.view(np.uint32) == results[0][1].view(np.uint32)).all(), info
         assert np.abs(mx - results[0][2]).max() <= 1e-5 * np.sqrt(V), info
