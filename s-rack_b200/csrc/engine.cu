@@ -350,24 +350,33 @@ static int schedule_program(const srk_patch& patch, const Engine& e, size_t n_vo
       // (cfg3 @ 4096 voices: 4.2 ms against 14.7 ms, profiles/r04g).
       const size_t groups = (n_voices + kVoicesPerGroup - 1) / kVoicesPerGroup;
       const size_t per_sm = std::max<size_t>((groups + std::max(e.n_sm, 1) - 1) / std::max(e.n_sm, 1), 1);
-      bool use = true;
-      if (mode != 1 && per_sm <= 2 && spec.max_stage_cost > 90.0) {
+      // cycles per sample, both ways.  A lone fused warp retires an instruction every ~2.6 cycles (measured at 4096
+      // voices: cfg2 1.95, cfg4 3.3, cfg3 2.9 -- f64-heavy stages are the slow ones).  The interpreter's pipeline runs at
+      // its slowest stage or, with more instructions than warps, at its 16 warps' share of everything (measured, cycles
+      // per sample: cfg2 132, cfg4 442, cfg3 172, cfg3b 262, cfg1 125 against (max, sum) of its cost model (115, 437),
+      // (115, 770), (57, 352), (80, 464), (47, 133)).  What this decides: patches whose weight is one CV-driven or sine
+      // oscillator go to the interpreter, which splits such a module over several warps (cfg3: 4.2 against 14.7 ms).
+      if (mode != 1 && per_sm <= 2) {
         Program pp;
         std::vector<uint4> pb;
         int pk = 0;
         std::string perr;
         if (schedule_interpreter(patch, e, n_voices, pp, pb, pk, perr) == SRK_OK && pp.n_warps > 1) {
-          prog = std::move(pp); blob = std::move(pb); K = pk;
-          note = "slowest fused stage too long: interpreter pipeline";
-          return SRK_OK;
+          const double t_fused = 2.6 * spec.max_stage_cost, t_interp = std::max(1.15 * pp.max_cost, 0.45 * pp.sum_cost) * (double)per_sm;
+          if (env_int("SRK_DEBUG", 0))
+            std::fprintf(stderr, "[srk] schedule: fused %d stages, slowest %.0f instr -> %.0f cycles/sample; interpreter pipeline %.0f (max %u sum %u warps %u)\n",
+                         spec.stages, spec.max_stage_cost, t_fused, t_interp, pp.max_cost, pp.sum_cost, pp.n_warps);
+          if (t_interp < t_fused) {
+            prog = std::move(pp); blob = std::move(pb); K = pk;
+            note = "interpreter pipeline estimated faster than the fused stages";
+            return SRK_OK;
+          }
         }
       }
-      if (use) {
-        build_blob(prog, blob);
-        fused = true;
-        K = spec.tile;
-        return SRK_OK;
-      }
+      build_blob(prog, blob);
+      fused = true;
+      K = spec.tile;
+      return SRK_OK;
     }
     note = why;
   }

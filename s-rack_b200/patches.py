@@ -11,8 +11,12 @@ import math
 
 import numpy as np
 
-from ._ffi import PARAM as P
-from ._ffi import SEQ_NONE, grid_cell
+try:
+    from .constants import PARAM as P
+    from .constants import SEQ_NONE, grid_cell
+except ImportError:  # loaded as a plain file next to constants.py (bench.py's CPU reference arm: no product library)
+    from constants import PARAM as P
+    from constants import SEQ_NONE, grid_cell
 
 SEED = 0x5EED5EED
 SAMPLE_RATE = 48000
