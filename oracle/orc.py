@@ -58,6 +58,7 @@ def lib():
         L.orc_debug_calc.argtypes = [C.c_void_p, C.c_size_t, C.c_int]
         L.orc_debug_execute.argtypes = [C.c_void_p, C.c_size_t]
         L.orc_debug_output.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+        L.orc_debug_set_output.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
         L.orc_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_version.restype = C.c_char_p
         _lib = L
@@ -204,6 +205,12 @@ class OraclePatch:
         out = np.zeros(self.buffer_size, dtype=np.float32)
         assert lib().orc_debug_output(self._h, voice, module, port, out.ctypes.data) == 0
         return out
+
+    def debug_set_output(self, module, port, data, voice=0):
+        """Overwrite an output buffer (one block): the modules reading that port see `data` at their next calc()."""
+        d = np.ascontiguousarray(data, dtype=np.float32)
+        assert d.size == self.buffer_size
+        assert lib().orc_debug_set_output(self._h, voice, module, port, d.ctypes.data) == 0
 
 
 def philox4x32_10(ctr, key):

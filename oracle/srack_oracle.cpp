@@ -1009,6 +1009,17 @@ int orc_debug_output(void* h, size_t voice, int module, int port, float* out) {
   return 0;
 }
 
+// Test hook: overwrite one output buffer of one module of one voice (the next calc() of a module wired to that port
+// then reads arbitrary input, NaN and infinities included; tests/test_oracle_independent.py).
+int orc_debug_set_output(void* h, size_t voice, int module, int port, const float* data) {
+  auto* p = static_cast<Patch*>(h);
+  if (voice >= p->voices.size() || module < 0 || module >= (int)p->kinds.size()) return 1;
+  Module* m = p->voices[voice].modules[module].get();
+  if (port < 0 || port >= (int)m->outs.size()) return 2;
+  std::memcpy(m->outs[port].data(), data, m->outs[port].size() * sizeof(float));
+  return 0;
+}
+
 void orc_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
   uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
   philox4x32_10(c, key[0], key[1]);
