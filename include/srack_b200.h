@@ -267,6 +267,24 @@ SRK_API int srk_sync(srk_patch* patch);
  * (and empty feedback history). */
 SRK_API int srk_reset(srk_patch* patch);
 
+/* ---- per-voice DSP state out and in: the device-side analogue of the state every reference module serializes
+ *      (`#[derive(Serialize)]` on OscillatorModule.pos, InternalMoogFilterState, ADSRModule.phase/mode/r_val ...,
+ *      written by ui.rs:98-114 and restored by ui.rs:115-134) -- a checkpoint of a render in progress.
+ * Export: every voice's state words, the history of the wires the cycle breaker cut and the absolute sample index of
+ * the range last rendered on this patch, as one opaque, versioned blob (valid until the next export or patch destroy;
+ * SRK_ERR_ARG when nothing has been rendered since the last wiring change).
+ * Import: into a planned patch with the same graph (module kinds in plan order, cut wires, buffer_size -- else
+ * SRK_ERR_ARG; SRK_ERR_SIZE for a truncated blob); the next srk_render() of the blob's n_voices / voice_offset
+ * continues bit for bit where the exporting patch stopped.  Parameters, sequencer tables and Sample tables are not
+ * part of the blob (they belong to the patch description / the .srk file). */
+SRK_API int srk_state_export(srk_patch* patch, const void** blob, size_t* n_bytes);
+SRK_API int srk_state_import(srk_patch* patch, const void* blob, size_t n_bytes);
+
+/* Scheduling hint: `n_voices` voices of OTHER patches are rendered on this patch's device at the same time (several
+ * patches, each on its own stream).  Launch shapes are chosen from the voice groups an SM has to hold, so concurrent
+ * renders should be scheduled for the sum.  Default 0.  Changing it re-plans the launch and resets the voice state. */
+SRK_API int srk_set_co_resident_voices(srk_patch* patch, size_t n_voices);
+
 /* ---- instrumentation ---------------------------------------------------- */
 /* Device time (CUDA events on the render stream) of the voice kernel alone and of the
  * whole call, for the last completed render; kernel launches issued so far. */
@@ -294,6 +312,10 @@ SRK_API int srk_fused_source(srk_patch* patch, size_t n_voices, const char** sou
  * $SRK_KERNEL_CACHE) so that the first render does not pay for NVRTC.  Needs no GPU.  *compiled = 1 when a
  * compilation happened, 0 when the cubin was cached already or the launch would not use a fused kernel. */
 SRK_API int srk_precompile(srk_patch* patch, size_t n_voices, int* compiled);
+/* Identity of the kernel image a render of n_voices would launch: "fused:<hash of generated source + op headers +
+ * compiler options>" or "interpreter:<hash of the kernel sources at build time>:<pipelined|solo|solo_full>".  Profiles
+ * are stamped with it.  Valid until the next call on the patch. */
+SRK_API int srk_kernel_id(srk_patch* patch, size_t n_voices, const char** id);
 /* The compiled, scheduled device program itself (what execute() becomes for n_voices voices):
  * one entry per instruction -- the modules of the plan in plan order (src/synth.rs:97-101), plus
  * ring loads/stores for the wires the cycle breaker cut (synth.rs:168-192), the stems / mixdown

@@ -89,6 +89,10 @@ _SIGNATURES = {
     "srk_get_program_info": (C.c_int, [_P, C.c_size_t, C.POINTER(srk_program_info)]),
     "srk_fused_source": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t)]),
     "srk_precompile": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_int)]),
+    "srk_kernel_id": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_char_p)]),
+    "srk_set_co_resident_voices": (C.c_int, [_P, C.c_size_t]),
+    "srk_state_export": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_size_t)]),
+    "srk_state_import": (C.c_int, [_P, _P, C.c_size_t]),
     "srk_get_program": (C.c_int, [_P, C.c_size_t, C.POINTER(srk_instr_info), C.c_size_t, C.POINTER(C.c_size_t),
                                   C.POINTER(srk_wire_info), C.c_size_t, C.POINTER(C.c_size_t)]),
 }

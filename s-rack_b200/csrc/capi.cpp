@@ -3,6 +3,7 @@
 // engine.cu.  Nothing here throws across the ABI.
 #include <algorithm>
 #include <cstring>
+#include <exception>
 #include <new>
 
 #include "engine.hpp"
@@ -34,6 +35,23 @@ int fail(srk_patch* p, int code, const char* msg) {
 void touch_wiring(srk_patch* p) {
   ++p->wiring_epoch;
   p->planned = false;
+}
+
+// Nothing may throw across the ABI: allocation failures (a huge per-voice array, a hostile .srk file) become a status.
+template <class F>
+int guarded(srk_patch* p, F&& f) noexcept {
+  try {
+    return f();
+  } catch (const std::bad_alloc&) {
+    return fail(p, SRK_ERR_LIMIT, "out of host memory");
+  } catch (const std::exception& e) {
+    if (p) {
+      try { p->last_error = e.what(); } catch (...) {}
+    }
+    return SRK_ERR_LIMIT;
+  } catch (...) {
+    return fail(p, SRK_ERR_LIMIT, "unexpected exception");
+  }
 }
 
 int n_inputs_for(const srk_patch* p, int kind) {
@@ -117,7 +135,7 @@ int srk_set_device(srk_patch* p, int device) {
 
 const char* srk_last_error(const srk_patch* p) { return p ? p->last_error.c_str() : "null patch"; }
 
-int srk_module_create(srk_patch* p, int kind, srk_module** out) {
+int srk_module_create(srk_patch* p, int kind, srk_module** out) { return guarded(p, [&]() -> int {
   if (!p || !out) return SRK_ERR_ARG;
   if (kind < 0 || kind >= SRK_KIND_COUNT) return fail(p, SRK_ERR_KIND, "unknown module kind");
   auto m = std::make_unique<srk_module>();
@@ -138,9 +156,9 @@ int srk_module_create(srk_patch* p, int kind, srk_module** out) {
   p->owned.push_back(std::move(m));
   touch_wiring(p);
   return SRK_OK;
-}
+}); }
 
-int srk_module_create_by_name(srk_patch* p, const char* name, srk_module** out) {
+int srk_module_create_by_name(srk_patch* p, const char* name, srk_module** out) { return guarded(p, [&]() -> int {
   if (!p || !name || !out) return SRK_ERR_ARG;
   for (const auto& e : kCatalog)
     if (std::strcmp(e.name, name) == 0) {
@@ -148,7 +166,7 @@ int srk_module_create_by_name(srk_patch* p, const char* name, srk_module** out) 
       return srk_module_create(p, e.kind, out);
     }
   return fail(p, SRK_ERR_KIND, "no such catalog entry");
-}
+}); }
 
 int srk_module_remove(srk_patch* p, srk_module* m) {
   if (!p || !m || m->patch != p) return SRK_ERR_ARG;
@@ -186,7 +204,7 @@ int srk_get_output_label(const srk_module* m, uint8_t idx, const char** label) {
   return SRK_OK;
 }
 
-int srk_connect(srk_module* sink, uint8_t idx, srk_module* src, uint8_t port) {
+int srk_connect(srk_module* sink, uint8_t idx, srk_module* src, uint8_t port) { return guarded((sink ? sink->patch : nullptr), [&]() -> int {
   if (!sink || !src) return SRK_ERR_ARG;
   srk_patch* p = sink->patch;
   if (src->patch != p) return fail(p, SRK_ERR_ARG, "modules belong to different patches");
@@ -196,7 +214,7 @@ int srk_connect(srk_module* sink, uint8_t idx, srk_module* src, uint8_t port) {
   sink->inputs[idx] = {src, port};
   touch_wiring(p);
   return SRK_OK;
-}
+}); }
 
 int srk_disconnect(srk_module* sink, uint8_t idx) {
   if (!sink) return SRK_ERR_ARG;
@@ -239,7 +257,7 @@ int srk_get_param_f32(const srk_module* m, int pid, float* value) {
   return SRK_OK;
 }
 
-int srk_set_param_f32_per_voice(srk_module* m, int pid, const float* values, size_t n) {
+int srk_set_param_f32_per_voice(srk_module* m, int pid, const float* values, size_t n) { return guarded((m ? m->patch : nullptr), [&]() -> int {
   if (!m || (!values && n)) return SRK_ERR_ARG;
   const srk::KindInfo& ki = srk::kind_info(m->kind);
   if (pid < 0 || pid >= ki.n_params) return fail(m->patch, SRK_ERR_PARAM, "unknown parameter id");
@@ -247,9 +265,9 @@ int srk_set_param_f32_per_voice(srk_module* m, int pid, const float* values, siz
   m->param_pv[pid].assign(values, values + n);
   ++m->patch->param_epoch;
   return SRK_OK;
-}
+}); }
 
-int srk_set_sequence(srk_module* m, const int32_t* cells, size_t n_steps) {
+int srk_set_sequence(srk_module* m, const int32_t* cells, size_t n_steps) { return guarded((m ? m->patch : nullptr), [&]() -> int {
   if (!m || !cells) return SRK_ERR_ARG;
   const bool grid = m->kind == SRK_KIND_GRID_SEQUENCER, pattern = m->kind == SRK_KIND_PATTERN_SEQUENCER;
   if (!grid && !pattern) return fail(m->patch, SRK_ERR_KIND, "module has no sequence table");
@@ -264,7 +282,7 @@ int srk_set_sequence(srk_module* m, const int32_t* cells, size_t n_steps) {
   m->seq_steps = n_steps;
   ++m->patch->table_epoch;
   return SRK_OK;
-}
+}); }
 
 int srk_get_sequence(const srk_module* m, int32_t* cells, size_t cap, size_t* n_steps) {
   if (!m) return SRK_ERR_ARG;
@@ -274,7 +292,7 @@ int srk_get_sequence(const srk_module* m, int32_t* cells, size_t cap, size_t* n_
   return SRK_OK;
 }
 
-int srk_set_sample(srk_module* m, const float* samples, size_t n, float sample_rate) {
+int srk_set_sample(srk_module* m, const float* samples, size_t n, float sample_rate) { return guarded((m ? m->patch : nullptr), [&]() -> int {
   if (!m || (!samples && n)) return SRK_ERR_ARG;
   if (m->kind != SRK_KIND_SAMPLE) return fail(m->patch, SRK_ERR_KIND, "module has no sample table");
   if (n >= (1ull << 31)) return fail(m->patch, SRK_ERR_LIMIT, "sample table longer than 2^31 - 1");
@@ -284,9 +302,9 @@ int srk_set_sample(srk_module* m, const float* samples, size_t n, float sample_r
   ++m->patch->wave_epoch;
   ++m->patch->table_epoch;
   return SRK_OK;
-}
+}); }
 
-int srk_load_wav(srk_module* m, const void* bytes, size_t n_bytes) {
+int srk_load_wav(srk_module* m, const void* bytes, size_t n_bytes) { return guarded((m ? m->patch : nullptr), [&]() -> int {
   if (!m || (!bytes && n_bytes)) return SRK_ERR_ARG;
   if (m->kind != SRK_KIND_SAMPLE) return fail(m->patch, SRK_ERR_KIND, "module has no sample table");
   std::string err;
@@ -300,7 +318,7 @@ int srk_load_wav(srk_module* m, const void* bytes, size_t n_bytes) {
   m->wave_rate = rate;
   m->wave_new = true;
   return SRK_OK;
-}
+}); }
 
 int srk_get_sample(const srk_module* m, float* samples, size_t cap, size_t* n, float* sample_rate) {
   if (!m) return SRK_ERR_ARG;
@@ -318,7 +336,7 @@ int srk_write_wav(const char* path, const float* planar, unsigned channels, size
 }
 
 // SynthModuleWorkspaceImpl::deserialize, ui.rs:115-134: the patch is emptied and rebuilt from the file.
-int srk_patch_load_srk(srk_patch* p, const void* bytes, size_t n_bytes, size_t* n_skipped_connections) {
+int srk_patch_load_srk(srk_patch* p, const void* bytes, size_t n_bytes, size_t* n_skipped_connections) { return guarded(p, [&]() -> int {
   if (!p || (!bytes && n_bytes)) return SRK_ERR_ARG;
   srk::SrkFile f;
   std::string err;
@@ -371,10 +389,10 @@ int srk_patch_load_srk(srk_patch* p, const void* bytes, size_t n_bytes, size_t* 
   p->last_error.clear();
   if (n_skipped_connections) *n_skipped_connections = skipped;
   return SRK_OK;
-}
+}); }
 
 // SynthModuleWorkspaceImpl::serialize, ui.rs:98-114.
-int srk_patch_save_srk(srk_patch* p, const void** bytes, size_t* n_bytes) {
+int srk_patch_save_srk(srk_patch* p, const void** bytes, size_t* n_bytes) { return guarded(p, [&]() -> int {
   if (!p || !bytes || !n_bytes) return SRK_ERR_ARG;
   srk::SrkFile f;
   for (const srk_module* m : p->modules) {  // capture_modules: list order
@@ -408,9 +426,9 @@ int srk_patch_save_srk(srk_patch* p, const void** bytes, size_t* n_bytes) {
   *bytes = p->saved.data();
   *n_bytes = p->saved.size();
   return SRK_OK;
-}
+}); }
 
-int srk_plan(srk_patch* p) {
+int srk_plan(srk_patch* p) { return guarded(p, [&]() -> int {
   if (!p) return SRK_ERR_ARG;
   p->plan.clear();
   p->cuts.clear();
@@ -429,7 +447,7 @@ int srk_plan(srk_patch* p) {
   for (auto& c : cuts) p->cuts.emplace_back(p->modules[c.first], p->modules[c.second]);
   p->planned = true;
   return SRK_OK;
-}
+}); }
 
 int srk_plan_get(const srk_patch* p, srk_module** out, size_t cap, size_t* n) {
   if (!p || !n) return SRK_ERR_ARG;
@@ -449,7 +467,7 @@ int srk_plan_cuts(const srk_patch* p, srk_module** readers, srk_module** writers
   return SRK_OK;
 }
 
-int srk_set_module_order(srk_patch* p, srk_module* const* order, size_t n) {
+int srk_set_module_order(srk_patch* p, srk_module* const* order, size_t n) { return guarded(p, [&]() -> int {
   if (!p || !order) return SRK_ERR_ARG;
   if (n != p->modules.size()) return fail(p, SRK_ERR_ARG, "order is not a permutation of the module list");
   std::vector<srk_module*> next(order, order + n), a = next, b = p->modules;
@@ -459,19 +477,19 @@ int srk_set_module_order(srk_patch* p, srk_module* const* order, size_t n) {
   p->modules = next;
   touch_wiring(p);
   return SRK_OK;
-}
+}); }
 
 int srk_render(srk_patch* p, size_t n_voices, size_t voice_offset, size_t n_samples, unsigned flags, float* stems,
-               float* mix) {
+               float* mix) { return guarded(p, [&]() -> int {
   if (!p) return SRK_ERR_ARG;
   return srk::engine_render(p, n_voices, voice_offset, n_samples, flags, stems, mix, nullptr, false);
-}
+}); }
 
 int srk_render_on_stream(srk_patch* p, size_t n_voices, size_t voice_offset, size_t n_samples, unsigned flags,
-                         float* stems, float* mix, void* cuda_stream) {
+                         float* stems, float* mix, void* cuda_stream) { return guarded(p, [&]() -> int {
   if (!p) return SRK_ERR_ARG;
   return srk::engine_render(p, n_voices, voice_offset, n_samples, flags, stems, mix, cuda_stream, true);
-}
+}); }
 
 int srk_sync(srk_patch* p) { return p ? srk::engine_sync(p) : SRK_ERR_ARG; }
 int srk_reset(srk_patch* p) { return p ? srk::engine_reset(p) : SRK_ERR_ARG; }
@@ -482,29 +500,53 @@ int srk_last_render_ms(srk_patch* p, float* kernel_ms, float* total_ms) {
 
 uint64_t srk_launch_count(const srk_patch* p) { return p ? srk::engine_launches(p) : 0; }
 
-int srk_get_program_info(srk_patch* p, size_t n_voices, srk_program_info* out) {
+int srk_get_program_info(srk_patch* p, size_t n_voices, srk_program_info* out) { return guarded(p, [&]() -> int {
   if (!p || !out) return SRK_ERR_ARG;
   return srk::engine_program_info(p, n_voices, out);
-}
+}); }
 
-int srk_fused_source(srk_patch* p, size_t n_voices, const char** source, size_t* n_bytes) {
+int srk_fused_source(srk_patch* p, size_t n_voices, const char** source, size_t* n_bytes) { return guarded(p, [&]() -> int {
   if (!p || !source) return SRK_ERR_ARG;
   int rc = srk::engine_fused_source(p, n_voices, p->fused_source);
   if (rc != SRK_OK) return rc;
   *source = p->fused_source.c_str();
   if (n_bytes) *n_bytes = p->fused_source.size();
   return SRK_OK;
-}
+}); }
 
-int srk_precompile(srk_patch* p, size_t n_voices, int* compiled) {
+int srk_precompile(srk_patch* p, size_t n_voices, int* compiled) { return guarded(p, [&]() -> int {
   if (!p) return SRK_ERR_ARG;
   return srk::engine_precompile(p, n_voices, compiled);
+}); }
+
+int srk_kernel_id(srk_patch* p, size_t n_voices, const char** id) { return guarded(p, [&]() -> int {
+  if (!p || !id) return SRK_ERR_ARG;
+  int rc = srk::engine_kernel_id(p, n_voices, p->kernel_id);
+  if (rc != SRK_OK) return rc;
+  *id = p->kernel_id.c_str();
+  return SRK_OK;
+}); }
+
+int srk_set_co_resident_voices(srk_patch* p, size_t n_voices) {
+  if (!p) return SRK_ERR_ARG;
+  p->co_resident_voices = n_voices;
+  return SRK_OK;
 }
 
+int srk_state_export(srk_patch* p, const void** blob, size_t* n_bytes) { return guarded(p, [&]() -> int {
+  if (!p || !blob || !n_bytes) return SRK_ERR_ARG;
+  return srk::engine_state_export(p, blob, n_bytes);
+}); }
+
+int srk_state_import(srk_patch* p, const void* blob, size_t n_bytes) { return guarded(p, [&]() -> int {
+  if (!p || !blob) return SRK_ERR_ARG;
+  return srk::engine_state_import(p, blob, n_bytes);
+}); }
+
 int srk_get_program(srk_patch* p, size_t n_voices, srk_instr_info* instrs, size_t instr_cap, size_t* n_instr,
-                    srk_wire_info* wires, size_t wire_cap, size_t* n_wires) {
+                    srk_wire_info* wires, size_t wire_cap, size_t* n_wires) { return guarded(p, [&]() -> int {
   if (!p) return SRK_ERR_ARG;
   return srk::engine_program_dump(p, n_voices, instrs, instr_cap, n_instr, wires, wire_cap, n_wires);
-}
+}); }
 
 }  // extern "C"

@@ -454,18 +454,23 @@ static int reset_state(srk_patch* patch, Engine& e) {
   return SRK_OK;
 }
 
+// The voice count the schedule is chosen for: this launch's plus the voices other patches render on the same device at the
+// same time (srk_set_co_resident_voices): what matters to every choice below is how many voice groups an SM holds.
+static size_t sched_voices(const srk_patch& patch, size_t n_voices) { return n_voices + patch.co_resident_voices; }
+
 // (Re)compile + (re)allocate for the current plan and voice range.
 static int engine_prepare(srk_patch* patch, size_t n_voices, size_t voice_offset) {
   Engine& e = *patch->engine;
   bool fresh = false;
-  const int want_warps = choose_max_warps(e, n_voices);
+  const size_t sv = sched_voices(*patch, n_voices);
+  const int want_warps = choose_max_warps(e, sv);
   const bool rewired = e.compiled_epoch != patch->wiring_epoch || e.compiled_max_warps != want_warps ||
-                       e.compiled_voices != n_voices;  // (a new voice count resets the voice state anyway)
+                       e.compiled_voices != sv;  // (a new voice count resets the voice state anyway)
   if (rewired || e.compiled_table_epoch != patch->table_epoch) {
     // (a sequence-table edit alone rebuilds the program image but keeps the voice state: the state
     // layout depends on the wiring only)
     std::string err;
-    int rc = schedule_program(*patch, e, n_voices, e.prog, e.blob, e.chunk, e.fused, e.fspec, e.fused_note, err);
+    int rc = schedule_program(*patch, e, sv, e.prog, e.blob, e.chunk, e.fused, e.fspec, e.fused_note, err);
     if (rc != SRK_OK) { patch->last_error = err; return rc; }
     e.fkernel = nullptr;
     if (e.fused) {
@@ -473,7 +478,7 @@ static int engine_prepare(srk_patch* patch, size_t n_voices, size_t voice_offset
       if (fused_kernel(e.fspec, &e.fkernel, why) != SRK_OK) {
         // no NVRTC here, or the generated source did not compile: the interpreter kernels take over
         if (fused_mode() == 1) { patch->last_error = why; return SRK_ERR_UNSUPPORTED; }
-        rc = schedule_interpreter(*patch, e, n_voices, e.prog, e.blob, e.chunk, err);
+        rc = schedule_interpreter(*patch, e, sv, e.prog, e.blob, e.chunk, err);
         if (rc != SRK_OK) { patch->last_error = err; return rc; }
         e.fused = false;
         e.fused_note = why;
@@ -489,7 +494,7 @@ static int engine_prepare(srk_patch* patch, size_t n_voices, size_t voice_offset
     SRK_CUDA(cudaStreamSynchronize(e.stream));
     e.compiled_epoch = patch->wiring_epoch;
     e.compiled_max_warps = want_warps;
-    e.compiled_voices = n_voices;
+    e.compiled_voices = sv;
     e.compiled_table_epoch = patch->table_epoch;
     fresh = rewired;
     e.uploaded_wave_epoch = 0;  // WaveDesc offsets follow the plan: re-concatenate
@@ -522,7 +527,7 @@ static int engine_prepare(srk_patch* patch, size_t n_voices, size_t voice_offset
       // per-voice (or uniform again) selects another kernel
       FusedSpec spec;
       std::string why;
-      if (fused_generate_fitting(*patch, e, e.prog, n_voices, spec, why) == SRK_OK && spec.source != e.fspec.source) {
+      if (fused_generate_fitting(*patch, e, e.prog, sv, spec, why) == SRK_OK && spec.source != e.fspec.source) {
         const FusedKernel* k = nullptr;
         if (fused_kernel(spec, &k, why) == SRK_OK) {
           e.fspec = std::move(spec);
@@ -561,7 +566,21 @@ int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t
   SRK_CUDA(cudaEventRecord(e.ev[0], work));
   rc = engine_prepare(patch, n_voices, voice_offset);
   if (rc != SRK_OK) return rc;
-  if (n_voices == 0 || n_samples == 0) { e.timed = false; return SRK_OK; }
+  if (n_voices == 0 || n_samples == 0) {
+    // no voices: the mix of nothing is silence (a rank that got no voices still contributes zeros to the NCCL sum)
+    if (mix && n_samples) {
+      const size_t bytes = (size_t)e.prog.channels * n_samples * sizeof(float);
+      if (flags & SRK_RENDER_DEVICE_OUT) {
+        SRK_CUDA(cudaMemsetAsync(mix, 0, bytes, work));
+        if (foreign) { SRK_CUDA(cudaEventRecord(e.ev[3], work)); SRK_CUDA(cudaStreamWaitEvent(caller, e.ev[3], 0)); }
+        if (!(flags & SRK_RENDER_ASYNC)) SRK_CUDA(cudaStreamSynchronize(work));
+      } else {
+        std::memset(mix, 0, bytes);
+      }
+    }
+    e.timed = false;
+    return SRK_OK;
+  }
 
   const Program& prog = e.prog;
   const size_t C = prog.channels;
@@ -627,7 +646,7 @@ int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t
   } else {
   K = chunk_for_length(prog, e.chunk, n_samples);  // <= e.chunk, which fitted
   T = (int)prog.n_warps * 32;
-  G = prog.n_warps == 1 ? choose_solo_groups(e, prog, e.blob.size(), K, n_voices) : 1;
+  G = prog.n_warps == 1 ? choose_solo_groups(e, prog, e.blob.size(), K, sched_voices(*patch, n_voices)) : 1;
   smem = smem_bytes_for(prog, e.blob.size(), K, G);
   const unsigned grid = (n_groups + G - 1) / G;
 
@@ -742,6 +761,7 @@ static int probe_program(srk_patch* patch, size_t n_voices, Program& prog, std::
   std::string err, note;
   bool is_fused = false;
   FusedSpec local;
+  n_voices = sched_voices(*patch, n_voices);
   int rc = schedule_program(*patch, probe, n_voices, prog, blob, K, is_fused, spec ? *spec : local, note, err);
   if (rc != SRK_OK) { patch->last_error = err; return rc; }
   if (is_fused && !fused) {  // the caller wants the interpreter's program (srk_get_program)
@@ -824,6 +844,112 @@ int engine_precompile(srk_patch* patch, size_t n_voices, int* compiled) {
   rc = fused_cubin(spec, cubin, key, &from_disk, nullptr, err);
   if (rc != SRK_OK) { patch->last_error = err; return rc; }
   if (compiled) *compiled = from_disk ? 0 : 1;
+  return SRK_OK;
+}
+
+// Which kernel image a render of n_voices runs: "fused:<hash of the generated source, the op headers and the compiler
+// options>" or "interpreter:<hash of dsp.cuh + voice_kernel.cuh at build time>:<pipelined|solo|solo_full>".  Profiles are
+// stamped with it (profiles/traffic.json) so that a number captured on another kernel is never quoted for this one.
+#ifndef SRK_SOURCE_HASH
+#define SRK_SOURCE_HASH "unknown"
+#endif
+int engine_kernel_id(srk_patch* patch, size_t n_voices, std::string& id) {
+  Program prog;
+  std::vector<uint4> blob;
+  int K = 0;
+  bool fused = false;
+  FusedSpec spec;
+  int rc = probe_program(patch, n_voices, prog, blob, K, nullptr, &fused, &spec);
+  if (rc != SRK_OK) return rc;
+  if (fused) { id = "fused:" + fused_key(spec); return SRK_OK; }
+  bool beyond_baseline = false;
+  for (const Instr& ins : prog.code) beyond_baseline |= ins.op == OP_GRIDSEQ || ins.op == OP_PATSEQ || ins.op == OP_SAMPLE;
+  id = std::string("interpreter:") + SRK_SOURCE_HASH + (prog.n_warps > 1 ? ":pipelined" : beyond_baseline ? ":solo_full" : ":solo");
+  return SRK_OK;
+}
+
+// ---- per-voice state export / import: the device-side analogue of the DSP state every reference module serializes
+// (ui.rs:98-134; `#[derive(Serialize)]` on oscillator phase, filter memory, envelope stage ...).  The blob is the raw
+// state words [S][V], the feedback rings [R][B][V] and the absolute sample index, behind a header that names the layout.
+namespace {
+struct StateHeader {
+  char magic[8];  // "SRKSTATE"
+  uint32_t version, S, R, B;
+  uint64_t V, voice_offset, n_abs, layout;
+};
+constexpr uint32_t kStateVersion = 1;
+
+// the state layout follows from the plan alone: module kinds in plan order and the wires the cycle breaker cut
+uint64_t state_layout_hash(const srk_patch& patch, const Program& prog) {
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&](uint64_t v) { for (int k = 0; k < 8; ++k) { h ^= (v >> (8 * k)) & 0xff; h *= 1099511628211ull; } };
+  auto plan_index = [&](const srk_module* m) -> uint64_t { for (size_t i = 0; i < patch.plan.size(); ++i) if (patch.plan[i] == m) return (uint64_t)i; return ~0ull; };
+  for (const srk_module* m : patch.plan) mix((uint64_t)m->kind);
+  for (const auto& c : patch.cuts) { mix(plan_index(c.first)); mix(plan_index(c.second)); }
+  mix(prog.state_init.size()); mix(prog.n_rings); mix(prog.ring_len);
+  return h;
+}
+}  // namespace
+
+int engine_state_export(srk_patch* patch, const void** blob, size_t* n_bytes) {
+  if (!patch->engine || !patch->engine->state_valid || !patch->engine->V || patch->engine->compiled_epoch != patch->wiring_epoch) {
+    patch->last_error = "no voice state to export: nothing has been rendered since the last wiring change";
+    return SRK_ERR_ARG;
+  }
+  Engine& e = *patch->engine;
+  SRK_CUDA(cudaSetDevice(e.device));
+  SRK_CUDA(cudaStreamSynchronize(e.stream));
+  const size_t state_bytes = e.prog.state_init.size() * e.V * sizeof(uint32_t);
+  const size_t ring_bytes = (size_t)e.prog.n_rings * e.prog.ring_len * e.V * sizeof(float);
+  patch->saved_state.resize(sizeof(StateHeader) + state_bytes + ring_bytes);
+  StateHeader h{};
+  std::memcpy(h.magic, "SRKSTATE", 8);
+  h.version = kStateVersion;
+  h.S = (uint32_t)e.prog.state_init.size();
+  h.R = e.prog.n_rings;
+  h.B = e.prog.ring_len;
+  h.V = e.V;
+  h.voice_offset = e.voice_offset;
+  h.n_abs = e.n_abs;
+  h.layout = state_layout_hash(*patch, e.prog);
+  unsigned char* out = patch->saved_state.data();
+  std::memcpy(out, &h, sizeof h);
+  if (state_bytes) SRK_CUDA(cudaMemcpy(out + sizeof h, e.d_state.p, state_bytes, cudaMemcpyDeviceToHost));
+  if (ring_bytes) SRK_CUDA(cudaMemcpy(out + sizeof h + state_bytes, e.d_rings.p, ring_bytes, cudaMemcpyDeviceToHost));
+  *blob = out;
+  *n_bytes = patch->saved_state.size();
+  return SRK_OK;
+}
+
+int engine_state_import(srk_patch* patch, const void* blob, size_t n_bytes) {
+  if (!patch->planned) { patch->last_error = "srk_plan() has not been called since the last wiring change"; return SRK_ERR_NOT_PLANNED; }
+  StateHeader h;
+  if (n_bytes < sizeof h) { patch->last_error = "state blob shorter than its header"; return SRK_ERR_ARG; }
+  std::memcpy(&h, blob, sizeof h);
+  if (std::memcmp(h.magic, "SRKSTATE", 8) != 0 || h.version != kStateVersion) { patch->last_error = "not a state blob of this version"; return SRK_ERR_ARG; }
+  if (h.V == 0 || h.V > (0xFFFFFFFFull / kMaxChunk)) { patch->last_error = "state blob: bad voice count"; return SRK_ERR_ARG; }
+  const size_t state_bytes = (size_t)h.S * h.V * sizeof(uint32_t);
+  const size_t ring_bytes = (size_t)h.R * h.B * h.V * sizeof(float);
+  if (n_bytes != sizeof h + state_bytes + ring_bytes) { patch->last_error = "state blob: size does not match its header"; return SRK_ERR_SIZE; }
+  int rc = engine_open(patch);
+  if (rc != SRK_OK) return rc;
+  Engine& e = *patch->engine;
+  SRK_CUDA(cudaSetDevice(e.device));
+  rc = engine_prepare(patch, (size_t)h.V, (size_t)h.voice_offset);  // compiles, allocates, X::new() state
+  if (rc != SRK_OK) return rc;
+  if (h.S != e.prog.state_init.size() || h.R != e.prog.n_rings || h.B != e.prog.ring_len || h.layout != state_layout_hash(*patch, e.prog)) {
+    patch->last_error = "state blob was exported from a different patch (module kinds in plan order, cut wires or buffer_size differ)";
+    return SRK_ERR_ARG;
+  }
+  const unsigned char* in = static_cast<const unsigned char*>(blob) + sizeof h;
+  if (state_bytes) SRK_CUDA(cudaMemcpyAsync(e.d_state.p, in, state_bytes, cudaMemcpyHostToDevice, e.stream));
+  if (ring_bytes) SRK_CUDA(cudaMemcpyAsync(e.d_rings.p, in + state_bytes, ring_bytes, cudaMemcpyHostToDevice, e.stream));
+  SRK_CUDA(cudaStreamSynchronize(e.stream));  // the caller's blob may go away
+  e.n_abs = h.n_abs;
+  e.state_valid = true;
+  // the imported play positions supersede a pending "rewind at the next render" of freshly loaded Sample tables
+  for (srk_module* m : patch->modules)
+    if (m->wave_new) { m->wave_new = false; ++patch->table_epoch; }
   return SRK_OK;
 }
 

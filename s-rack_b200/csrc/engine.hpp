@@ -20,6 +20,9 @@ uint64_t engine_launches(const srk_patch* patch);
 int engine_program_info(srk_patch* patch, size_t n_voices, srk_program_info* out);
 int engine_fused_source(srk_patch* patch, size_t n_voices, std::string& source);
 int engine_precompile(srk_patch* patch, size_t n_voices, int* compiled);
+int engine_kernel_id(srk_patch* patch, size_t n_voices, std::string& id);
+int engine_state_export(srk_patch* patch, const void** blob, size_t* n_bytes);
+int engine_state_import(srk_patch* patch, const void* blob, size_t n_bytes);
 int engine_program_dump(srk_patch* patch, size_t n_voices, srk_instr_info* instrs, size_t instr_cap, size_t* n_instr,
                         srk_wire_info* wires, size_t wire_cap, size_t* n_wires);
 

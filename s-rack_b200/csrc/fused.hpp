@@ -42,6 +42,8 @@ struct FusedOptions {
 int fused_generate(const srk_patch& patch, const Program& prog, const FusedOptions& opt, FusedSpec& out, std::string& err);
 
 std::string fused_hash(const std::string& text, const std::string& salt);
+// cache key of a generated kernel: hash of its source, the op headers and the compiler options
+std::string fused_key(const FusedSpec& spec);
 
 struct FusedKernel {
   void* library = nullptr;  // cudaLibrary_t

@@ -113,9 +113,13 @@ std::string fused_cache_dir() {
   return dir + "/kernel_cache";
 }
 
-int fused_cubin(const FusedSpec& spec, std::vector<char>& cubin, std::string& key, bool* from_disk, double* compile_ms, std::string& err) {
+std::string fused_key(const FusedSpec& spec) {
   static const std::string kSalt = salt();
-  key = fused_hash(spec.source, kSalt);
+  return fused_hash(spec.source, kSalt);
+}
+
+int fused_cubin(const FusedSpec& spec, std::vector<char>& cubin, std::string& key, bool* from_disk, double* compile_ms, std::string& err) {
+  key = fused_key(spec);
   const std::string dir = fused_cache_dir();
   const std::string path = dir + "/" + key + ".cubin";
   if (from_disk) *from_disk = false;
@@ -171,8 +175,7 @@ int fused_kernel(const FusedSpec& spec, const FusedKernel** out, std::string& er
   std::string key;
   bool from_disk = false;
   double ms = 0.0;
-  static const std::string kSalt = salt();
-  key = fused_hash(spec.source, kSalt);
+  key = fused_key(spec);
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) { err = "no current CUDA device"; return SRK_ERR_CUDA; }
   std::lock_guard<std::mutex> lock(mu);

@@ -75,6 +75,9 @@ struct srk_patch {
   std::vector<std::pair<std::string, std::pair<float, float>>> positions;  // GUI positions of a loaded .srk, written back on save
   std::vector<unsigned char> saved;  // last srk_patch_save_srk() image
   std::string fused_source;          // last srk_fused_source() text
+  std::string kernel_id;             // last srk_kernel_id() text
+  std::vector<unsigned char> saved_state;  // last srk_state_export() blob
+  size_t co_resident_voices = 0;     // srk_set_co_resident_voices(): voices other patches render on this device concurrently
   std::unique_ptr<srk::Engine, void (*)(srk::Engine*)> engine{nullptr, nullptr};
 
   int index_of(const srk_module* m) const {

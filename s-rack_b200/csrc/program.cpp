@@ -72,6 +72,13 @@ uint16_t pow2_ceil(int x) {
 
 }  // namespace
 
+// `steps_per_octave` is a u16 in the reference (sequencer.rs:22); the parameter arrives as f32 through the ABI or a file:
+// NaN and values below 0 become 0, values above 65535 saturate (a float -> u16 cast outside the range is undefined in C++).
+static uint16_t steps_per_octave_u16(float v) {
+  if (!(v > 0.0f)) return 0;
+  return v >= 65535.0f ? (uint16_t)65535 : (uint16_t)v;
+}
+
 int compile_program(const srk_patch& patch, int max_warps, Program& prog, std::string& err) {
   prog = Program();
   const int n = (int)patch.modules.size();
@@ -214,7 +221,7 @@ int compile_program(const srk_patch& patch, int max_warps, Program& prog, std::s
         p.ins.aux = (uint16_t)prog.tables.size();
         p.ins.n_ch = (uint8_t)mod->seq_steps;
         // `val as f32 * (1.0 / self.steps_per_octave as f32)` (sequencer.rs:233-234): the f32 reciprocal
-        p.ins.imm = 1.0f / (float)(uint16_t)mod->param[SRK_GRIDSEQ_STEPS_PER_OCTAVE];
+        p.ins.imm = 1.0f / (float)steps_per_octave_u16(mod->param[SRK_GRIDSEQ_STEPS_PER_OCTAVE]);
         prog.tables.insert(prog.tables.end(), mod->sequence.begin(), mod->sequence.end());
         break;
       case SRK_KIND_SAMPLE: {
@@ -294,7 +301,8 @@ int compile_program(const srk_patch& patch, int max_warps, Program& prog, std::s
       code.push_back(s);
     }
   }
-  if (code.size() > 4000 || prog.state_init.size() > 60000 || prog.param_src.size() > 60000) {
+  // (table offsets ride in the 16-bit Instr::aux: a pattern sequencer takes 512 words)
+  if (code.size() > 4000 || prog.state_init.size() > 60000 || prog.param_src.size() > 60000 || prog.tables.size() > 65535) {
     err = "patch too large";
     return SRK_ERR_LIMIT;
   }

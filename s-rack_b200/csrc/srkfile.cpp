@@ -26,6 +26,7 @@
 // (they only matter as the first block of history of a wire the cycle breaker cut).
 #include "srkfile.hpp"
 
+#include <algorithm>
 #include <cstring>
 #include <map>
 
@@ -53,6 +54,12 @@ struct Reader {
   const unsigned char* end;
   std::string err;
   int depth = 0;
+  // Memory is bounded by the bytes actually consumed, not by the counts a header declares: containers grow element by
+  // element (every element costs at least one input byte) and the tree may hold at most kMaxNodes values in total
+  // (a Val is ~112 bytes: 4M nodes = 450 MB is far above any real patch; f32 arrays -- port buffers, wave tables -- do not
+  // count, they are stored flat).
+  static constexpr size_t kMaxNodes = 4u << 20;
+  size_t nodes = 0;
 
   bool need(size_t n) {
     if ((size_t)(end - p) < n) { err = "truncated MessagePack"; return false; }
@@ -88,20 +95,23 @@ struct Reader {
       }
     }
     v.type = Val::ARR;
-    v.arr.resize(n);
-    for (size_t k = 0; k < n; ++k)
-      if (!read(v.arr[k])) return false;
+    return read_items(n, v);
+  }
+  bool read_items(size_t n, Val& v) {
+    v.arr.reserve(std::min<size_t>(n, 64));
+    for (size_t k = 0; k < n; ++k) {
+      v.arr.emplace_back();
+      if (!read(v.arr.back())) return false;
+    }
     return true;
   }
   bool read_map(size_t n, Val& v) {
-    if (2 * n > (size_t)(end - p)) { err = "map longer than the file"; return false; }
+    if (n > (size_t)(end - p) / 2) { err = "map longer than the file"; return false; }
     v.type = Val::MAP;
-    v.arr.resize(2 * n);
-    for (size_t k = 0; k < 2 * n; ++k)
-      if (!read(v.arr[k])) return false;
-    return true;
+    return read_items(2 * n, v);
   }
   bool read(Val& v) {
+    if (++nodes > kMaxNodes) { err = "MessagePack document has too many values"; return false; }
     if (++depth > 64) { err = "MessagePack nested too deep"; return false; }
     const bool ok = read1(v);
     --depth;
@@ -536,7 +546,7 @@ void srk_file_encode(const SrkFile& f, size_t buffer_size, uint16_t sample_rate,
           w.array(2); w.uint((uint32_t)c & 0xFFFF); w.boolean((c >> 16) & 1);
         }
         w.uint(2);  // octaves (sequencer.rs:39; GUI only)
-        w.uint((uint16_t)m.param[SRK_GRIDSEQ_STEPS_PER_OCTAVE]);
+        { const float spo = m.param[SRK_GRIDSEQ_STEPS_PER_OCTAVE]; w.uint(!(spo > 0.0f) ? 0u : spo >= 65535.0f ? 65535u : (unsigned)spo); }
         if (m.state.size() == 2) {  // current_step, detectors, last, ui_dirty
           w.uint(m.state[0] & 0xFFFF); w.detector((m.state[0] >> 16) & 1); w.detector((m.state[0] >> 17) & 1); w.f32(wf(m.state[1]));
         } else {

@@ -323,6 +323,27 @@ class Patch:
         self._check(lib.srk_precompile(self._h, n_voices, C.byref(done)))
         return bool(done.value)
 
+    def kernel_id(self, n_voices=0):
+        """Identity of the kernel image a render of n_voices would launch (profiles are stamped with it)."""
+        s = C.c_char_p()
+        self._check(lib.srk_kernel_id(self._h, n_voices, C.byref(s)))
+        return (s.value or b"").decode()
+
+    def set_co_resident_voices(self, n_voices):
+        """Voices other patches render on this device concurrently: the launch is scheduled for the sum."""
+        self._check(lib.srk_set_co_resident_voices(self._h, int(n_voices)))
+
+    # -- per-voice DSP state: checkpoint / resume of a render (the reference serializes it with the patch, ui.rs:98-134)
+    def state_export(self):
+        """-> bytes: state words, feedback history and sample index of the voice range last rendered."""
+        ptr, n = C.c_void_p(), C.c_size_t()
+        self._check(lib.srk_state_export(self._h, C.byref(ptr), C.byref(n)))
+        return C.string_at(ptr.value, n.value)
+
+    def state_import(self, blob):
+        blob = bytes(blob)
+        self._check(lib.srk_state_import(self._h, blob, len(blob)))
+
     def program(self, n_voices=0):
         """The compiled, scheduled device program for n_voices voices -> (instrs, wires): lists of
         dicts (op name, flags, warp, stage, in/out wire slots, ...) and (first_tile, n_tiles)."""

@@ -182,3 +182,55 @@ def test_render_without_plan_or_device_fails_loudly(srk):
         with pytest.raises(srk.SrackError) as e:
             p.render(1, 16)
         assert e.value.status == srk.STATUS["ERR_NO_DEVICE"]  # no CPU path
+
+
+def test_kernel_id_names_the_image_a_render_would_use(srk):
+    """srk_kernel_id (no device needed): equal patches -> equal ids, another graph or another launch shape -> another
+    id; the interpreter kernels are named by the hash of their sources at build time."""
+    def patch(builder, V):
+        p = srk.Patch()
+        builder(p, V)
+        p.plan()
+        return p
+    a, b = patch(srk.patches.cfg2, 4096), patch(srk.patches.cfg2, 4096)
+    ida = a.kernel_id(65536)
+    assert ida == b.kernel_id(65536) and ida.startswith("fused:") and len(ida) > 12
+    assert ida != patch(srk.patches.cfg4, 4096).kernel_id(65536)
+    assert ida != a.kernel_id(4096)  # few voice groups per SM: the staged variant
+    import os
+    os.environ["SRK_FUSED"] = "0"
+    try:
+        idi = a.kernel_id(65536)
+    finally:
+        del os.environ["SRK_FUSED"]
+    assert idi.startswith("interpreter:") and idi.endswith(":solo") and "unknown" not in idi
+
+
+def test_state_blob_calls_fail_cleanly_without_a_render(srk):
+    import ctypes as C
+    p = srk.Patch()
+    srk.patches.cfg2(p, 8)
+    with pytest.raises(srk.SrackError):   # not planned
+        p.state_import(b"SRKSTATE" + bytes(64))
+    p.plan()
+    with pytest.raises(srk.SrackError):   # nothing rendered
+        p.state_export()
+    with pytest.raises(srk.SrackError):   # not a blob
+        p.state_import(b"nonsense")
+
+
+def test_hostile_srk_file_is_refused_without_a_memory_blowup(srk):
+    """nested array32 headers declaring huge counts used to allocate count x sizeof(Val) per level."""
+    import resource
+    import time
+    p = srk.Patch()
+    evil = (b"\xdd\x7f\xff\xff\xff" * 60) + b"\xc0" * (256 * 1024)
+    before = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss
+    t0 = time.time()
+    with pytest.raises(srk.SrackError):
+        p.load_srk(evil)
+    wide = b"\xdd\x00\x03\xff\xff" + b"\xc0" * (0x3ffff)  # one honest, wide array of nils: still not a patch
+    with pytest.raises(srk.SrackError):
+        p.load_srk(wide)
+    assert time.time() - t0 < 5.0
+    assert resource.getrusage(resource.RUSAGE_SELF).ru_maxrss - before < 200 * 1024  # KiB

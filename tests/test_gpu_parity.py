@@ -655,3 +655,94 @@ def test_baseline_size_cfg3b_feedback(srk, orc, cuda_device):
     ref, _ = op.render(33, N, voice_offset=40000)
     s = assert_parity(st, ref, what="cfg3b voice slice")
     assert s["bit_identical"] > 0.98
+
+
+@pytest.mark.parametrize("name,B", [("cfg2", 1024), ("cfg3b", 256), ("cfg4", 1024), ("sequenced", 1024), ("sampler", 1024)])
+def test_state_export_import_resumes_bit_for_bit(srk, orc, cuda_device, name, B):
+    """Checkpoint / resume (the reference serializes every module's DSP state, ui.rs:98-134):
+    render 20000 samples, export the per-voice state, import it into a NEW patch built from the same description,
+    render 28000 more == one 48000-sample render, bit for bit, stems and mix -- incl. cfg3b's feedback ring, the
+    noise counter (cfg4), step counters (sequenced) and play positions (sampler)."""
+    builders = dict(srk.patches.CONFIGS)
+    builder = builders[name][0] if name in builders else getattr(srk.patches, name)
+    V, N1, N2 = 100, 20000, 28000
+
+    def fresh():
+        p = srk.Patch(srk.AudioConfig(48000, B, 2))
+        builder(p, V)
+        p.plan()
+        return p
+
+    whole = fresh()
+    w_st, w_mix = whole.render(V, N1 + N2, stems=True)
+    a = fresh()
+    a_st, a_mix = a.render(V, N1, stems=True)
+    blob = a.state_export()
+    assert blob[:8] == b"SRKSTATE"
+    b = fresh()
+    b.state_import(blob)
+    b_st, b_mix = b.render(V, N2, stems=True)
+    got = np.concatenate([a_st, b_st], axis=1)
+    assert (got.view(np.uint32) == w_st.view(np.uint32)).all()
+    assert (np.concatenate([a_mix, b_mix], axis=1).view(np.uint32) == w_mix.view(np.uint32)).all()
+    # the exporting patch carries on unchanged, and an export straight after an import returns the same blob
+    a_st2, _ = a.render(V, N2, stems=True)
+    assert (a_st2.view(np.uint32) == b_st.view(np.uint32)).all()
+    c = fresh()
+    c.state_import(blob)
+    assert c.state_export() == blob
+    # a blob from another graph, or a truncated one, is refused
+    other = srk.Patch(srk.AudioConfig(48000, B, 2))
+    srk.patches.cfg1(other, V)
+    other.plan()
+    with pytest.raises(srk.SrackError):
+        other.state_import(blob)
+    with pytest.raises(srk.SrackError):
+        fresh().state_import(blob[:-4])
+
+
+def test_state_export_needs_a_render_and_shards_keep_their_offset(srk, orc, cuda_device):
+    p = srk.Patch()
+    srk.patches.cfg4(p, 64)
+    p.plan()
+    with pytest.raises(srk.SrackError):
+        p.state_export()
+    # a shard's blob resumes the shard (voice_offset is part of it: the noise key and the per-voice parameters follow)
+    st1, _ = p.render(24, 3000, voice_offset=40, stems=True)
+    blob = p.state_export()
+    q = srk.Patch()
+    srk.patches.cfg4(q, 64)
+    q.plan()
+    q.state_import(blob)
+    a, _ = p.render(24, 2000, voice_offset=40, stems=True)
+    b, _ = q.render(24, 2000, voice_offset=40, stems=True)
+    assert (a.view(np.uint32) == b.view(np.uint32)).all()
+
+
+def test_no_voices_gives_a_silent_mix(srk, cuda_device):
+    """A rank that got no voices (world size > voices) must contribute zeros to the NCCL sum."""
+    p = srk.Patch()
+    srk.patches.cfg2(p, 8)
+    p.plan()
+    mix = np.full((2, 512), 7.0, np.float32)
+    p.render_into(0, 512, 0, None, mix.ctypes.data)
+    assert not mix.any()
+
+
+def test_co_resident_hint_changes_the_launch_shape_not_the_bits(srk, orc, cuda_device, schedule):
+    """Several patches rendering at once on one device are scheduled for the sum of their voices
+    (srk_set_co_resident_voices): another launch shape, the same samples."""
+    V, N = 256, 6000
+    a = srk.Patch()
+    srk.patches.cfg4(a, V)
+    a.plan()
+    b = srk.Patch()
+    srk.patches.cfg4(b, V)
+    b.set_co_resident_voices(65536)
+    b.plan()
+    ia, ib = a.program_info(V), b.program_info(V)
+    if schedule == "auto":
+        assert ia["n_warps"] > 1 and ib["n_warps"] == 1  # staged when alone on the chip, one warp per group when it is full
+    a_st, a_mix = a.render(V, N, stems=True)
+    b_st, b_mix = b.render(V, N, stems=True)
+    assert (a_st.view(np.uint32) == b_st.view(np.uint32)).all()
