@@ -37,6 +37,7 @@
 
 #include <type_traits>
 
+#include "libm_glibc.cuh"
 #include "program.hpp"
 
 namespace srk {
@@ -222,7 +223,7 @@ struct OscOp {
         if (DM == 2)
           dl[j] = __hiloint2double(__float_as_int(dhi[(k0 + j) * L]), __float_as_int(dlo[(k0 + j) * L]));
         else
-          dl[j] = HAS_CV ? __ddiv_rn(dmul(440.0, exp2(dadd((double)cvv[j], val))), sr) : delta_const;
+          dl[j] = HAS_CV ? __ddiv_rn(dmul(440.0, exp2_glibc(dadd((double)cvv[j], val))), sr) : delta_const;
       }
       // the recurrence: sync reset, pos += delta; pos %= 1.0 (:151-152)
       const double pos0 = pos;
@@ -410,7 +411,7 @@ struct OscDeltaOp {
 #pragma unroll
       for (int j = 0; j < U; ++j) c[j] = cv[(k0 + j) * L];
 #pragma unroll
-      for (int j = 0; j < U; ++j) d[j] = __ddiv_rn(dmul(440.0, exp2(dadd((double)c[j], val))), sr);
+      for (int j = 0; j < U; ++j) d[j] = __ddiv_rn(dmul(440.0, exp2_glibc(dadd((double)c[j], val))), sr);
 #pragma unroll
       for (int j = 0; j < U; ++j) {
         lo[(k0 + j) * L] = __int_as_float(__double2loint(d[j]));
@@ -1183,11 +1184,10 @@ struct MixerOp {
 };
 
 // ---- MathModule / NonLinearModule::calc, src/synth/math.rs:139-160, :292-313 ----
-// math.rs:203-205 `if a > 0.0 { a.powf(b) } else { -(-a).powf(b) }` in f32.  glibc's powf
-// evaluates in f64 and rounds once; f64 pow here then one rounding agrees with it except
-// when the f64 results straddle an f32 rounding boundary.  Out of line: pow() is large.
+// math.rs:203-205 `if a > 0.0 { a.powf(b) } else { -(-a).powf(b) }` in f32: the platform's powf, restated
+// operation by operation in libm_glibc.cuh (bit-identical to glibc 2.39).  Out of line: it is large.
 static __device__ __noinline__ float nonlinear(float a, float b) {
-  return a > 0.0f ? __double2float_rn(pow((double)a, (double)b)) : -__double2float_rn(pow((double)(-a), (double)b));
+  return a > 0.0f ? powf_glibc(a, b) : -powf_glibc(-a, b);
 }
 
 template <int WHICH>

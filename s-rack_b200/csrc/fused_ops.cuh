@@ -15,6 +15,7 @@
 // No standard headers: NVRTC has none.  Everything is inside namespace fz.
 #pragma once
 #include "fused_args.h"
+#include "libm_glibc.cuh"
 
 namespace fz {
 
@@ -287,7 +288,7 @@ struct Osc {
       last = false;
     }
 #pragma unroll
-    for (int j = 0; j < U; ++j) dl[j] = HAS_CV ? __ddiv_rn(dmul(440.0, exp2(dadd((double)cv[j], val))), sr) : d0;
+    for (int j = 0; j < U; ++j) dl[j] = HAS_CV ? __ddiv_rn(dmul(440.0, exp2_glibc(dadd((double)cv[j], val))), sr) : d0;
     const double pos0 = pos;
     bool odd = false;
 #pragma unroll
@@ -666,7 +667,7 @@ struct Mixer {
 
 // ---- MathModule / NonLinearModule::calc, src/synth/math.rs:139-160, :203-205, :292-313 ----------
 static __device__ __noinline__ float nonlinear(float a, float b) {
-  return a > 0.0f ? __double2float_rn(pow((double)a, (double)b)) : -__double2float_rn(pow((double)(-a), (double)b));
+  return a > 0.0f ? powf_glibc(a, b) : -powf_glibc(-a, b);  // glibc's powf, bit for bit (libm_glibc.cuh)
 }
 template <int WHICH /*0 add 1 sub 2 mul 3 non-linear*/, bool HAS_A, bool HAS_B>
 struct Math {

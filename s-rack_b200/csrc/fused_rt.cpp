@@ -19,7 +19,7 @@
 #include <memory>
 #include <mutex>
 
-#include "fused_embed.inc"  // kFusedOpsSrc, kFusedArgsSrc: the two headers as strings (Makefile)
+#include "fused_embed.inc"  // kFusedOpsSrc, kFusedArgsSrc, kFusedLibmSrc: the headers as strings (Makefile)
 
 namespace srk {
 
@@ -77,6 +77,7 @@ const Nvrtc& nvrtc() {
 std::string salt() {
   std::string s(kFusedOpsSrc);
   s += kFusedArgsSrc;
+  s += kFusedLibmSrc;
   for (int i = 0; i < kNumNvrtcOptions; ++i) { s += kNvrtcOptions[i]; s += ' '; }
   return s;
 }
@@ -133,9 +134,9 @@ int fused_cubin(const FusedSpec& spec, std::vector<char>& cubin, std::string& ke
   if (!rt.ok()) { err = "fused kernels unavailable: " + rt.why; return SRK_ERR_UNSUPPORTED; }
   const auto t0 = std::chrono::steady_clock::now();
   nvrtcProgram prog = nullptr;
-  const char* headers[] = {kFusedOpsSrc, kFusedArgsSrc};
-  const char* names[] = {"fused_ops.cuh", "fused_args.h"};
-  if (rt.create(&prog, spec.source.c_str(), "srk_fused.cu", 2, headers, names) != NVRTC_SUCCESS) {
+  const char* headers[] = {kFusedOpsSrc, kFusedArgsSrc, kFusedLibmSrc};
+  const char* names[] = {"fused_ops.cuh", "fused_args.h", "libm_glibc.cuh"};
+  if (rt.create(&prog, spec.source.c_str(), "srk_fused.cu", 3, headers, names) != NVRTC_SUCCESS) {
     err = "nvrtcCreateProgram failed";
     return SRK_ERR_LIMIT;
   }

@@ -1,0 +1,74 @@
+"""s-rack_b200/csrc/libm_glibc.cuh -- the operation-by-operation restatements of glibc 2.39's exp2 (f64: the oscillator's
+V/oct conversion, oscillator.rs:43-48) and powf (the Non-Linear module, math.rs:203-205) that the device computes with --
+compiled for the host (tests/c/libm_glibc_host.cpp: the same header, intrinsics swapped for plain arithmetic) and held to
+the platform's libm, bit for bit, over random and special inputs.  The platform's libm is what the CPU oracle calls, so
+this pins the device's arithmetic to the oracle's without a GPU; the GPU tests then check the device against the oracle
+through patches."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def host(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("libm") / "libm_glibc_host.so")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-mfma", "-shared", "-fPIC", "-o", so,
+                           os.path.join(ROOT, "tests", "c", "libm_glibc_host.cpp")])
+    L = ctypes.CDLL(so)
+    L.t_exp2_glibc.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
+    L.t_powf_glibc.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
+    return L
+
+
+@pytest.fixture(scope="module")
+def libm():
+    m = ctypes.CDLL("libm.so.6")
+    m.exp2.restype = ctypes.c_double
+    m.exp2.argtypes = [ctypes.c_double]
+    m.powf.restype = ctypes.c_float
+    m.powf.argtypes = [ctypes.c_float, ctypes.c_float]
+    m.gnu_get_libc_version = ctypes.CDLL("libc.so.6").gnu_get_libc_version
+    m.gnu_get_libc_version.restype = ctypes.c_char_p
+    return m
+
+
+def test_exp2_f64_equals_glibc_bit_for_bit(host, libm):
+    rng = np.random.default_rng(1)
+    x = np.concatenate([
+        rng.uniform(-12, 12, 150000),                   # the V/oct range of any audible patch
+        np.float32(rng.uniform(-8, 8, 50000)).astype(np.float64) + np.float32(rng.uniform(-3, 3, 50000)).astype(np.float64),  # f64(cv) + f64(val)
+        rng.uniform(-1100, 1100, 60000),                # overflow, underflow, the subnormal range
+        rng.standard_normal(20000) * 1e-12, rng.standard_normal(2000) * 1e-17,
+        np.arange(-1080, 1030, dtype=np.float64), np.arange(-1080, 1030, dtype=np.float64) + 0.5,
+        np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1024.0, 1023.9999999999999, -1075.0, -1074.9999, -1022.0, -1022.0000001, 928.0,
+                  928.0000001, -928.5, 511.99999, 512.0, 1e-300, -1e-300, 2.0 ** -54, -(2.0 ** -54), 2.0 ** -55, 5e-324]),
+    ])
+    y = np.zeros_like(x)
+    host.t_exp2_glibc(x.ctypes.data, y.ctypes.data, x.size)
+    ref = np.array([libm.exp2(float(v)) for v in x])
+    same = (y.view(np.uint64) == ref.view(np.uint64)) | (np.isnan(y) & np.isnan(ref))
+    assert same.all(), f"glibc {libm.gnu_get_libc_version().decode()}: {int((~same).sum())} of {x.size} differ, e.g. x = {x[~same][:5]}"
+
+
+def test_powf_equals_glibc_bit_for_bit(host, libm):
+    rng = np.random.default_rng(2)
+    a = np.concatenate([rng.uniform(0, 4, 150000), np.exp(rng.uniform(-87, 88, 80000)), rng.uniform(-3, 3, 30000),
+                        rng.uniform(0, 1.2e-38, 5000)]).astype(np.float32)
+    b = np.concatenate([rng.uniform(0.5, 2, 150000), rng.uniform(-40, 40, 80000), rng.integers(-5, 6, 30000).astype(np.float64),
+                        rng.uniform(-2, 2, 5000)]).astype(np.float32)
+    sp = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1.0, -1.0, 1e-42, -1e-42, 3e38, 0.5, 2.0, -2.0, -8.0, 3.0, -3.0, 2.5, -0.5, 1e10,
+                   127.0, 128.0, -149.0, -150.0, 16777216.0, 16777217.0, 8388609.0], dtype=np.float32)
+    # (signalling NaNs are not exercised: ctypes widens the argument to a Python float, which quiets it on the way to libm)
+    A, Bm = np.meshgrid(sp, sp)
+    a, b = np.concatenate([a, A.ravel()]), np.concatenate([b, Bm.ravel()])
+    z = np.zeros_like(a)
+    host.t_powf_glibc(a.ctypes.data, b.ctypes.data, z.ctypes.data, a.size)
+    ref = np.array([libm.powf(float(u), float(v)) for u, v in zip(a, b)], dtype=np.float32)
+    same = (z.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(z) & np.isnan(ref))
+    bad = np.where(~same)[0][:5]
+    assert same.all(), f"{int((~same).sum())} of {a.size} differ, e.g. {[(float(a[i]), float(b[i]), float(z[i]), float(ref[i])) for i in bad]}"
