@@ -15,8 +15,8 @@ roofline, so the driver's records carry them:
   N = 1 : `configs` = cfg2 @ 65536 voices (the full chip), cfg3 and cfg3b @ 65536 (configs[2]), cfg4 @ 32768 (one GPU's
           share of configs[3]); `block_cadence` (srk_render per 1024-sample block); the CPU baselines.
   N > 1 : `cfg4_shard` (configs[3]: 32768 voices per GPU, 262144 at N = 8), `cfg5` (configs[4]: 8 graphs x 32768 voices
-          dealt to the ranks, one graph per GPU at N = 8) and `cfg5_balanced` (every graph voice-sharded over all ranks,
-          a rank's eight launches concurrent on eight streams).
+          dealt to the ranks, one graph per GPU at N = 8) and `cfg5_balanced` (the same job dealt as (graph, voice range)
+          pieces: graphs longer than a rank's fair share are cut in two).
 `mix_check` verifies the result in the same run: at N = 1 the mix against the f64 sum of the stems; at N > 1 the
 NCCL-reduced mix against the f64 sum of the gathered per-rank mixes, and rank 0 re-renders another rank's voice range
 (voice_offset) and compares it with what that rank produced, bit for bit.
@@ -525,11 +525,7 @@ def graphs_on_ranks(ctx, V, steps, warmup):
         weights.append(p.last_render_ms()[0])
         del p
     weights = ctx.max_over_ranks(*weights)
-    load, owner = [0.0] * world, {}
-    for g in sorted(range(len(graphs)), key=lambda i: (-weights[i], i)):
-        r = min(range(world), key=lambda k: (load[k], k))
-        owner[g] = r
-        load[r] += weights[g]
+    owner, load = lpt(weights, world)
     mine = [g for g in range(len(graphs)) if owner[g] == rank]
     patches = [(g, ctx.patch(names[g], V)) for g in mine]
     mixes = [torch.empty((C, N_SAMPLES), dtype=torch.float32, device=ctx.dev) for _ in mine]
@@ -595,46 +591,79 @@ def graphs_on_ranks(ctx, V, steps, warmup):
                             "frac": algo / (k_sum * 1e-3) / 1e9 / peak, "traffic": None,
                             "kernel": "sum over the 8 graphs' voice-kernel launches", "kernel_ms": k_sum},
                 "per_graph": per_graph, "gpu_launches": int(launches), "mix_check": check}
-    return rec, total.clone()
+    return rec, total.clone(), weights
 
 
-def graphs_balanced(ctx, V, steps, warmup, reference_mix=None):
-    """cfg5 with every GPU carrying the same load: each of the 8 graphs is voice-sharded over ALL ranks (rank r renders
-    voices [r V/N, (r+1) V/N) of every graph), and a rank's eight launches run CONCURRENTLY, one stream per patch, each
-    scheduled for the voices that share the device (srk_set_co_resident_voices)."""
+def lpt(times, world):
+    """Longest-processing-time-first: -> (owner per item, load per rank)."""
+    load, owner = [0.0] * world, [0] * len(times)
+    for i in sorted(range(len(times)), key=lambda i: (-times[i], i)):
+        r = min(range(world), key=lambda k: (load[k], k))
+        owner[i] = r
+        load[r] += times[i]
+    return owner, load
+
+
+def graphs_balanced(ctx, V, steps, warmup, whole_ms, reference_mix=None):
+    """cfg5 beyond one graph per GPU: the work is dealt as (graph, voice range) PIECES.  A graph whose kernel is longer than
+    a rank's fair share is cut into two half ranges (voice_offset) when that shortens the longest rank -- with the half's
+    kernel time measured in this run, because a half costs more than half (fewer voice groups per SM: less latency hiding).
+    Pieces go to ranks longest first; a rank renders its pieces one after the other, sums their mixes, then the one NCCL sum."""
     torch, srk = ctx.torch, ctx.srk
     graphs = srk.patches.CFG5_GRAPHS
     names = [g.__name__ for g in graphs]
     world, rank = ctx.world, ctx.rank
-    off, cnt = srk.shard.voice_range(V, rank, world)
-    buf = ctx.stems(cnt * len(graphs)).view(-1)
-    per = C * N_SAMPLES * cnt
-    patches, stems, mixes = [], [], []
-    for i, n in enumerate(names):
-        p = ctx.patch(n, V)
-        p.set_co_resident_voices(cnt * (len(graphs) - 1))
-        patches.append(p)
-        stems.append(buf[i * per:(i + 1) * per])
-        mixes.append(torch.empty((C, N_SAMPLES), dtype=torch.float32, device=ctx.dev))
+    stems = ctx.stems(V)
+    scratch = torch.empty((C, N_SAMPLES), dtype=torch.float32, device=ctx.dev)
+    half = V // 2
+    fair = sum(whole_ms) / world
+    half_ms = {}
+    for g in range(len(graphs)):  # candidates: measured on every rank, max over ranks -> the same decision everywhere
+        if whole_ms[g] > fair and world > 1:
+            p = ctx.patch(names[g], V)
+            for _ in range(2):
+                p.render_into(half, N_SAMPLES, 0, stems.data_ptr(), scratch.data_ptr(), device_out=True, stream=ctx.stream)
+            half_ms[g] = p.last_render_ms()[0]
+            del p
+    if half_ms:
+        vals = ctx.max_over_ranks(*[half_ms[g] for g in sorted(half_ms)])
+        half_ms = dict(zip(sorted(half_ms), vals))
+    split = set()
+    for g in sorted(half_ms, key=lambda g: -whole_ms[g]):
+        def makespan(sp):
+            t = [x for i in range(len(graphs)) for x in ([half_ms[i]] * 2 if i in sp else [whole_ms[i]])]
+            return max(lpt(t, world)[1])
+        if makespan(split | {g}) < makespan(split):
+            split.add(g)
+    pieces = []  # (graph, voice offset, voices, estimated ms)
+    for g in range(len(graphs)):
+        if g in split:
+            pieces += [(g, 0, half, half_ms[g]), (g, half, V - half, half_ms[g])]
+        else:
+            pieces.append((g, 0, V, whole_ms[g]))
+    owner, load = lpt([p[3] for p in pieces], world)
+    mine = [pieces[i] for i in range(len(pieces)) if owner[i] == rank]
+    patches = [(ctx.patch(names[g], V), off, cnt) for g, off, cnt, _ in mine]
+    mixes = [torch.empty((C, N_SAMPLES), dtype=torch.float32, device=ctx.dev) for _ in mine]
     total = torch.zeros((C, N_SAMPLES), dtype=torch.float32, device=ctx.dev)
 
     def local():
-        torch.cuda.current_stream().synchronize()  # the previous step's sum has read the mixes
-        for p, st, mx in zip(patches, stems, mixes):  # each on its patch's own stream: concurrent
-            p.render_into(cnt, N_SAMPLES, off, st.data_ptr(), mx.data_ptr(), device_out=True, async_=True)
-        for p in patches:
-            p.sync()
-        torch.sum(torch.stack(mixes), dim=0, out=total)
+        for (p, off, cnt), mx in zip(patches, mixes):
+            p.render_into(cnt, N_SAMPLES, off, stems.data_ptr(), mx.data_ptr(), device_out=True, async_=True, stream=ctx.stream)
+        if mixes:
+            torch.sum(torch.stack(mixes), dim=0, out=total)
+        else:
+            total.zero_()
 
     def step():
         local()
         if world > 1:
             srk.shard.reduce_mix(total)
 
-    launches0 = sum(p.launch_count() for p in patches)
+    launches0 = sum(p.launch_count() for p, _, _ in patches)
     ms = timed_steps(ctx, step, steps, warmup)
-    launches = (sum(p.launch_count() for p in patches) - launches0) * steps // (steps + warmup)
-    for p in patches:
+    launches = (sum(p.launch_count() for p, _, _ in patches) - launches0) * steps // (steps + warmup)
+    for p, _, _ in patches:
         p.reset()
     local()
     torch.cuda.synchronize()
@@ -654,11 +683,13 @@ def graphs_balanced(ctx, V, steps, warmup, reference_mix=None):
         check["max_err_over_bound_vs_whole_graphs"] = float((err / bound).max())
         if not same:
             check["result"] = "FAILED"
-    info = patches[3].program_info(cnt)
-    return {"workload": f"cfg5 balanced: each of the 8 graphs voice-sharded over all {world} ranks ({cnt} voices per graph per GPU), "
-                        "a rank's 8 launches concurrent on 8 streams", "voices_total": len(graphs) * V, "scaling": "strong",
-            "value": len(graphs) * V * N_SAMPLES / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "warmup": warmup,
-            "gpu_launches": int(launches), "launch_shape_cfg4": launch_shape(info), "mix_check": check}
+    return {"workload": f"cfg5 balanced: 8 graphs x {V} voices dealt to {world} ranks as (graph, voice range) pieces, longest first",
+            "voices_total": len(graphs) * V, "scaling": "strong", "value": len(graphs) * V * N_SAMPLES / (ms * 1e-3), "unit": UNIT,
+            "ms_per_step": ms, "steps": steps, "warmup": warmup, "fair_share_ms": fair,
+            "split_in_two": {names[g]: {"whole_ms": whole_ms[g], "half_ms": half_ms[g]} for g in sorted(split)},
+            "pieces": [{"graph": names[g], "voice_offset": off, "voices": cnt, "rank": owner[i], "estimated_ms": t}
+                       for i, (g, off, cnt, t) in enumerate(pieces)],
+            "rank_load_ms": load, "gpu_launches": int(launches), "mix_check": check}
 
 
 def main():
@@ -682,8 +713,8 @@ def main():
     ctx = Ctx(args)
     srk, torch, world, rank = ctx.srk, ctx.torch, ctx.world, ctx.rank
     if args.config == "cfg5":
-        rec, total = graphs_on_ranks(ctx, args.voices_per_gpu or srk.patches.CFG5_VOICES, args.steps, args.warmup)
-        bal = graphs_balanced(ctx, args.voices_per_gpu or srk.patches.CFG5_VOICES, args.steps, args.warmup, total)
+        rec, total, weights = graphs_on_ranks(ctx, args.voices_per_gpu or srk.patches.CFG5_VOICES, args.steps, args.warmup)
+        bal = graphs_balanced(ctx, args.voices_per_gpu or srk.patches.CFG5_VOICES, args.steps, args.warmup, weights, total)
         if rank == 0:
             line = {"metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                     "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -744,9 +775,9 @@ def main():
     elif default_run:
         cfg4, _, _, _ = voice_shard(ctx, "cfg4", 32768, max(3, min(args.steps, 5)), 3, e2e=False)
         extras["cfg4_shard"] = cfg4
-        g, total = graphs_on_ranks(ctx, srk.patches.CFG5_VOICES, max(3, min(args.steps, 5)), 3)
+        g, total, weights = graphs_on_ranks(ctx, srk.patches.CFG5_VOICES, max(3, min(args.steps, 5)), 3)
         extras["cfg5"] = g
-        extras["cfg5_balanced"] = graphs_balanced(ctx, srk.patches.CFG5_VOICES, max(3, min(args.steps, 5)), 3, total)
+        extras["cfg5_balanced"] = graphs_balanced(ctx, srk.patches.CFG5_VOICES, max(3, min(args.steps, 5)), 3, weights, total)
 
     if rank == 0:
         cpu = cpu1 = None

@@ -51,7 +51,7 @@ def test_cfg2_subtractive_is_bit_exact(srk, orc, cuda_device):
 def test_cfg3_fm(srk, orc, cuda_device):
     gp, op, g, g_mix, o, o_mix = render_pair(srk, orc, srk.patches.cfg3, 99, 8192)
     s = assert_parity(g, o, what="cfg3")
-    assert s["bit_identical"] > 0.99
+    assert s["bit_identical"] > 0.999  # (measured 1.0, profiles/r05d_parity_report.txt; the f64 sin is CUDA's, <= 1 ulp from glibc's)
     assert_mix_parity(g_mix, o_mix, 99)
 
 
@@ -61,14 +61,14 @@ def test_cfg3b_feedback_delay_equals_buffer_size(srk, orc, cuda_device, B):
     gp, op, g, g_mix, o, o_mix = render_pair(srk, orc, srk.patches.cfg3b, 70, N, B=B)
     assert len(gp.plan_cuts()) == 1
     s = assert_parity(g, o, what=f"cfg3b B={B}")
-    assert s["bit_identical"] > 0.98
+    assert s["bit_identical"] > 0.999
 
 
 def test_cfg4_full_subtractive(srk, orc, cuda_device):
     gp, op, g, g_mix, o, o_mix = render_pair(srk, orc, srk.patches.cfg4, 70, 26000)
     assert np.abs(o).max() > 0.1
     s = assert_parity(g, o, what="cfg4")
-    assert s["bit_identical"] > 0.99
+    assert s["bit_identical"] > 0.999
     assert_mix_parity(g_mix, o_mix, 70)
 
 
