@@ -59,6 +59,9 @@ extern "C" {
                      sample_rate: u32, bits: c_int) -> c_int;
     fn srk_patch_load_srk(patch: *mut srk_patch, bytes: *const c_void, n_bytes: usize, n_skipped: *mut usize) -> c_int;
     fn srk_patch_save_srk(patch: *mut srk_patch, bytes: *mut *const c_void, n_bytes: *mut usize) -> c_int;
+    fn srk_state_export(patch: *mut srk_patch, blob: *mut *const c_void, n_bytes: *mut usize) -> c_int;
+    fn srk_state_import(patch: *mut srk_patch, blob: *const c_void, n_bytes: usize) -> c_int;
+    fn srk_set_co_resident_voices(patch: *mut srk_patch, n_voices: usize) -> c_int;
     fn srk_plan(patch: *mut srk_patch) -> c_int;
     fn srk_plan_get(patch: *const srk_patch, out: *mut *mut srk_module, cap: usize, n: *mut usize) -> c_int;
     fn srk_render(patch: *mut srk_patch, n_voices: usize, voice_offset: usize, n_samples: usize,
@@ -216,6 +219,25 @@ impl Patch {
         let (mut p, mut n) = (ptr::null(), 0usize);
         self.check(unsafe { srk_patch_save_srk(self.h, &mut p, &mut n) })?;
         Ok(unsafe { std::slice::from_raw_parts(p as *const u8, n) }.to_vec())
+    }
+
+    /// Checkpoint of a render in progress: every voice's DSP state (what the reference's modules serialize with
+    /// `#[derive(Serialize)]`, `ui.rs:98-114`), the history of cut wires and the sample index, for the voice range
+    /// last rendered.
+    pub fn state_export(&mut self) -> Result<Vec<u8>, Error> {
+        let (mut p, mut n) = (ptr::null(), 0usize);
+        self.check(unsafe { srk_state_export(self.h, &mut p, &mut n) })?;
+        Ok(unsafe { std::slice::from_raw_parts(p as *const u8, n) }.to_vec())
+    }
+
+    /// Resume: the next `execute` of the blob's voice range continues bit for bit (`ui.rs:115-134`).
+    pub fn state_import(&mut self, blob: &[u8]) -> Result<(), Error> {
+        self.check(unsafe { srk_state_import(self.h, blob.as_ptr() as *const c_void, blob.len()) })
+    }
+
+    /// Voices other patches render on this device at the same time (the launch is scheduled for the sum).
+    pub fn set_co_resident_voices(&mut self, n_voices: usize) -> Result<(), Error> {
+        self.check(unsafe { srk_set_co_resident_voices(self.h, n_voices) })
     }
 }
 

@@ -108,6 +108,7 @@ template <bool HAS_CV, bool HAS_SYNC, int OUTS, bool AA, int RATE>
 struct Osc {
   double pos, d0, val, sr;
   double om0, h1, h2, rd0;  // fast-path bounds and RN(1 / d0) for a constant delta (see run)
+  double rsr;               // RN(1 / sample_rate)
   bool last, small;
 
   FZ_DEV void load(const Ctx& c, u32 sw, u32 val_bits, u32 d_lo, u32 d_hi, float sample_rate) {
@@ -116,6 +117,7 @@ struct Osc {
     val = (double)asf(val_bits);
     d0 = __hiloint2double((int)d_hi, (int)d_lo);
     sr = (double)sample_rate;
+    rsr = __drcp_rn(sr);
     om0 = dsub(1.0, d0);
     // square: (pos + 0.5) % 1.0 stays clear of both ends while pos <= h1 (< 0.5) or pos >= h2 (> 0.5).
     // h1 + 0.5 == om0 exactly, so fl(pos + 0.5) <= om0 for every pos <= h1 (rounding is monotonic);
@@ -287,8 +289,29 @@ struct Osc {
     } else {
       last = false;
     }
+    if (HAS_CV) {
+      // delta = 440 * 2^(cv + val) / sample_rate (:43-48, :132).  The divisor is constant over the render: Markstein's
+      // division by a constant (five f64 instructions, no branch) whenever every numerator of the group is a normal number
+      // whose quotient stays normal, IEEE division otherwise (2^x under- or overflowed, or the CV was not finite)
+      double num[U];
+      bool tame = true;
 #pragma unroll
-    for (int j = 0; j < U; ++j) dl[j] = HAS_CV ? __ddiv_rn(dmul(440.0, exp2_glibc(dadd((double)cv[j], val))), sr) : d0;
+      for (int j = 0; j < U; ++j) {
+        num[j] = dmul(440.0, exp2_glibc(dadd((double)cv[j], val)));
+        const u32 ex = ((u32)__double2hiint(num[j]) >> 20) & 0x7ffu;
+        tame &= (ex - 64u) < 1920u;  // biased exponent in [64, 1984)
+      }
+      if (__all_sync(0xFFFFFFFFu, tame)) {
+#pragma unroll
+        for (int j = 0; j < U; ++j) dl[j] = ddiv_by_const(num[j], sr, rsr);
+      } else {
+#pragma unroll
+        for (int j = 0; j < U; ++j) dl[j] = __ddiv_rn(num[j], sr);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < U; ++j) dl[j] = d0;
+    }
     const double pos0 = pos;
     bool odd = false;
 #pragma unroll

@@ -20,6 +20,13 @@
 #define LG_COLD static __device__ __noinline__
 #define LG_TAB static __device__ const
 #define LG_LD(p) __ldg(p)
+#define LG_ALIGN16 __align__(16)
+// one 16-byte load for a (tail, bits) pair of the exp2 table: the lanes of a warp hit 32 different entries
+struct lg_pair { unsigned long long lo, hi; };
+static __device__ __forceinline__ lg_pair lg_ld_pair(const unsigned long long* p) {
+  const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(p));
+  lg_pair r; r.lo = v.x; r.hi = v.y; return r;
+}
 LG_FN double lg_add(double a, double b) { return __dadd_rn(a, b); }
 LG_FN double lg_sub(double a, double b) { return __dsub_rn(a, b); }
 LG_FN double lg_mul(double a, double b) { return __dmul_rn(a, b); }
@@ -39,6 +46,9 @@ LG_FN float lg_narrow(double x) { return __double2float_rn(x); }
 #define LG_COLD static
 #define LG_TAB static const
 #define LG_LD(p) (*(p))
+#define LG_ALIGN16 __attribute__((aligned(16)))
+struct lg_pair { unsigned long long lo, hi; };
+static inline lg_pair lg_ld_pair(const unsigned long long* p) { lg_pair r; r.lo = p[0]; r.hi = p[1]; return r; }
 LG_FN double lg_add(double a, double b) { return a + b; }
 LG_FN double lg_sub(double a, double b) { return a - b; }
 LG_FN double lg_mul(double a, double b) { return a * b; }
@@ -57,7 +67,7 @@ LG_FN float lg_narrow(double x) { return (float)x; }
 // exp2 (f64)
 // ---------------------------------------------------------------------------------------------------------------------
 // __exp_data.tab: 2^(i/128) as (tail, value bits - (i << 45)) pairs
-LG_TAB unsigned long long kLgExp2Tab[256] = {
+LG_TAB LG_ALIGN16 unsigned long long kLgExp2Tab[256] = {
     0x0000000000000000ull, 0x3ff0000000000000ull, 0x3c9b3b4f1a88bf6eull, 0x3feff63da9fb3335ull,
     0xbc7160139cd8dc5dull, 0x3fefec9a3e778061ull, 0xbc905e7a108766d1ull, 0x3fefe315e86e7f85ull,
     0x3c8cd2523567f613ull, 0x3fefd9b0d3158574ull, 0xbc8bce8023f98efaull, 0x3fefd06b29ddf6deull,
@@ -163,8 +173,9 @@ LG_FN double exp2_glibc(double x) {
   kd = lg_sub(kd, shift);
   const double r = lg_sub(x, kd);
   const unsigned idx = 2u * (unsigned)(ki & 127u);
-  const double tail = lg_f64(LG_LD(&kLgExp2Tab[idx]));
-  const unsigned long long sbits = LG_LD(&kLgExp2Tab[idx + 1]) + (ki << 45);
+  const lg_pair e = lg_ld_pair(&kLgExp2Tab[idx]);
+  const double tail = lg_f64(e.lo);
+  const unsigned long long sbits = e.hi + (ki << 45);
   const double r2 = lg_mul(r, r);
   // tail + r C1 + r2 (C2 + r C3) + r2 r2 (C4 + r C5), left to right as the C source associates
   double tmp = lg_add(tail, lg_mul(r, 0x1.62e42fefa39efp-1));

@@ -72,3 +72,12 @@ def test_powf_equals_glibc_bit_for_bit(host, libm):
     same = (z.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(z) & np.isnan(ref))
     bad = np.where(~same)[0][:5]
     assert same.all(), f"{int((~same).sum())} of {a.size} differ, e.g. {[(float(a[i]), float(b[i]), float(z[i]), float(ref[i])) for i in bad]}"
+
+
+def test_division_by_a_render_constant_equals_ieee_division(tmp_path):
+    """fused_ops.cuh ddiv_by_const (Markstein's final step on a correctly rounded reciprocal) against `a / b` on the
+    operand ranges of the polyBLEP correction and of the V/oct conversion: tests/c/ddiv_markstein.c, 1e8 pairs."""
+    exe = str(tmp_path / "ddiv_markstein")
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-mfma", "-o", exe, os.path.join(ROOT, "tests", "c", "ddiv_markstein.c"), "-lm"])
+    r = subprocess.run([exe, "50000000"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "0 mismatches" in r.stdout, r.stdout[-800:]
