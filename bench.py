@@ -379,8 +379,6 @@ def voice_shard(ctx, name, V_gpu, steps, warmup, e2e=True, sampler=None):
     V_total = V_gpu * world
     off, cnt = srk.shard.voice_range(V_total, rank, world)
     patch = ctx.patch(name, V_total)
-    info = patch.program_info(cnt)
-    kid = patch.kernel_id(cnt)
     stems = ctx.stems(cnt)
     mix = torch.empty((C, N_SAMPLES), dtype=torch.float32, device=ctx.dev)
 
@@ -397,11 +395,12 @@ def voice_shard(ctx, name, V_gpu, steps, warmup, e2e=True, sampler=None):
     ms_step = timed_steps(ctx, step_resident, steps, warmup)
     launches = (patch.launch_count() - launches0) * steps // (steps + warmup)
     kernel_ms = kernel_ms_of(ctx, [patch], lambda p: render(p))[0]
+    kid = patch.kernel_id(cnt)  # (after the first renders: the launch shape in use may be a measured choice)
     rec = {"workload": f"{name} @ {V_gpu} voices per GPU x {N_SAMPLES} samples, stems + mix in HBM", "voices_per_gpu": V_gpu,
            "voices_total": V_total, "value": V_total * N_SAMPLES / (ms_step * 1e-3), "unit": UNIT, "ms_per_step": ms_step,
            "steps": steps, "warmup": warmup, "kernel_ms": kernel_ms, "gpu_launches": int(launches), **launch_shape(patch.program_info(cnt)),
-           "l2": f"each step writes {C * N_SAMPLES * cnt * 4 / 1e6:.0f} MB of stems per GPU (> 126 MB L2), no flush needed"}
-    del info
+           "l2": f"each step writes {C * N_SAMPLES * cnt * 4 / 1e6:.0f} MB of stems per GPU (> 126 MB L2), no flush needed",
+           "schedule": patch.schedule_report()}
 
     # ---- the result, checked in the same run
     patch.reset()
@@ -483,7 +482,7 @@ def single_gpu_config(ctx, name, V, steps=4, warmup=2):
     rec = {"workload": f"{name} @ {V} voices x {N_SAMPLES} samples, stems + mix in HBM", "voices": V,
            "value": V * N_SAMPLES / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "kernel_ms": k, "steps": steps, "warmup": warmup,
            "roofline": roofline(name, V, k, p.kernel_id(V)), "gpu_launches": int(launches), **launch_shape(p.program_info(V)),
-           "mix_check": check_mix_against_stems(ctx, mix, stems, V),
+           "mix_check": check_mix_against_stems(ctx, mix, stems, V), "schedule": p.schedule_report(),
            "timing": f"CUDA events on the launching stream around {steps} steps; {C * N_SAMPLES * V * 4 / 1e9:.1f} GB of stems per step (> L2)"}
     return rec
 

@@ -308,14 +308,22 @@ SRK_API int srk_get_program_info(srk_patch* patch, size_t n_voices, srk_program_
 /* The CUDA C++ translation unit generated for this patch (the wiring; the DSP is csrc/fused_ops.cuh) when a
  * render of n_voices would use a fused kernel, else an empty string.  Valid until the next call on the patch. */
 SRK_API int srk_fused_source(srk_patch* patch, size_t n_voices, const char** source, size_t* n_bytes);
-/* Compiles that kernel for sm_100a into the on-disk cubin cache (kernel_cache/ next to the library, or
- * $SRK_KERNEL_CACHE) so that the first render does not pay for NVRTC.  Needs no GPU.  *compiled = 1 when a
- * compilation happened, 0 when the cubin was cached already or the launch would not use a fused kernel. */
+/* Compiles that kernel -- and the alternative launch shapes a long render measures against it (srk_schedule_report) --
+ * for sm_100a into the on-disk cubin cache (kernel_cache/ next to the library, or $SRK_KERNEL_CACHE) so that the first
+ * render does not pay for NVRTC.  Needs no GPU.  *compiled = the number of kernels compiled now (0: all cached already,
+ * or the launch would not use a fused kernel). */
 SRK_API int srk_precompile(srk_patch* patch, size_t n_voices, int* compiled);
 /* Identity of the kernel image a render of n_voices would launch: "fused:<hash of generated source + op headers +
  * compiler options>" or "interpreter:<hash of the kernel sources at build time>:<pipelined|solo|solo_full>".  Profiles
  * are stamped with it.  Valid until the next call on the patch. */
 SRK_API int srk_kernel_id(srk_patch* patch, size_t n_voices, const char** id);
+/* How the launch shape in use was chosen.  The first render of at least 16384 samples after a (re)plan measures the
+ * plausible launch shapes (fused kernel with 4 or 8 samples per straight-line group, one more pipeline stage, the
+ * interpreter's pipeline) for a few thousand samples each on a scratch copy of the voice state and keeps the fastest;
+ * every shape computes the same bits.  *report: "" before that, else the winner and the measured times (or the cached
+ * decision, kernel_cache/<key>.tune).  SRK_TUNE=0 in the environment, or any forced schedule knob, disables it.
+ * srk_get_program_info / srk_kernel_id describe the shape in use once a render has happened.  Valid until the next call. */
+SRK_API int srk_schedule_report(srk_patch* patch, const char** report);
 /* The compiled, scheduled device program itself (what execute() becomes for n_voices voices):
  * one entry per instruction -- the modules of the plan in plan order (src/synth.rs:97-101), plus
  * ring loads/stores for the wires the cycle breaker cut (synth.rs:168-192), the stems / mixdown

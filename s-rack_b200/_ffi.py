@@ -90,6 +90,7 @@ _SIGNATURES = {
     "srk_fused_source": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t)]),
     "srk_precompile": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_int)]),
     "srk_kernel_id": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_char_p)]),
+    "srk_schedule_report": (C.c_int, [_P, C.POINTER(C.c_char_p)]),
     "srk_set_co_resident_voices": (C.c_int, [_P, C.c_size_t]),
     "srk_state_export": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "srk_state_import": (C.c_int, [_P, _P, C.c_size_t]),

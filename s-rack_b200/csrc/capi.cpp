@@ -527,6 +527,14 @@ int srk_kernel_id(srk_patch* p, size_t n_voices, const char** id) { return guard
   return SRK_OK;
 }); }
 
+int srk_schedule_report(srk_patch* p, const char** report) { return guarded(p, [&]() -> int {
+  if (!p || !report) return SRK_ERR_ARG;
+  int rc = srk::engine_tune_report(p, p->tune_report);
+  if (rc != SRK_OK) return rc;
+  *report = p->tune_report.c_str();
+  return SRK_OK;
+}); }
+
 int srk_set_co_resident_voices(srk_patch* p, size_t n_voices) {
   if (!p) return SRK_ERR_ARG;
   p->co_resident_voices = n_voices;

@@ -19,6 +19,8 @@
 #include "engine.hpp"
 
 #include <cuda_runtime.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cmath>
@@ -81,6 +83,8 @@ int env_int(const char* name, int dflt) {
 
 }  // namespace
 
+static bool tune_allowed();
+
 struct Engine {
   int device = -1;
   cudaStream_t stream = nullptr;
@@ -109,11 +113,19 @@ struct Engine {
   const FusedKernel* fkernel = nullptr;
   std::string fused_note;  // why the interpreter is used instead, if it is
   std::vector<uint32_t> uniform_words;  // parameter word w for voice 0 of the range (read by fused kernels for uniform words)
+  // measured schedule choice (tune_schedule): pending until a render long enough to be worth it; the options of the
+  // fused kernel that won are kept for the regenerations a parameter change can cause
+  bool tune_pending = false, tuned = false, have_forced = false;
+  FusedOptions forced;
+  std::string tune_note;
+  DevBuf d_tune_state, d_tune_rings, d_tune_stems, d_tune_partial, d_tune_prog;
 
   ~Engine() {
     if (device >= 0) {
       cudaSetDevice(device);
-      for (auto* b : {&d_prog, &d_state, &d_state_init, &d_params, &d_rings, &d_partial, &d_stems, &d_mix, &d_waves}) b->release();
+      for (auto* b : {&d_prog, &d_state, &d_state_init, &d_params, &d_rings, &d_partial, &d_stems, &d_mix, &d_waves, &d_tune_state,
+                      &d_tune_rings, &d_tune_stems, &d_tune_partial, &d_tune_prog})
+        b->release();
       if (h_params) cudaFreeHost(h_params);
       for (auto& e : ev)
         if (e) cudaEventDestroy(e);
@@ -283,7 +295,8 @@ static int fused_mode() { return env_int("SRK_FUSED", -1); }
 // Build options of the fused kernel for a launch of n_voices.  With few voice groups per SM a group is cut into
 // stages (one warp each, a tile apart): the render is then bound by dependent-instruction latency and more warps per
 // SM are what hides it (cfg2 @ 4096 voices: 6.7 ms as one warp per group, profiles/r04c).
-static FusedOptions fused_options(const Engine& e, size_t n_voices) {
+static FusedOptions fused_options(const Engine& e, size_t n_voices, const FusedOptions* forced = nullptr) {
+  if (forced) return *forced;  // (a measured choice, tune_schedule)
   FusedOptions o;
   o.group = env_int("SRK_FUSED_GROUP", 4);
   o.min_blocks = env_int("SRK_FUSED_MINB", 4);
@@ -298,8 +311,9 @@ static FusedOptions fused_options(const Engine& e, size_t n_voices) {
   return o;
 }
 // ... and the variant that fits: every group an SM gets must be resident at once (the launch is one wave)
-static int fused_generate_fitting(const srk_patch& patch, const Engine& e, const Program& prog, size_t n_voices, FusedSpec& spec, std::string& why) {
-  FusedOptions o = fused_options(e, n_voices);
+static int fused_generate_fitting(const srk_patch& patch, const Engine& e, const Program& prog, size_t n_voices, FusedSpec& spec, std::string& why,
+                                  const FusedOptions* forced = nullptr) {
+  FusedOptions o = fused_options(e, n_voices, forced);
   const size_t groups = (n_voices + kVoicesPerGroup - 1) / kVoicesPerGroup;
   const size_t n_sm = (size_t)std::max(e.n_sm, 1);
   const size_t per_sm = std::max<size_t>((groups + n_sm - 1) / n_sm, 1);
@@ -470,7 +484,18 @@ static int engine_prepare(srk_patch* patch, size_t n_voices, size_t voice_offset
     // (a sequence-table edit alone rebuilds the program image but keeps the voice state: the state
     // layout depends on the wiring only)
     std::string err;
-    int rc = schedule_program(*patch, e, sv, e.prog, e.blob, e.chunk, e.fused, e.fspec, e.fused_note, err);
+    int rc;
+    if (!rewired && e.tuned && e.fused && e.have_forced) {
+      // a table edit under a measured choice: the same launch shape around the new program image
+      std::string why;
+      rc = compile_program(*patch, 1, e.prog, err);
+      if (rc == SRK_OK && fused_generate_fitting(*patch, e, e.prog, sv, e.fspec, why, &e.forced) != SRK_OK) { rc = SRK_ERR_LIMIT; err = why; }
+      if (rc == SRK_OK) { build_blob(e.prog, e.blob); e.chunk = e.fspec.tile; }
+    } else if (!rewired && e.tuned && !e.fused) {
+      rc = schedule_interpreter(*patch, e, sv, e.prog, e.blob, e.chunk, err);
+    } else {
+      rc = schedule_program(*patch, e, sv, e.prog, e.blob, e.chunk, e.fused, e.fspec, e.fused_note, err);
+    }
     if (rc != SRK_OK) { patch->last_error = err; return rc; }
     e.fkernel = nullptr;
     if (e.fused) {
@@ -492,6 +517,12 @@ static int engine_prepare(srk_patch* patch, size_t n_voices, size_t voice_offset
                                cudaMemcpyHostToDevice, e.stream));
     // the host vectors must outlive the async copies
     SRK_CUDA(cudaStreamSynchronize(e.stream));
+    if (rewired) {
+      e.tune_pending = tune_allowed();
+      e.tuned = false;
+      e.have_forced = false;
+      e.tune_note.clear();
+    }
     e.compiled_epoch = patch->wiring_epoch;
     e.compiled_max_warps = want_warps;
     e.compiled_voices = sv;
@@ -527,7 +558,7 @@ static int engine_prepare(srk_patch* patch, size_t n_voices, size_t voice_offset
       // per-voice (or uniform again) selects another kernel
       FusedSpec spec;
       std::string why;
-      if (fused_generate_fitting(*patch, e, e.prog, sv, spec, why) == SRK_OK && spec.source != e.fspec.source) {
+      if (fused_generate_fitting(*patch, e, e.prog, sv, spec, why, e.have_forced ? &e.forced : nullptr) == SRK_OK && spec.source != e.fspec.source) {
         const FusedKernel* k = nullptr;
         if (fused_kernel(spec, &k, why) == SRK_OK) {
           e.fspec = std::move(spec);
@@ -543,6 +574,369 @@ static int engine_prepare(srk_patch* patch, size_t n_voices, size_t voice_offset
     SRK_CUDA(cudaStreamSynchronize(e.stream));  // staging buffer is reused by the next upload
     e.uploaded_param_epoch = patch->param_epoch;
   }
+  return SRK_OK;
+}
+
+// One way to run the compiled patch for a launch shape: the interpreter's program (pipelined or one warp per group), or
+// the one-warp program plus the fused kernel generated from it.
+struct Schedule {
+  Program prog;
+  std::vector<uint4> blob;
+  int chunk = 0;
+  bool fused = false;
+  FusedSpec fspec;
+  FusedOptions fopt;  // what the fused kernel was generated with, when that was forced
+  bool forced = false;
+  const FusedKernel* fkernel = nullptr;
+  std::string id;     // "fused:<key>" or "interpreter:<warps>x<chunk>"
+};
+struct SchedView {
+  const Program* prog;
+  size_t blob_vec;
+  int chunk;
+  bool fused;
+  const FusedSpec* fspec;
+  const FusedKernel* fkernel;
+};
+static SchedView view_of(const Engine& e) { return SchedView{&e.prog, e.blob.size(), e.chunk, e.fused, &e.fspec, e.fkernel}; }
+static SchedView view_of(const Schedule& s) { return SchedView{&s.prog, s.blob.size(), s.chunk, s.fused, &s.fspec, s.fkernel}; }
+
+struct LaunchIO {
+  uint32_t* state;
+  float* rings;
+  float* stems;    // device, or null
+  float* partial;  // device [G][C][N], or null (no mix)
+  size_t n_voices, voice_offset, n_samples;
+  uint64_t n_abs;
+};
+struct LaunchShape { int K = 0, G = 1, T = 0; size_t smem = 0; };
+
+// One voice-kernel launch of a schedule -- the engine's current one or a tuning candidate -- on `work`.
+static int launch_voice_kernel(srk_patch* patch, Engine& e, const SchedView& v, const void* d_prog, const LaunchIO& io, cudaStream_t work,
+                               LaunchShape& shape) {
+  const Program& prog = *v.prog;
+  const size_t C = prog.channels;
+  const size_t n_voices = io.n_voices, voice_offset = io.voice_offset, n_samples = io.n_samples;
+  const unsigned n_groups = (unsigned)((n_voices + kVoicesPerGroup - 1) / kVoicesPerGroup);
+  int K = 0, G = 1, T = 0;
+  size_t smem = 0;
+  if (v.fused) {
+    // ---- fused kernel: S warps (stages) per voice group, everything in registers; single-stage groups may share a block
+    const int S = std::max(1, v.fspec->stages);
+    const int wpb = S > 1 ? 1 : std::max(1, std::min(env_int("SRK_FUSED_WPB", 1), kFusedMaxThreads / 32));  // groups per block
+    SrkFusedArgs args{};
+    args.state = (unsigned*)io.state;
+    args.params = (const unsigned*)e.d_params.p;
+    args.rings = io.rings;
+    args.stems = io.stems;
+    args.partial = io.partial;
+    args.waves = (const float*)e.d_waves.p;
+    args.tables = reinterpret_cast<const int*>(reinterpret_cast<const unsigned char*>(d_prog) + blob_table_offset(prog));
+    args.V = (unsigned)n_voices;
+    args.voice_offset = (unsigned)voice_offset;
+    args.n_samples = (unsigned)n_samples;
+    args.C = (unsigned)C;
+    args.B = std::max<uint32_t>(prog.ring_len, 1);
+    args.ring_phase = (unsigned)(io.n_abs % args.B);
+    args.n_abs = (unsigned)io.n_abs;
+    args.seed_lo = (unsigned)patch->seed;
+    args.seed_hi = (unsigned)(patch->seed >> 32);
+    SrkTensorMap tmap{};
+    args.use_tma = 0;
+    if (io.stems && n_voices % 4 == 0 && env_int("SRK_FUSED_TMA", 1)) {
+      std::string why;
+      if (fused_stems_map(&tmap, io.stems, C, n_samples, n_voices, (unsigned)v.fspec->tile, why) == SRK_OK) args.use_tma = 1;
+    }
+    for (size_t w = 0; w < e.uniform_words.size() && w < SRK_FUSED_MAX_UNIFORM; ++w) args.u[w] = e.uniform_words[w];
+    smem = v.fspec->smem_per_group * wpb;
+    FusedKernel* fk = const_cast<FusedKernel*>(v.fkernel);
+    if (smem > fk->max_smem_set) {
+      SRK_CUDA(cudaFuncSetAttribute((const void*)fk->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SRK_CUDA(cudaFuncSetAttribute((const void*)fk->kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      fk->max_smem_set = smem;
+    }
+    void* kargs[] = {&args, &tmap};
+    const unsigned grid = (n_groups + wpb - 1) / wpb;
+    SRK_CUDA(cudaLaunchKernel((const void*)fk->kernel, dim3(grid), dim3(32u * S * wpb), kargs, smem, work));
+    K = v.fspec->tile;
+    G = wpb;
+    T = 32 * S;
+  } else {
+  K = chunk_for_length(prog, v.chunk, n_samples);  // <= the chunk that fitted
+  T = (int)prog.n_warps * 32;
+  G = prog.n_warps == 1 ? choose_solo_groups(e, prog, v.blob_vec, K, sched_voices(*patch, n_voices)) : 1;
+  smem = smem_bytes_for(prog, v.blob_vec, K, G);
+  const unsigned grid = (n_groups + G - 1) / G;
+
+  RenderArgs a{};
+  a.blob = (const uint4*)d_prog;
+  a.state = io.state;
+  a.params = (const uint32_t*)e.d_params.p;
+  a.rings = io.rings;
+  a.stems = io.stems;
+  a.partial = io.partial;
+  a.waves = (const float*)e.d_waves.p;
+  a.blob_vec = (uint32_t)v.blob_vec;
+  a.table_off = (uint32_t)blob_table_offset(prog);
+  a.n_instr = (uint32_t)prog.code.size();
+  a.n_wires = (uint32_t)prog.wires.size();
+  a.n_warps = prog.n_warps;
+  a.n_stages = prog.n_stages;
+  a.n_tiles = prog.n_tiles;
+  a.V = (uint32_t)n_voices;
+  a.voice_offset = (uint32_t)voice_offset;
+  a.n_samples = (uint32_t)n_samples;
+  a.S = (uint32_t)prog.state_init.size();
+  a.P = (uint32_t)prog.param_src.size();
+  a.C = (uint32_t)C;
+  a.B = std::max<uint32_t>(prog.ring_len, 1);
+  a.K = (uint32_t)K;
+  a.log2K = 0;
+  while ((1u << a.log2K) < a.K) ++a.log2K;
+  a.ring_phase = (uint32_t)(io.n_abs % a.B);
+  a.seed_lo = (uint32_t)patch->seed;
+  a.seed_hi = (uint32_t)(patch->seed >> 32);
+  a.solo_op_barrier = G > 1 && env_int("SRK_SOLO_OP_BARRIER", 0) ? 1u : 0u;
+
+  bool beyond_baseline = false;  // sequencers / sample player: the larger one-warp image
+  for (const Instr& ins : prog.code) beyond_baseline |= ins.op == OP_GRIDSEQ || ins.op == OP_PATSEQ || ins.op == OP_SAMPLE;
+  SRK_CUDA(prog.n_warps > 1 ? launch_voices_pipelined(a, grid, (unsigned)T, smem, work)
+           : beyond_baseline ? launch_voices_solo_full(a, grid, 32u * G, smem, work)
+                             : launch_voices_solo(a, grid, 32u * G, smem, work));
+  }
+  SRK_CUDA(cudaGetLastError());
+  shape.K = K; shape.G = G; shape.T = T; shape.smem = smem;
+  return SRK_OK;
+}
+
+// ----------------------------------------------------------------------------
+// Measured schedule choice.  schedule_program() picks a launch shape from a cost model (instructions per sample, voice
+// groups per SM); which shape is actually fastest also depends on things the model does not see -- how well ptxas
+// interleaves a stage's straight-line groups, instruction-cache footprint, the stems traffic.  So the first render of
+// a schedule that is long enough to be worth it runs the plausible alternatives for a few thousand samples each on a
+// scratch copy of the voice state, timed with CUDA events on the render stream, and keeps the fastest.  Every
+// candidate computes the same bits (tests/test_gpu_parity.py::test_measured_schedule_choice_keeps_the_bits), so the
+// choice is invisible in the output.  The decision is cached next to the cubins (kernel_cache/<key>.tune).
+// Off with SRK_TUNE=0 or whenever a schedule knob is forced through the environment.
+// ----------------------------------------------------------------------------
+constexpr size_t kTuneMinSamples = 16384;  // shorter renders keep the cost model's choice (tuning would dominate them)
+
+static bool tune_allowed() {
+  if (!env_int("SRK_TUNE", 1)) return false;
+  for (const char* k : {"SRK_FUSED", "SRK_WARPS", "SRK_STEP", "SRK_FUSED_STAGES", "SRK_FUSED_GROUP", "SRK_FUSED_TILE_ROWS", "SRK_SOLO_GROUPS",
+                        "SRK_FUSED_MINB", "SRK_FUSED_WPB", "SRK_SOLO_OP_BARRIER"}) {
+    const char* v = std::getenv(k);
+    if (v && *v) return false;
+  }
+  return true;
+}
+
+static std::string interp_id(const Program& prog, int chunk) {
+  return "interpreter:" + std::to_string(prog.n_warps) + "x" + std::to_string(chunk);
+}
+
+// The alternatives worth measuring next to the schedule `cur` the cost model picked for `sv` scheduling voices.
+// cur itself is out[0].  Needs no device.
+static void schedule_candidates(const srk_patch& patch, const Engine& lim, size_t sv, Schedule cur, std::vector<Schedule>& out) {
+  const size_t groups = (sv + kVoicesPerGroup - 1) / kVoicesPerGroup;
+  const size_t n_sm = (size_t)std::max(lim.n_sm, 1);
+  const size_t per_sm = std::max<size_t>((groups + n_sm - 1) / n_sm, 1);
+  const size_t budget = (size_t)lim.smem_sm - 1024 * std::min<size_t>(per_sm, 32);
+  cur.id = cur.fused ? "fused:" + fused_key(cur.fspec) : interp_id(cur.prog, cur.chunk);
+  const bool cur_fused = cur.fused;
+  const int S0 = cur.fused ? cur.fspec.stages : 0, g0 = cur.fused ? cur.fspec.group : 4, t0 = cur.fused ? cur.fspec.tile : 32;
+  out.clear();
+  out.push_back(std::move(cur));
+  auto add_fused = [&](int stages, int group, int tile) {
+    Program one;
+    std::string err, why;
+    if (compile_program(patch, 1, one, err) != SRK_OK) return;
+    FusedOptions o;
+    o.group = group; o.min_blocks = 4; o.stages = stages; o.exact_stages = true; o.tile = tile;
+    FusedSpec spec;
+    if (fused_generate(patch, one, o, spec, why) != SRK_OK || spec.stages != stages || spec.group != group) return;
+    if (spec.stages > 1 && spec.smem_per_group * per_sm > budget) return;
+    for (const Schedule& c : out)
+      if (c.fused && c.fspec.source == spec.source) return;
+    Schedule s;
+    s.prog = std::move(one);
+    build_blob(s.prog, s.blob);
+    s.chunk = spec.tile;
+    s.fused = true;
+    s.fopt = o;
+    s.forced = true;
+    s.id = "fused:" + fused_key(spec);
+    s.fspec = std::move(spec);
+    out.push_back(std::move(s));
+  };
+  if (cur_fused) {
+    add_fused(S0, g0 == 8 ? 4 : 8, t0);                      // samples per straight-line group: 4 or 8
+    if (S0 > 1 && S0 < 8) { add_fused(S0 + 1, 4, t0); add_fused(S0 + 1, 8, t0); }  // one more pipeline stage
+    if (per_sm <= 2) {                                       // the interpreter's pipeline (splits single modules over warps)
+      Schedule s;
+      std::string err;
+      if (schedule_interpreter(patch, lim, sv, s.prog, s.blob, s.chunk, err) == SRK_OK && s.prog.n_warps > 1) {
+        s.id = interp_id(s.prog, s.chunk);
+        out.push_back(std::move(s));
+      }
+    }
+  } else {
+    Program one;
+    std::string err, why;
+    FusedSpec spec;
+    if (fused_mode() != 0 && compile_program(patch, 1, one, err) == SRK_OK && fused_generate_fitting(patch, lim, one, sv, spec, why) == SRK_OK) {
+      add_fused(spec.stages, 4, spec.tile);
+      add_fused(spec.stages, 8, spec.tile);
+    }
+  }
+}
+
+static void adopt_schedule(Engine& e, Schedule&& s) {
+  e.prog = std::move(s.prog);
+  e.blob = std::move(s.blob);
+  e.chunk = s.chunk;
+  e.fused = s.fused;
+  e.fspec = std::move(s.fspec);
+  e.fkernel = s.fkernel;
+  e.have_forced = s.fused && s.forced;
+  e.forced = s.fopt;
+}
+
+static int tune_schedule(srk_patch* patch, Engine& e, size_t n_voices, size_t voice_offset, bool want_stems, bool want_mix) {
+  e.tune_pending = false;
+  const size_t sv = sched_voices(*patch, n_voices);
+  Schedule cur;
+  cur.prog = e.prog; cur.blob = e.blob; cur.chunk = e.chunk; cur.fused = e.fused; cur.fspec = e.fspec; cur.fkernel = e.fkernel;
+  std::vector<Schedule> cand;
+  schedule_candidates(*patch, e, sv, std::move(cur), cand);
+  // candidates must share the state and parameter layout of the current program (they do: both follow the plan)
+  for (size_t i = cand.size(); i-- > 1;) {
+    const Program& a = cand[0].prog;
+    const Program& b = cand[i].prog;
+    bool same = a.state_init == b.state_init && a.param_src.size() == b.param_src.size() && a.n_rings == b.n_rings && a.ring_len == b.ring_len;
+    for (size_t w = 0; same && w < a.param_src.size(); ++w)
+      same = a.param_src[w].module == b.param_src[w].module && a.param_src[w].pid == b.param_src[w].pid;
+    if (!same) cand.erase(cand.begin() + (long)i);
+  }
+  for (size_t i = cand.size(); i-- > 1;) {  // load (compile) the fused kernels; one that does not build is no candidate
+    std::string why;
+    if (cand[i].fused && fused_kernel(cand[i].fspec, &cand[i].fkernel, why) != SRK_OK) cand.erase(cand.begin() + (long)i);
+  }
+  if (cand.size() < 2) { e.tuned = true; e.tune_note = "no alternative schedule"; return SRK_OK; }
+
+  // ---- a decision made earlier for exactly these candidates on this kind of launch?
+  std::string all;
+  for (const Schedule& c : cand) { all += c.id; all += '\n'; }
+  all += "V=" + std::to_string(sv) + " stems=" + std::to_string((int)want_stems) + " mix=" + std::to_string((int)want_mix) + " sm=" + std::to_string(e.n_sm);
+  const std::string path = fused_cache_dir() + "/" + fused_hash(all, "tune-v1") + ".tune";
+  size_t best = cand.size();
+  const char* nocache = std::getenv("SRK_KERNEL_CACHE_OFF");
+  if (!(nocache && nocache[0] == '1')) {
+    if (FILE* f = std::fopen(path.c_str(), "r")) {
+      char line[256] = {0};
+      if (std::fgets(line, sizeof line, f)) {
+        std::string id(line);
+        while (!id.empty() && (id.back() == '\n' || id.back() == '\r')) id.pop_back();
+        for (size_t i = 0; i < cand.size(); ++i)
+          if (cand[i].id == id) best = i;
+      }
+      std::fclose(f);
+    }
+  }
+  std::string report;
+  const int pick = env_int("SRK_TUNE_PICK", -1);  // tests: take candidate #pick instead of measuring
+  if (pick >= 0) {
+    best = std::min<size_t>((size_t)pick, cand.size() - 1);
+    e.tune_note = "picked " + cand[best].id + " (SRK_TUNE_PICK) of " + std::to_string(cand.size()) + " candidates";
+    if (best != 0) {
+      adopt_schedule(e, std::move(cand[best]));
+      SRK_CUDA(e.d_prog.ensure(e.blob.size() * sizeof(uint4)));
+      SRK_CUDA(cudaMemcpyAsync(e.d_prog.p, e.blob.data(), e.blob.size() * sizeof(uint4), cudaMemcpyHostToDevice, e.stream));
+      SRK_CUDA(cudaStreamSynchronize(e.stream));
+    }
+    e.tuned = true;
+    return SRK_OK;
+  }
+  if (best == cand.size()) {
+    // ---- measure: T(2K) - T(K) per candidate (launch overhead, state load/store and pipeline fill cancel)
+    const Program& p0 = cand[0].prog;
+    const size_t C = p0.channels;
+    size_t K1 = 2048;
+    if (want_stems)
+      while (K1 > 256 && C * 2 * K1 * n_voices * sizeof(float) > (256u << 20)) K1 /= 2;
+    if (p0.n_rings) K1 = std::max<size_t>(K1, std::min<size_t>(4 * p0.ring_len, 8192));  // past the first wrap of a feedback ring
+    const size_t K2 = 2 * K1;
+    const unsigned n_groups = (unsigned)((n_voices + kVoicesPerGroup - 1) / kVoicesPerGroup);
+    const size_t state_bytes = std::max<size_t>(p0.state_init.size() * n_voices, 1) * sizeof(uint32_t);
+    const size_t ring_bytes = std::max<size_t>((size_t)p0.n_rings * p0.ring_len * n_voices, 1) * sizeof(float);
+    SRK_CUDA(e.d_tune_state.ensure(state_bytes));
+    SRK_CUDA(e.d_tune_rings.ensure(ring_bytes));
+    if (want_stems) SRK_CUDA(e.d_tune_stems.ensure(C * K2 * n_voices * sizeof(float)));
+    if (want_mix) SRK_CUDA(e.d_tune_partial.ensure((size_t)n_groups * C * K2 * sizeof(float)));
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    SRK_CUDA(cudaEventCreate(&ev0));
+    SRK_CUDA(cudaEventCreate(&ev1));
+    double best_ms = 0.0;
+    int rc = SRK_OK;
+    for (size_t i = 0; i < cand.size() && rc == SRK_OK; ++i) {
+      const Schedule& c = cand[i];
+      if (e.d_tune_prog.ensure(c.blob.size() * sizeof(uint4)) != cudaSuccess ||
+          cudaMemcpyAsync(e.d_tune_prog.p, c.blob.data(), c.blob.size() * sizeof(uint4), cudaMemcpyHostToDevice, e.stream) != cudaSuccess) { rc = SRK_ERR_CUDA; break; }
+      float t[3] = {0, 0, 0};
+      const size_t len[3] = {K1, K1, K2};  // (the first launch also pays for loading the kernel image)
+      for (int k = 0; k < 3 && rc == SRK_OK; ++k) {
+        cudaMemcpyAsync(e.d_tune_state.p, e.d_state.p, state_bytes, cudaMemcpyDeviceToDevice, e.stream);
+        cudaMemcpyAsync(e.d_tune_rings.p, e.d_rings.p, ring_bytes, cudaMemcpyDeviceToDevice, e.stream);
+        LaunchIO io{};
+        io.state = (uint32_t*)e.d_tune_state.p;
+        io.rings = (float*)e.d_tune_rings.p;
+        io.stems = want_stems ? (float*)e.d_tune_stems.p : nullptr;
+        io.partial = want_mix ? (float*)e.d_tune_partial.p : nullptr;
+        io.n_voices = n_voices;
+        io.voice_offset = voice_offset;
+        io.n_samples = len[k];
+        io.n_abs = e.n_abs;
+        LaunchShape shape;
+        cudaEventRecord(ev0, e.stream);
+        rc = launch_voice_kernel(patch, e, view_of(c), e.d_tune_prog.p, io, e.stream, shape);
+        cudaEventRecord(ev1, e.stream);
+        if (rc == SRK_OK && cudaEventSynchronize(ev1) != cudaSuccess) rc = SRK_ERR_CUDA;
+        if (rc == SRK_OK) cudaEventElapsedTime(&t[k], ev0, ev1);
+        ++e.launches;
+      }
+      const double slope = (double)t[2] - (double)t[1];  // ms per K1 samples in steady state
+      char buf[160];
+      std::snprintf(buf, sizeof buf, "%s%s %.4f", i ? ", " : "", c.id.c_str(), slope);
+      report += buf;
+      if (rc == SRK_OK && slope > 0.0 && (best == cand.size() || slope < best_ms)) { best = i; best_ms = slope; }
+    }
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    for (DevBuf* b : {&e.d_tune_state, &e.d_tune_rings, &e.d_tune_stems, &e.d_tune_partial, &e.d_tune_prog}) b->release();
+    if (rc != SRK_OK) return rc;
+    if (best == cand.size()) best = 0;
+    report = "measured ms per " + std::to_string(K1) + " samples: " + report;
+    if (!(nocache && nocache[0] == '1')) {
+      mkdir(fused_cache_dir().c_str(), 0755);
+      const std::string tmp = path + ".tmp." + std::to_string((long)getpid());
+      if (FILE* f = std::fopen(tmp.c_str(), "w")) {
+        std::fprintf(f, "%s\n%s\n%s\n", cand[best].id.c_str(), report.c_str(), all.c_str());
+        std::fclose(f);
+        if (std::rename(tmp.c_str(), path.c_str()) != 0) std::remove(tmp.c_str());
+      }
+    }
+  } else {
+    report = "decision from " + path;
+  }
+  e.tune_note = "chose " + cand[best].id + "; " + report;
+  if (env_int("SRK_DEBUG", 0)) std::fprintf(stderr, "[srk] tune: %s\n", e.tune_note.c_str());
+  if (best != 0) {
+    adopt_schedule(e, std::move(cand[best]));
+    SRK_CUDA(e.d_prog.ensure(e.blob.size() * sizeof(uint4)));
+    SRK_CUDA(cudaMemcpyAsync(e.d_prog.p, e.blob.data(), e.blob.size() * sizeof(uint4), cudaMemcpyHostToDevice, e.stream));
+    SRK_CUDA(cudaStreamSynchronize(e.stream));
+  }
+  e.tuned = true;
   return SRK_OK;
 }
 
@@ -582,6 +976,11 @@ int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t
     return SRK_OK;
   }
 
+  if (e.tune_pending && n_samples >= kTuneMinSamples) {
+    rc = tune_schedule(patch, e, n_voices, voice_offset, stems != nullptr, mix != nullptr);
+    if (rc != SRK_OK) return rc;
+    SRK_CUDA(cudaEventRecord(e.ev[0], work));  // the measurement is not part of this call's device time
+  }
   const Program& prog = e.prog;
   const size_t C = prog.channels;
   const unsigned n_groups = (unsigned)((n_voices + kVoicesPerGroup - 1) / kVoicesPerGroup);
@@ -599,94 +998,21 @@ int engine_render(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t
     SRK_CUDA(e.d_partial.ensure((size_t)n_groups * C * n_samples * sizeof(float)));
   }
 
-  int K = 0, G = 1, T = 0;
-  size_t smem = 0;
-  if (e.fused) {
-    // ---- fused kernel: S warps (stages) per voice group, everything in registers; single-stage groups may share a block
-    const int S = std::max(1, e.fspec.stages);
-    const int wpb = S > 1 ? 1 : std::max(1, std::min(env_int("SRK_FUSED_WPB", 1), kFusedMaxThreads / 32));  // groups per block
-    SrkFusedArgs args{};
-    args.state = (unsigned*)e.d_state.p;
-    args.params = (const unsigned*)e.d_params.p;
-    args.rings = (float*)e.d_rings.p;
-    args.stems = d_stems;
-    args.partial = mix ? (float*)e.d_partial.p : nullptr;
-    args.waves = (const float*)e.d_waves.p;
-    args.tables = reinterpret_cast<const int*>(reinterpret_cast<const unsigned char*>(e.d_prog.p) + blob_table_offset(prog));
-    args.V = (unsigned)n_voices;
-    args.voice_offset = (unsigned)voice_offset;
-    args.n_samples = (unsigned)n_samples;
-    args.C = (unsigned)C;
-    args.B = std::max<uint32_t>(prog.ring_len, 1);
-    args.ring_phase = (unsigned)(e.n_abs % args.B);
-    args.n_abs = (unsigned)e.n_abs;
-    args.seed_lo = (unsigned)patch->seed;
-    args.seed_hi = (unsigned)(patch->seed >> 32);
-    SrkTensorMap tmap{};
-    args.use_tma = 0;
-    if (d_stems && n_voices % 4 == 0 && env_int("SRK_FUSED_TMA", 1)) {
-      std::string why;
-      if (fused_stems_map(&tmap, d_stems, C, n_samples, n_voices, (unsigned)e.fspec.tile, why) == SRK_OK) args.use_tma = 1;
-    }
-    for (size_t w = 0; w < e.uniform_words.size() && w < SRK_FUSED_MAX_UNIFORM; ++w) args.u[w] = e.uniform_words[w];
-    smem = e.fspec.smem_per_group * wpb;
-    FusedKernel* fk = const_cast<FusedKernel*>(e.fkernel);
-    if (smem > fk->max_smem_set) {
-      SRK_CUDA(cudaFuncSetAttribute((const void*)fk->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      SRK_CUDA(cudaFuncSetAttribute((const void*)fk->kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-      fk->max_smem_set = smem;
-    }
-    void* kargs[] = {&args, &tmap};
-    const unsigned grid = (n_groups + wpb - 1) / wpb;
-    SRK_CUDA(cudaEventRecord(e.ev[1], work));
-    SRK_CUDA(cudaLaunchKernel((const void*)fk->kernel, dim3(grid), dim3(32u * S * wpb), kargs, smem, work));
-    K = e.fspec.tile;
-    G = wpb;
-    T = 32 * S;
-  } else {
-  K = chunk_for_length(prog, e.chunk, n_samples);  // <= e.chunk, which fitted
-  T = (int)prog.n_warps * 32;
-  G = prog.n_warps == 1 ? choose_solo_groups(e, prog, e.blob.size(), K, sched_voices(*patch, n_voices)) : 1;
-  smem = smem_bytes_for(prog, e.blob.size(), K, G);
-  const unsigned grid = (n_groups + G - 1) / G;
-
-  RenderArgs a{};
-  a.blob = (const uint4*)e.d_prog.p;
-  a.state = (uint32_t*)e.d_state.p;
-  a.params = (const uint32_t*)e.d_params.p;
-  a.rings = (float*)e.d_rings.p;
-  a.stems = d_stems;
-  a.partial = mix ? (float*)e.d_partial.p : nullptr;
-  a.waves = (const float*)e.d_waves.p;
-  a.blob_vec = (uint32_t)e.blob.size();
-  a.table_off = (uint32_t)blob_table_offset(prog);
-  a.n_instr = (uint32_t)prog.code.size();
-  a.n_wires = (uint32_t)prog.wires.size();
-  a.n_warps = prog.n_warps;
-  a.n_stages = prog.n_stages;
-  a.n_tiles = prog.n_tiles;
-  a.V = (uint32_t)n_voices;
-  a.voice_offset = (uint32_t)voice_offset;
-  a.n_samples = (uint32_t)n_samples;
-  a.S = (uint32_t)prog.state_init.size();
-  a.P = (uint32_t)prog.param_src.size();
-  a.C = (uint32_t)C;
-  a.B = std::max<uint32_t>(prog.ring_len, 1);
-  a.K = (uint32_t)K;
-  a.log2K = 0;
-  while ((1u << a.log2K) < a.K) ++a.log2K;
-  a.ring_phase = (uint32_t)(e.n_abs % a.B);
-  a.seed_lo = (uint32_t)patch->seed;
-  a.seed_hi = (uint32_t)(patch->seed >> 32);
-  a.solo_op_barrier = G > 1 && env_int("SRK_SOLO_OP_BARRIER", 0) ? 1u : 0u;
-
+  LaunchIO io{};
+  io.state = (uint32_t*)e.d_state.p;
+  io.rings = (float*)e.d_rings.p;
+  io.stems = d_stems;
+  io.partial = mix ? (float*)e.d_partial.p : nullptr;
+  io.n_voices = n_voices;
+  io.voice_offset = voice_offset;
+  io.n_samples = n_samples;
+  io.n_abs = e.n_abs;
+  LaunchShape shape;
   SRK_CUDA(cudaEventRecord(e.ev[1], work));
-  bool beyond_baseline = false;  // sequencers / sample player: the larger one-warp image
-  for (const Instr& ins : prog.code) beyond_baseline |= ins.op == OP_GRIDSEQ || ins.op == OP_PATSEQ || ins.op == OP_SAMPLE;
-  SRK_CUDA(prog.n_warps > 1 ? launch_voices_pipelined(a, grid, (unsigned)T, smem, work)
-           : beyond_baseline ? launch_voices_solo_full(a, grid, 32u * G, smem, work)
-                             : launch_voices_solo(a, grid, 32u * G, smem, work));
-  }
+  rc = launch_voice_kernel(patch, e, view_of(e), e.d_prog.p, io, work, shape);
+  if (rc != SRK_OK) return rc;
+  const int K = shape.K, G = shape.G, T = shape.T;
+  const size_t smem = shape.smem;
   SRK_CUDA(cudaGetLastError());
   ++e.launches;
   SRK_CUDA(cudaEventRecord(e.ev[2], work));
@@ -774,14 +1100,27 @@ static int probe_program(srk_patch* patch, size_t n_voices, Program& prog, std::
   return SRK_OK;
 }
 
+// The engine holds the schedule (possibly a measured choice) a render of n_voices uses right now.
+static bool engine_has_schedule_for(const srk_patch* patch, size_t n_voices) {
+  const Engine* e = patch->engine.get();
+  return e && patch->planned && e->compiled_epoch == patch->wiring_epoch && e->compiled_table_epoch == patch->table_epoch &&
+         e->compiled_voices == sched_voices(*patch, n_voices) && (!e->fused || e->fkernel);
+}
+
 int engine_program_info(srk_patch* patch, size_t n_voices, srk_program_info* out) {
   Program prog;
   std::vector<uint4> blob;
   int K = 0, G = 1;
   bool fused = false;
   FusedSpec spec;
-  int rc = probe_program(patch, n_voices, prog, blob, K, &G, &fused, &spec);
-  if (rc != SRK_OK) return rc;
+  if (engine_has_schedule_for(patch, n_voices)) {
+    const Engine& e = *patch->engine;
+    prog = e.prog; blob = e.blob; K = e.chunk; fused = e.fused; spec = e.fspec;
+    G = prog.n_warps == 1 && !fused ? choose_solo_groups(e, prog, blob.size(), K, sched_voices(*patch, n_voices)) : 1;
+  } else {
+    int rc = probe_program(patch, n_voices, prog, blob, K, &G, &fused, &spec);
+    if (rc != SRK_OK) return rc;
+  }
   std::memset(out, 0, sizeof *out);
   out->n_instr = (uint32_t)prog.code.size();
   out->step_samples = (uint32_t)K;
@@ -837,13 +1176,31 @@ int engine_precompile(srk_patch* patch, size_t n_voices, int* compiled) {
   FusedSpec spec;
   if (compiled) *compiled = 0;
   int rc = probe_program(patch, n_voices, prog, blob, K, nullptr, &fused, &spec);
-  if (rc != SRK_OK || !fused) return rc;
-  std::vector<char> cubin;
-  std::string key, err;
-  bool from_disk = false;
-  rc = fused_cubin(spec, cubin, key, &from_disk, nullptr, err);
-  if (rc != SRK_OK) { patch->last_error = err; return rc; }
-  if (compiled) *compiled = from_disk ? 0 : 1;
+  if (rc != SRK_OK) return rc;
+  // the schedule the cost model picks and the alternatives a long render would measure against it (tune_schedule)
+  Engine probe;
+  probe.smem_optin = patch->engine ? patch->engine->smem_optin : 227 * 1024;
+  probe.n_sm = patch->engine ? patch->engine->n_sm : 148;
+  probe.smem_sm = patch->engine ? patch->engine->smem_sm : 228 * 1024;
+  Schedule cur;
+  cur.prog = std::move(prog); cur.blob = std::move(blob); cur.chunk = K; cur.fused = fused; cur.fspec = std::move(spec);
+  std::vector<Schedule> cand;
+  if (tune_allowed()) schedule_candidates(*patch, probe, sched_voices(*patch, n_voices), std::move(cur), cand);
+  else cand.push_back(std::move(cur));
+  for (const Schedule& c : cand) {
+    if (!c.fused) continue;
+    std::vector<char> cubin;
+    std::string key, err;
+    bool from_disk = false;
+    rc = fused_cubin(c.fspec, cubin, key, &from_disk, nullptr, err);
+    if (rc != SRK_OK) { patch->last_error = err; return rc; }
+    if (compiled && !from_disk) ++*compiled;
+  }
+  return SRK_OK;
+}
+
+int engine_tune_report(srk_patch* patch, std::string& report) {
+  report = patch->engine ? patch->engine->tune_note : std::string();
   return SRK_OK;
 }
 
@@ -859,8 +1216,13 @@ int engine_kernel_id(srk_patch* patch, size_t n_voices, std::string& id) {
   int K = 0;
   bool fused = false;
   FusedSpec spec;
-  int rc = probe_program(patch, n_voices, prog, blob, K, nullptr, &fused, &spec);
-  if (rc != SRK_OK) return rc;
+  if (engine_has_schedule_for(patch, n_voices)) {  // what the engine launches right now (a measured choice included)
+    const Engine& e = *patch->engine;
+    prog = e.prog; fused = e.fused; spec = e.fspec;
+  } else {
+    int rc = probe_program(patch, n_voices, prog, blob, K, nullptr, &fused, &spec);
+    if (rc != SRK_OK) return rc;
+  }
   if (fused) { id = "fused:" + fused_key(spec); return SRK_OK; }
   bool beyond_baseline = false;
   for (const Instr& ins : prog.code) beyond_baseline |= ins.op == OP_GRIDSEQ || ins.op == OP_PATSEQ || ins.op == OP_SAMPLE;

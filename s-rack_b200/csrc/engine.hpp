@@ -20,6 +20,7 @@ uint64_t engine_launches(const srk_patch* patch);
 int engine_program_info(srk_patch* patch, size_t n_voices, srk_program_info* out);
 int engine_fused_source(srk_patch* patch, size_t n_voices, std::string& source);
 int engine_precompile(srk_patch* patch, size_t n_voices, int* compiled);
+int engine_tune_report(srk_patch* patch, std::string& report);
 int engine_kernel_id(srk_patch* patch, size_t n_voices, std::string& id);
 int engine_state_export(srk_patch* patch, const void** blob, size_t* n_bytes);
 int engine_state_import(srk_patch* patch, const void* blob, size_t n_bytes);

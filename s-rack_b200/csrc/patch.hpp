@@ -76,6 +76,7 @@ struct srk_patch {
   std::vector<unsigned char> saved;  // last srk_patch_save_srk() image
   std::string fused_source;          // last srk_fused_source() text
   std::string kernel_id;             // last srk_kernel_id() text
+  std::string tune_report;           // last srk_schedule_report() text
   std::vector<unsigned char> saved_state;  // last srk_state_export() blob
   size_t co_resident_voices = 0;     // srk_set_co_resident_voices(): voices other patches render on this device concurrently
   std::unique_ptr<srk::Engine, void (*)(srk::Engine*)> engine{nullptr, nullptr};

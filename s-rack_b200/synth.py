@@ -318,15 +318,22 @@ class Patch:
         return (src.value or b"").decode()
 
     def precompile(self, n_voices=0):
-        """Compile that kernel into the on-disk cubin cache (NVRTC, no GPU needed) -> True when it compiled now."""
+        """Compile the fused kernels a render of n_voices can launch -- the cost model's choice and the alternatives a long
+        render measures against it -- into the on-disk cubin cache (NVRTC, no GPU needed) -> how many were compiled now."""
         done = C.c_int()
         self._check(lib.srk_precompile(self._h, n_voices, C.byref(done)))
-        return bool(done.value)
+        return int(done.value)
 
     def kernel_id(self, n_voices=0):
         """Identity of the kernel image a render of n_voices would launch (profiles are stamped with it)."""
         s = C.c_char_p()
         self._check(lib.srk_kernel_id(self._h, n_voices, C.byref(s)))
+        return (s.value or b"").decode()
+
+    def schedule_report(self):
+        """How the launch shape in use was chosen: '' or the measured candidates and the winner."""
+        s = C.c_char_p()
+        self._check(lib.srk_schedule_report(self._h, C.byref(s)))
         return (s.value or b"").decode()
 
     def set_co_resident_voices(self, n_voices):

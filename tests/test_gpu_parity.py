@@ -776,3 +776,49 @@ def test_cv_driven_oscillators_and_non_linear_are_bit_exact(srk, orc, cuda_devic
     assert len(gp.plan_cuts()) == 1
     assert np.abs(o[0]).max() > 0.5 and np.abs(o[1]).max() > 0.5 and np.isfinite(o).all()
     assert_parity(g, o, exact=True, what="CV-driven saw + Non-Linear")
+
+
+@pytest.mark.parametrize("name,B,V", [("cfg2", 1024, 200), ("cfg4", 1024, 96), ("cfg3b", 256, 64), ("sampler", 1024, 70), ("cfg2", 1024, 20000)])
+def test_measured_schedule_choice_keeps_the_bits(srk, orc, cuda_device, monkeypatch, schedule, name, B, V):
+    """The first long render of a schedule measures the alternative launch shapes and keeps the fastest
+    (engine.cu tune_schedule).  Whatever it keeps -- every candidate is forced in turn here -- the samples are the ones
+    the cost model's choice gives, the voice state carries over into the next call, and srk_get_program_info /
+    srk_kernel_id describe the shape in use."""
+    if schedule != "auto":
+        pytest.skip("a forced schedule knob turns the measurement off")
+    builders = dict(srk.patches.CONFIGS)
+    builder = builders[name][0] if name in builders else getattr(srk.patches, name)
+    N1, N2 = 16384, 3000
+
+    def render(env):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        p = srk.Patch(srk.AudioConfig(48000, B, 2))
+        builder(p, V)
+        p.plan()
+        a = p.render(V, N1, stems=True)
+        b = p.render(V, N2, stems=True)   # (sampler: the table epoch moved after the first call: the kept shape is rebuilt)
+        out = (np.concatenate([a[0], b[0]], axis=1), np.concatenate([a[1], b[1]], axis=1), p.schedule_report(), p.kernel_id(V), p.program_info(V))
+        for k in env:
+            monkeypatch.delenv(k)
+        return out
+
+    base_st, base_mix, rep0, _, _ = render({"SRK_TUNE": "0"})
+    assert rep0 == ""
+    ids = set()
+    for pick in range(6):
+        st, mix, rep, kid, info = render({"SRK_TUNE_PICK": str(pick)})
+        assert "picked" in rep or "no alternative" in rep
+        assert (st.view(np.uint32) == base_st.view(np.uint32)).all(), (pick, rep)
+        assert (mix.view(np.uint32) == base_mix.view(np.uint32)).all(), (pick, rep)
+        assert (kid.startswith("fused:") and info["fused"] == 1) or (kid.startswith("interpreter:") and info["fused"] == 0)
+        if "picked" in rep:
+            assert kid.split(":")[1][:12] in rep or kid.startswith("interpreter:")
+        ids.add(kid)
+    if V <= 200:
+        assert len(ids) >= 3  # several launch shapes were really exercised
+    # and the real thing: measure (no cached decision), then the same decision from the cache
+    st, mix, rep, kid, _ = render({"SRK_KERNEL_CACHE_OFF": "0", "SRK_KERNEL_CACHE": str(os.path.join(GOLDEN, "..", "..", "gpurun_out", "tune_test_cache_%s_%d" % (name, V)))})
+    assert (st.view(np.uint32) == base_st.view(np.uint32)).all() and ("measured" in rep or "decision from" in rep)
+    st2, _, rep2, kid2, _ = render({"SRK_KERNEL_CACHE": str(os.path.join(GOLDEN, "..", "..", "gpurun_out", "tune_test_cache_%s_%d" % (name, V)))})
+    assert "decision from" in rep2 and kid2 == kid and (st2.view(np.uint32) == base_st.view(np.uint32)).all()
