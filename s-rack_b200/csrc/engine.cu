@@ -694,6 +694,7 @@ static int launch_voice_kernel(srk_patch* patch, Engine& e, const SchedView& v, 
   a.log2K = 0;
   while ((1u << a.log2K) < a.K) ++a.log2K;
   a.ring_phase = (uint32_t)(io.n_abs % a.B);
+  a.n_abs = (uint32_t)io.n_abs;
   a.seed_lo = (uint32_t)patch->seed;
   a.seed_hi = (uint32_t)(patch->seed >> 32);
   a.solo_op_barrier = G > 1 && env_int("SRK_SOLO_OP_BARRIER", 0) ? 1u : 0u;

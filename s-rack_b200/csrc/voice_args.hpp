@@ -28,6 +28,7 @@ struct RenderArgs {
   uint32_t K;             // samples per chunk: power of two <= 128
   uint32_t log2K;
   uint32_t ring_phase;    // absolute sample index of sample 0, mod B
+  uint32_t n_abs;         // ... and its low 32 bits: fixes the mixdown's summation order (run_mix)
   uint32_t seed_lo, seed_hi;
   uint32_t solo_op_barrier;  // one-warp schedule, several groups per block: barrier after every instruction, not only per chunk
 };

@@ -84,45 +84,51 @@ __device__ __forceinline__ void run_output(const Instr& ins, const dsp::Lane& ln
 }
 
 // OP_MIX: this group's share of the mixdown, partial[group][c][n] = sum over the group's voices.
-// Transposed read of the [K][32] tile, R = min(K, 32) sample rows at a time: lane (k, seg) adds
-// R columns of sample row k (rotated start => 32 lanes on 32 banks), then a butterfly over seg.
-// Fixed order => reproducible bits.
+// Transposed read of the [K][32] tile, 32 sample rows at a time: lane r adds the 32 voices of sample row r, four voices
+// per LDS.128, starting at the 16-byte chunk (absolute sample index) mod 8 -- the eight lanes of a quarter warp read eight
+// different chunks (no bank conflict), and the order of the additions is a function of the absolute sample index alone:
+// the mix has the same bits whatever the chunk length, however a render is cut into calls, and whichever schedule runs
+// (the fused kernels add in exactly this order, fused_ops.cuh Out::flush).
 __device__ __forceinline__ void run_mix(const Instr& ins, const dsp::Lane& ln, const GroupCtx& g, int kk) {
   const RenderArgs& a = g.a;
   const uint32_t n0 = ln.chunk * a.K;
   if (!a.partial || g.n_active == 0) return;
-  const uint32_t R = min(a.K, 32u), log2R = min(a.log2K, 5u);
   const int lane = g.lane;
   if (g.solo) __syncwarp();  // the tile was written by this warp a moment ago
-  const uint32_t k = lane & (R - 1), seg = lane >> log2R;
   for (int kb = 0; kb < kk; kb += 32) {
+    const int r = kb + lane;  // this lane's sample row
+    const uint32_t s8 = (a.n_abs + n0 + (uint32_t)r) & 7u;
     float sum = 0.0f;
     for (int j = 0; j < ins.n_ch; ++j) {
       const float* src = dsp::wire(ln, ins.in[j]);
       if (!src) {
         sum = 0.0f;
       } else if (j == 0 || ins.in[j] != ins.in[j - 1]) {
-        const float* row = src - lane + (kb + k) * 32 + seg * R;  // R columns [seg*R, seg*R + R) of row kb + k
         float acc = 0.0f;
-        if (g.n_active == 32) {
-          uint32_t col = k;
-#pragma unroll 8
-          for (uint32_t q = 0; q < R; ++q) {
-            acc = dsp::fadd(acc, row[col]);
-            col = (col + 1) & (R - 1);
-          }
-        } else {
-          const uint32_t col0 = seg * R;
-          for (uint32_t q = 0; q < R; ++q) {
-            const uint32_t col = (q + k) & (R - 1);
-            const float x = row[col];
-            acc = dsp::fadd(acc, col0 + col < g.n_active ? x : 0.0f);
+        if (r < kk) {
+          const float4* row4 = reinterpret_cast<const float4*>(src - lane + r * 32);
+          if (g.n_active == 32) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float4 x = row4[(s8 + k) & 7u];
+              acc = dsp::fadd(dsp::fadd(dsp::fadd(dsp::fadd(acc, x.x), x.y), x.z), x.w);
+            }
+          } else {
+#pragma unroll 1
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t ch4 = (s8 + k) & 7u;
+              const float4 x = row4[ch4];
+              const uint32_t v0 = ch4 * 4u;
+              acc = dsp::fadd(acc, v0 < g.n_active ? x.x : 0.0f);
+              acc = dsp::fadd(acc, v0 + 1u < g.n_active ? x.y : 0.0f);
+              acc = dsp::fadd(acc, v0 + 2u < g.n_active ? x.z : 0.0f);
+              acc = dsp::fadd(acc, v0 + 3u < g.n_active ? x.w : 0.0f);
+            }
           }
         }
-        for (uint32_t off = R; off < 32; off <<= 1) acc = dsp::fadd(acc, __shfl_xor_sync(0xFFFFFFFFu, acc, off));
         sum = acc;
       }  // else: same wire as the previous channel, same sums
-      if (kb + lane < kk) a.partial[((size_t)g.group * a.C + ins.aux + j) * a.n_samples + n0 + kb + lane] = sum;
+      if (r < kk) a.partial[((size_t)g.group * a.C + ins.aux + j) * a.n_samples + n0 + r] = sum;
     }
   }
   if (g.solo) __syncwarp();

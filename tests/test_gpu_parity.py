@@ -274,12 +274,17 @@ def test_determinism_reset_and_chunk_invariance(srk, orc, cuda_device):
     assert (a_mix.view(np.uint32) == b_mix.view(np.uint32)).all()
     p.reset()
     chunks, done = [], 0
+    mixes = []
     for n in (1, 15, 16, 17, 1000, 4096, N - 5145):  # state persists across calls like across blocks
-        chunks.append(p.render(V, n, stems=True)[0])
+        st, mx = p.render(V, n, stems=True)
+        chunks.append(st)
+        mixes.append(mx)
         done += n
     assert done == N
     c_st = np.concatenate(chunks, axis=1)
     assert (a_st.view(np.uint32) == c_st.view(np.uint32)).all()
+    # the mixdown adds a sample's voices in an order fixed by the absolute sample index: chunking does not move a bit
+    assert (a_mix.view(np.uint32) == np.concatenate(mixes, axis=1).view(np.uint32)).all()
 
 
 def test_chunked_feedback_patch_keeps_ring_phase(srk, orc, cuda_device):
@@ -563,7 +568,7 @@ def test_schedule_invariance(srk, orc, cuda_device, monkeypatch, name, B):
     assert any(r[0]["fused"] and r[0]["n_warps"] > 1 for r in results) and any(r[0]["fused"] and r[0]["n_warps"] == 1 for r in results)
     for info, st, mx in results[1:]:
         assert (st.view(np.uint32) == results[0][1].view(np.uint32)).all(), info
-        assert np.abs(mx - results[0][2]).max() <= 1e-5 * np.sqrt(V), info
+        assert (mx.view(np.uint32) == results[0][2].view(np.uint32)).all(), info  # one summation order for every schedule
     gp, op, _, _ = build_both(srk, orc, builder, V, buffer_size=B)
     o_st, _ = op.render(V, N + 997)
     assert_parity(results[0][1], o_st, what=f"{name} schedule 0")
