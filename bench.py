@@ -13,7 +13,8 @@ of the stereo mix per step).  A step = one 1-second render (48000 samples) of ev
 Every other BASELINE config rides along in the same line as a sub-record with its own ms_per_step / kernel_ms /
 roofline, so the driver's records carry them:
   N = 1 : `configs` = cfg2 @ 65536 voices (the full chip), cfg3 and cfg3b @ 65536 (configs[2]), cfg4 @ 32768 (one GPU's
-          share of configs[3]); `block_cadence` (srk_render per 1024-sample block); the CPU baselines.
+          share of configs[3]); `cfg5` (configs[4], all eight graphs on the one GPU: the N = 1 point of its strong-scaling
+          curve); `block_cadence` (srk_render per 1024-sample block); the CPU baselines.
   N > 1 : `cfg4_shard` (configs[3]: 32768 voices per GPU, 262144 at N = 8), `cfg5` (configs[4]: 8 graphs x 32768 voices
           dealt to the ranks, one graph per GPU at N = 8) and `cfg5_balanced` (the same job dealt as (graph, voice range)
           pieces: graphs longer than a rank's fair share are cut in two).
@@ -771,6 +772,9 @@ def main():
                 "cfg4_32768": single_gpu_config(ctx, "cfg4", 32768),    # one GPU's share of BASELINE configs[3]
             }
             extras["full_chip"] = extras["configs"]["cfg2_65536"]
+            # BASELINE configs[4] on one GPU: the N = 1 point of its strong-scaling curve (N > 1: graphs dealt to ranks)
+            g, _, _ = graphs_on_ranks(ctx, srk.patches.CFG5_VOICES, 3, 3)
+            extras["cfg5"] = g
     elif default_run:
         cfg4, _, _, _ = voice_shard(ctx, "cfg4", 32768, max(3, min(args.steps, 5)), 3, e2e=False)
         extras["cfg4_shard"] = cfg4
@@ -804,6 +808,7 @@ def main():
             "e2e": head["e2e"],
             "mix_check": "ok" if all(c and c.get("result") == "ok" for c in checks) else "FAILED",
             "mix_check_detail": head["mix_check"],
+            "schedule": head["schedule"],
             "gpu_launches": head["gpu_launches"],
             "clocks": clocks,
             **extras,
