@@ -325,7 +325,9 @@ static int fused_generate_fitting(const srk_patch& patch, const Engine& e, const
       std::fprintf(stderr, "[srk] fused: stages %d tile %d cross wires %d smem/group %zu x %zu groups/SM (budget %zu)\n", spec.stages, spec.tile,
                    spec.n_cross, spec.smem_per_group, per_sm, budget);
     if (spec.stages == 1 || spec.smem_per_group * per_sm <= budget) return SRK_OK;
-    if (o.tile == 32) o.tile = 16;  // shorter tiles first, then fewer stages
+    if (forced) return SRK_ERR_LIMIT;  // (a measured candidate either fits as asked for or is no candidate)
+    if (spec.split_moog) o.split_moog = false;  // the coefficient wires first, then shorter tiles, then fewer stages
+    else if (o.tile == 32) o.tile = 16;
     else { o.stages = spec.stages - 1; o.exact_stages = false; o.tile = 32; }
   }
 }
@@ -748,12 +750,12 @@ static void schedule_candidates(const srk_patch& patch, const Engine& lim, size_
   const int S0 = cur.fused ? cur.fspec.stages : 0, g0 = cur.fused ? cur.fspec.group : 4, t0 = cur.fused ? cur.fspec.tile : 32;
   out.clear();
   out.push_back(std::move(cur));
-  auto add_fused = [&](int stages, int group, int tile) {
+  auto add_fused = [&](int stages, int group, int tile, bool split) {
     Program one;
     std::string err, why;
     if (compile_program(patch, 1, one, err) != SRK_OK) return;
     FusedOptions o;
-    o.group = group; o.min_blocks = 4; o.stages = stages; o.exact_stages = true; o.tile = tile;
+    o.group = group; o.min_blocks = 4; o.stages = stages; o.exact_stages = true; o.tile = tile; o.split_moog = split;
     FusedSpec spec;
     if (fused_generate(patch, one, o, spec, why) != SRK_OK || spec.stages != stages || spec.group != group) return;
     if (spec.stages > 1 && spec.smem_per_group * per_sm > budget) return;
@@ -771,8 +773,13 @@ static void schedule_candidates(const srk_patch& patch, const Engine& lim, size_
     out.push_back(std::move(s));
   };
   if (cur_fused) {
-    add_fused(S0, g0 == 8 ? 4 : 8, t0);                      // samples per straight-line group: 4 or 8
-    if (S0 > 1 && S0 < 8) { add_fused(S0 + 1, 4, t0); add_fused(S0 + 1, 8, t0); }  // one more pipeline stage
+    const bool sp0 = out[0].fspec.split_moog;
+    add_fused(S0, g0 == 8 ? 4 : 8, t0, sp0);                 // samples per straight-line group: 4 or 8
+    if (S0 > 1 && S0 < 8) { add_fused(S0 + 1, 4, t0, sp0); add_fused(S0 + 1, 8, t0, sp0); }  // one more pipeline stage
+    if (S0 > 1) {                                            // the ladder filters' coefficients inside / outside their stage
+      add_fused(S0, 4, t0, !sp0); add_fused(S0, 8, t0, !sp0);
+      if (S0 < 8) { add_fused(S0 + 1, 4, t0, !sp0); add_fused(S0 + 1, 8, t0, !sp0); }
+    }
     if (per_sm <= 2) {                                       // the interpreter's pipeline (splits single modules over warps)
       Schedule s;
       std::string err;
@@ -786,8 +793,8 @@ static void schedule_candidates(const srk_patch& patch, const Engine& lim, size_
     std::string err, why;
     FusedSpec spec;
     if (fused_mode() != 0 && compile_program(patch, 1, one, err) == SRK_OK && fused_generate_fitting(patch, lim, one, sv, spec, why) == SRK_OK) {
-      add_fused(spec.stages, 4, spec.tile);
-      add_fused(spec.stages, 8, spec.tile);
+      add_fused(spec.stages, 4, spec.tile, spec.split_moog);
+      add_fused(spec.stages, 8, spec.tile, spec.split_moog);
     }
   }
 }

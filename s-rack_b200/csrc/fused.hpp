@@ -23,6 +23,7 @@ struct FusedSpec {
   int group = 4;                 // samples per straight-line group
   int min_blocks = 4;            // second __launch_bounds__ argument (register cap = 65536 / (128 * min_blocks))
   int stages = 1;                // warps per voice group: consecutive slices of the patch, one tile apart
+  bool split_moog = false;       // the ladder filters' coefficient blocks are ops of their own
   int tile = 32;                 // samples per output / cross-stage tile
   double max_stage_cost = 0.0;   // cost model: instructions per voice-sample of the slowest stage
   int n_cross = 0;               // wires that cross a stage boundary
@@ -36,6 +37,7 @@ struct FusedOptions {
   int stages = 1;      // at most; the generator picks the count whose slowest stage is cheapest
   bool exact_stages = false;  // ... unless told to use exactly that many (experiments, tests)
   int tile = 32;
+  bool split_moog = true;  // staged kernels: the ladder filter's coefficient block as an op of its own (another stage)
 };
 
 // `prog` must be the one-warp program of the planned patch (compile_program(patch, 1, ...)).

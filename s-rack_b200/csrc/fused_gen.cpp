@@ -104,6 +104,33 @@ int fused_generate(const srk_patch& patch, const Program& prog, const FusedOptio
       if (ins.op == OP_RING_STORE && ring_load_node.count(ins.aux)) nd.deps.push_back(ring_load_node[ins.aux]);  // the load reads the slots the store overwrites
       nodes.push_back(nd);
     }
+    // Staged kernels: a CV-driven ladder filter becomes coefficients (MoogCoef: CV -> f, p, q on three wires) + ladder
+    // (MoogCore), so that the stage cut can put the coefficient block on another warp than the ladder's dependent chain.
+    if (opt.split_moog && opt.stages > 1) {
+      const size_t n0 = nodes.size();
+      for (size_t i = 0; i < n0; ++i) {
+        if (nodes[i].ins.op != OP_MOOG || nodes[i].in[1] < 0 || (nodes[i].ins.flags & F_MOOG_EXT_COEF)) continue;
+        Node coef;
+        coef.ins = nodes[i].ins;
+        coef.ins.op = OP_MOOG_COEF;
+        coef.ins.flags = 0;
+        coef.in[0] = nodes[i].in[1];
+        coef.in[1] = coef.in[2] = coef.in[3] = -1;
+        coef.deps.push_back(producer[coef.in[0]]);
+        for (int k = 0; k < 3; ++k) {
+          coef.out[k] = n_ssa++;
+          producer.push_back((int)nodes.size());
+        }
+        coef.ins.in[0] = 0; coef.ins.in[1] = coef.ins.in[2] = coef.ins.in[3] = -1;  // (slot numbers are not used past this point;
+        coef.ins.out[0] = coef.ins.out[1] = coef.ins.out[2] = 0;                    //  only "connected or not" is)
+        Node& core = nodes[i];
+        core.ins.flags |= F_MOOG_EXT_COEF;
+        for (int k = 0; k < 3; ++k) { core.in[1 + k] = coef.out[k]; core.ins.in[1 + k] = 0; }
+        core.deps.push_back((int)nodes.size());
+        nodes.push_back(coef);
+        out.split_moog = true;
+      }
+    }
     out.n_ssa = n_ssa;
   }
   // Oscillators with a constant delta: "audio rate" when every voice's delta is in [2^-200, 1/8) and large enough that
@@ -147,7 +174,7 @@ int fused_generate(const srk_patch& patch, const Program& prog, const FusedOptio
           for (int d : nodes[i].deps) ready &= done[d] != 0;
           if (!reorder) { pick = (int)i; break; }
           const uint8_t op = nodes[i].ins.op;
-          const bool light = op == OP_MATH || op == OP_VCA || op == OP_MIXER;  // stateless: next to its producers
+          const bool light = op == OP_MATH || op == OP_VCA || op == OP_MIXER || op == OP_MOOG_COEF;  // (nearly) stateless: next to its producers
           if (ready && (pass == 1 || nodes[i].branchy || op == OP_RING_LOAD || light)) pick = (int)i;
         }
       done[pick] = 1;
@@ -214,11 +241,26 @@ int fused_generate(const srk_patch& patch, const Program& prog, const FusedOptio
         pc.generic = " | " + m + ".needs_generic()";
         break;
       case OP_MOOG:
+        if (ins.flags & F_MOOG_EXT_COEF) {  // coefficients arrive on wires in[1..3] from a MoogCoef
+          decl << "      MoogCore<" << (ins.in[0] >= 0 ? T : F) << ", " << outs_mask(ins) << "> " << m << ";\n";
+          load << "      " << m << ".load(c, " << ins.state << "u);\n";
+          body << "        " << m << ".run<U, FAST>(" << IN(0) << ", " << IN(1) << ", " << IN(2) << ", " << IN(3) << ", " << OUTW(0) << ", " << OUTW(1)
+               << ", " << OUTW(2) << ");\n";
+          store << "      " << m << ".store(c, " << ins.state << "u);\n";
+          break;
+        }
         decl << "      Moog<" << (ins.in[0] >= 0 ? T : F) << ", " << (ins.in[1] >= 0 ? T : F) << ", " << outs_mask(ins) << "> " << m << ";\n";
         load << "      " << m << ".load(c, " << ins.state << "u, " << PW(ins.param) << ", " << PW(ins.param + 1) << ", " << PW(ins.param + 2) << ");\n";
         body << "        " << m << ".run<U, FAST>(" << IN(0) << ", " << IN(1) << ", " << OUTW(0) << ", " << OUTW(1) << ", " << OUTW(2) << ");\n";
         store << "      " << m << ".store(c, " << ins.state << "u);\n";
         if (ins.in[1] >= 0) pc.generic = " | " + m + ".needs_generic()";
+        break;
+      case OP_MOOG_COEF:
+        decl << "      MoogCoef " << m << ";\n";
+        load << "      " << m << ".load(c, " << ins.state << "u, " << PW(ins.param) << ", " << PW(ins.param + 1) << ", " << PW(ins.param + 2) << ");\n";
+        body << "        " << m << ".run<U, FAST>(" << IN(0) << ", " << OUTW(0) << ", " << OUTW(1) << ", " << OUTW(2) << ");\n";
+        store << "      " << m << ".store(c, " << ins.state << "u);\n";
+        pc.generic = " | " + m + ".needs_generic()";
         break;
       case OP_ADSR:
         decl << "      Adsr<" << (ins.in[0] >= 0 ? T : F) << "> " << m << ";\n";
@@ -290,7 +332,8 @@ int fused_generate(const srk_patch& patch, const Program& prog, const FusedOptio
         return c;
       }
       case OP_NOISE: return 17.0;
-      case OP_MOOG: return ins.in[1] >= 0 ? 53.0 : 39.0;
+      case OP_MOOG: return (ins.flags & F_MOOG_EXT_COEF) ? 42.0 : ins.in[1] >= 0 ? 53.0 : 39.0;
+      case OP_MOOG_COEF: return 15.0;
       case OP_ADSR: return 10.0;
       case OP_VCA: return 3.5;
       case OP_MIXER: return 6.0;

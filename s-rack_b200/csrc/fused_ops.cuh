@@ -490,6 +490,91 @@ struct Moog {
   }
 };
 
+// The ladder filter as two ops, for kernels cut into pipeline stages: the coefficient block (:61-68; a pure function of
+// the CV, 14 instructions per sample, none of them on the ladder's dependent chain) can then run in ANOTHER stage -- the
+// ladder's own stage is the slowest of every BASELINE patch (cfg2 @ 4096 voices: 2.80 ms with the coefficients inside
+// it, 2.42 ms without them, profiles/r05i) -- and travels as three wires (f, p, q).  Same arithmetic, same state words:
+// MoogCoef owns f, p, q and the cache key (c_freq, c_res), MoogCore the delay line b0..b4.
+struct MoogCoef {
+  float f, p, q, c_freq, c_res;
+  float freq, r, exp_amt;
+  bool virgin;
+  FZ_DEV void load(const Ctx& c, u32 sw, u32 freq_bits, u32 res_bits, u32 exp_bits) {
+    f = asf(c.ld_state(sw)); p = asf(c.ld_state(sw + 1)); q = asf(c.ld_state(sw + 2));
+    c_freq = asf(c.ld_state(sw + 8)); c_res = asf(c.ld_state(sw + 9));
+    freq = asf(freq_bits);
+    r = fminf(fmaxf(asf(res_bits), 0.0f), 1.0f);  // :214
+    exp_amt = asf(exp_bits);
+    virgin = (c_freq == 0.0f) & (c_res == 0.0f) & (f == 0.0f);
+  }
+  FZ_DEV void store(const Ctx& c, u32 sw) const {
+    c.st_state(sw, asu(f)); c.st_state(sw + 1, asu(p)); c.st_state(sw + 2, asu(q));
+    c.st_state(sw + 8, asu(c_freq)); c.st_state(sw + 9, asu(c_res));
+  }
+  FZ_DEV bool needs_generic() const { return __any_sync(0xFFFFFFFFu, virgin); }
+  template <int U, bool FAST>
+  FZ_DEV void run(const float* cv, float* fo, float* po, float* qo) {
+    float fc[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) fc[j] = fminf(fmaxf(fadd(freq, fmul(cv[j], exp_amt)), 0.0f), 0.9f);  // :213
+#pragma unroll
+    for (int j = 0; j < U; ++j) moog_coef(fc[j], r, fo[j], po[j], qo[j]);
+    if (!FAST && __any_sync(0xFFFFFFFFu, virgin)) {
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        virgin = virgin & (fc[j] == 0.0f) & (r == 0.0f);
+        if (virgin) { fo[j] = 0.0f; po[j] = 0.0f; qo[j] = 0.0f; }
+      }
+    }
+    if (FAST || !virgin) { c_freq = fc[U - 1]; c_res = r; }
+    f = fo[U - 1]; p = po[U - 1]; q = qo[U - 1];
+  }
+};
+
+template <bool HAS_AUDIO, int OUTS>
+struct MoogCore {
+  float b0, b1, b2, b3, b4;
+  FZ_DEV void load(const Ctx& c, u32 sw) {
+    b0 = asf(c.ld_state(sw + 3)); b1 = asf(c.ld_state(sw + 4)); b2 = asf(c.ld_state(sw + 5));
+    b3 = asf(c.ld_state(sw + 6)); b4 = asf(c.ld_state(sw + 7));
+  }
+  FZ_DEV void store(const Ctx& c, u32 sw) const {
+    c.st_state(sw + 3, asu(b0)); c.st_state(sw + 4, asu(b1)); c.st_state(sw + 5, asu(b2));
+    c.st_state(sw + 6, asu(b3)); c.st_state(sw + 7, asu(b4));
+  }
+  template <int U, bool FAST>
+  FZ_DEV void run(const float* audio, const float* fj, const float* pj, const float* qj, float* lowpass, float* bandpass, float* highpass) {
+    float in_[U], o3[U], o4[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {  // :69-82
+      const float in = fsub(HAS_AUDIO ? audio[j] : 0.0f, fmul(qj[j], b4));
+      float t1 = b1;
+      b1 = fsub(fmul(fadd(in, b0), pj[j]), fmul(b1, fj[j]));
+      const float t2 = b2;
+      b2 = fsub(fmul(fadd(b1, t1), pj[j]), fmul(b2, fj[j]));
+      t1 = b3;
+      b3 = fsub(fmul(fadd(b2, t2), pj[j]), fmul(b3, fj[j]));
+      b4 = fsub(fmul(fadd(b3, t1), pj[j]), fmul(b4, fj[j]));
+      b4 = fsub(b4, fmul(fmul(fmul(b4, b4), b4), 0.166667f));  // powi(3)
+      b0 = clamp1(in);
+      b1 = clamp1(b1); b2 = clamp1(b2); b3 = clamp1(b3); b4 = clamp1(b4);
+      in_[j] = in; o3[j] = b3; o4[j] = b4;
+    }
+    if (OUTS & 1) {
+#pragma unroll
+      for (int j = 0; j < U; ++j) lowpass[j] = o4[j];
+    }
+    if (OUTS & 4) {
+#pragma unroll
+      for (int j = 0; j < U; ++j) highpass[j] = fsub(in_[j], o4[j]);
+    }
+    if (OUTS & 2) {
+#pragma unroll
+      for (int j = 0; j < U; ++j) bandpass[j] = fmul(3.0f, fsub(o3[j], o4[j]));
+    }
+  }
+};
+
 // ---- ADSRModule::calc, src/synth/adsr.rs:134-217 --------------------------------------------------
 enum : u32 { ADSR_ATTACK = 0, ADSR_DECAY = 1, ADSR_SUSTAIN = 2, ADSR_RELEASE = 3, ADSR_NONE = 4 };
 

@@ -1,7 +1,10 @@
 #!/usr/bin/env python
-"""Small renders of every BASELINE patch under both schedules, meant to be run under
-compute-sanitizer (memcheck / racecheck) on the GPU box:
-    compute-sanitizer --tool racecheck python scripts/sanitize.py"""
+"""Small renders of every BASELINE patch under every kernel family and launch shape, meant to be run under
+compute-sanitizer (memcheck / racecheck / synccheck) on the GPU box:
+    compute-sanitizer --tool racecheck python scripts/sanitize.py
+Fused kernels: one warp per voice group, 3 and 5 pipeline stages (tile rings + acquire/release counters in shared
+memory), with the TMA stems path (voices % 4 == 0) and the per-lane store path; interpreter kernels: one warp per group
+and pipelined."""
 import os
 import sys
 
@@ -11,20 +14,37 @@ import numpy as np
 
 import srack_b200 as srk
 
-for warps in ("1", "16"):
-    os.environ["SRK_WARPS"] = warps
-    for name in ("cfg1", "cfg2", "cfg3", "cfg3b", "cfg4", "sequenced", "sampler"):
+KNOBS = ("SRK_FUSED", "SRK_FUSED_STAGES", "SRK_FUSED_GROUP", "SRK_WARPS", "SRK_SOLO_GROUPS")
+
+
+def run(label, env, names, V, N=1500):
+    for k in KNOBS:
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    for name in names:
         p = srk.Patch(srk.AudioConfig(48000, 256, 2))
-        (srk.patches.CONFIGS[name][0] if name in srk.patches.CONFIGS else getattr(srk.patches, name))(p, 70)
+        (srk.patches.CONFIGS[name][0] if name in srk.patches.CONFIGS else getattr(srk.patches, name))(p, V)
         p.plan()
-        st, mx = p.render(70, 1500, stems=True, mix=True)
-        st2, _ = p.render(70, 37, stems=True, mix=True)
-        assert np.isfinite(st).all() and np.isfinite(mx).all()
-        print(name, "warps", warps, p.program_info(70)["n_warps"], float(np.abs(st).max()), flush=True)
-# several voice groups per block in the one-warp schedule, ragged last block and a table reload
-os.environ["SRK_WARPS"] = "1"
+        st, mx = p.render(V, N, stems=True, mix=True)
+        st2, _ = p.render(V, 37, stems=True, mix=True)
+        _, mx3 = p.render(V, 64, stems=False, mix=True)
+        assert np.isfinite(st).all() and np.isfinite(mx).all() and np.isfinite(mx3).all()
+        info = p.program_info(V)
+        print(f"{label:28s} {name:10s} V={V} fused={info['fused']} warps={info['n_warps']} max|x|={float(np.abs(st).max()):.3f}", flush=True)
+
+
+ALL = ("cfg1", "cfg2", "cfg3", "cfg3b", "cfg4", "sequenced", "sampler")
+for stages in ("1", "3", "5"):
+    run(f"fused stages<={stages} (TMA)", {"SRK_FUSED": "1", "SRK_FUSED_STAGES": stages}, ALL, 72)
+    run(f"fused stages<={stages} (no TMA)", {"SRK_FUSED": "1", "SRK_FUSED_STAGES": stages}, ("cfg2", "cfg3b", "cfg4"), 70)
+run("fused stages<=4, groups of 8", {"SRK_FUSED": "1", "SRK_FUSED_STAGES": "4", "SRK_FUSED_GROUP": "8"}, ("cfg2", "cfg4", "cfg3b"), 72)
+for warps in ("1", "16"):
+    run(f"interpreter warps<={warps}", {"SRK_FUSED": "0", "SRK_WARPS": warps}, ALL, 70)
+# several voice groups per block in the interpreter's one-warp schedule, ragged last block and a table reload
 for groups in ("3", "16"):
-    os.environ["SRK_SOLO_GROUPS"] = groups
+    for k in KNOBS:
+        os.environ.pop(k, None)
+    os.environ.update({"SRK_FUSED": "0", "SRK_WARPS": "1", "SRK_SOLO_GROUPS": groups})
     p = srk.Patch(srk.AudioConfig(48000, 256, 2))
     h = srk.patches.sampler(p, 333)
     p.plan()
