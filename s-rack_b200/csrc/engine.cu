@@ -308,6 +308,8 @@ static FusedOptions fused_options(const Engine& e, size_t n_voices, const FusedO
   o.stages = per_sm <= 4 ? (int)std::min<size_t>(8, 16 / per_sm) : 1;
   if (env_int("SRK_FUSED_STAGES", 0) > 0) { o.stages = env_int("SRK_FUSED_STAGES", 1); o.exact_stages = true; }
   o.tile = env_int("SRK_FUSED_TILE_ROWS", 32);
+  o.split_moog = env_int("SRK_FUSED_SPLIT_MOOG", 1) != 0;
+  o.prefetch = env_int("SRK_FUSED_PREFETCH", 0) != 0;
   return o;
 }
 // ... and the variant that fits: every group an SM gets must be resident at once (the launch is one wave)
@@ -727,7 +729,7 @@ constexpr size_t kTuneMinSamples = 16384;  // shorter renders keep the cost mode
 static bool tune_allowed() {
   if (!env_int("SRK_TUNE", 1)) return false;
   for (const char* k : {"SRK_FUSED", "SRK_WARPS", "SRK_STEP", "SRK_FUSED_STAGES", "SRK_FUSED_GROUP", "SRK_FUSED_TILE_ROWS", "SRK_SOLO_GROUPS",
-                        "SRK_FUSED_MINB", "SRK_FUSED_WPB", "SRK_SOLO_OP_BARRIER"}) {
+                        "SRK_FUSED_MINB", "SRK_FUSED_WPB", "SRK_SOLO_OP_BARRIER", "SRK_FUSED_SPLIT_MOOG", "SRK_FUSED_PREFETCH"}) {
     const char* v = std::getenv(k);
     if (v && *v) return false;
   }
@@ -836,19 +838,26 @@ static int tune_schedule(srk_patch* patch, Engine& e, size_t n_voices, size_t vo
   std::string all;
   for (const Schedule& c : cand) { all += c.id; all += '\n'; }
   all += "V=" + std::to_string(sv) + " stems=" + std::to_string((int)want_stems) + " mix=" + std::to_string((int)want_mix) + " sm=" + std::to_string(e.n_sm);
-  const std::string path = fused_cache_dir() + "/" + fused_hash(all, "tune-v1") + ".tune";
+  const std::string name = fused_hash(all, "tune-v1") + ".tune";
+  const std::string path = fused_cache_dir() + "/" + name;
   size_t best = cand.size();
+  std::string found_in;
   const char* nocache = std::getenv("SRK_KERNEL_CACHE_OFF");
   if (!(nocache && nocache[0] == '1')) {
-    if (FILE* f = std::fopen(path.c_str(), "r")) {
+    // this machine's own measurements first, then the decisions shipped with the library (tuned/: measured on B200 for
+    // the BASELINE launches, so that a fresh checkout runs the kernels the committed profiles describe)
+    for (const std::string& file : {path, fused_tuned_dir() + "/" + name}) {
+      FILE* f = std::fopen(file.c_str(), "r");
+      if (!f) continue;
       char line[256] = {0};
       if (std::fgets(line, sizeof line, f)) {
         std::string id(line);
         while (!id.empty() && (id.back() == '\n' || id.back() == '\r')) id.pop_back();
         for (size_t i = 0; i < cand.size(); ++i)
-          if (cand[i].id == id) best = i;
+          if (cand[i].id == id) { best = i; found_in = file; }
       }
       std::fclose(f);
+      if (best != cand.size()) break;
     }
   }
   std::string report;
@@ -934,7 +943,7 @@ static int tune_schedule(srk_patch* patch, Engine& e, size_t n_voices, size_t vo
       }
     }
   } else {
-    report = "decision from " + path;
+    report = "decision from " + found_in;
   }
   e.tune_note = "chose " + cand[best].id + "; " + report;
   if (env_int("SRK_DEBUG", 0)) std::fprintf(stderr, "[srk] tune: %s\n", e.tune_note.c_str());

@@ -38,6 +38,7 @@ struct FusedOptions {
   bool exact_stages = false;  // ... unless told to use exactly that many (experiments, tests)
   int tile = 32;
   bool split_moog = true;  // staged kernels: the ladder filter's coefficient block as an op of its own (another stage)
+  bool prefetch = false;   // staged kernels: a stage loads its cross-stage inputs one sample group ahead (measured: slower)
 };
 
 // `prog` must be the one-warp program of the planned patch (compile_program(patch, 1, ...)).
@@ -69,5 +70,6 @@ int fused_kernel(const FusedSpec& spec, const FusedKernel** out, std::string& er
 int fused_stems_map(SrkTensorMap* map, float* stems, uint64_t C, uint64_t N, uint64_t V, unsigned tile_rows, std::string& err);
 
 std::string fused_cache_dir();
+std::string fused_tuned_dir();  // read-only: schedule decisions shipped with the library (tuned/ next to it, or $SRK_TUNED_DIR)
 
 }  // namespace srk

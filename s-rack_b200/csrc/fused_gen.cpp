@@ -472,9 +472,16 @@ int fused_generate(const srk_patch& patch, const Program& prog, const FusedOptio
       has_ring |= nd.ins.op == OP_RING_LOAD || nd.ins.op == OP_RING_STORE;
     }
     // cross inputs first, then the ops, then cross outputs
+    std::ostringstream gets, gets_first, gets_next, take_next;  // plain | prefetching: before the loop / next group / rotate
+    std::vector<int> cross_in;
     for (int w : used)
       if (cross_id[w] >= 0 && prod_stage[w] != st) {
-        body << "        pipe.get<U>(" << first_tile[w] << "u + t % " << depth[w] << "u, row, w" << w << ");\n";
+        const std::string slot = std::to_string(first_tile[w]) + "u + t % " + std::to_string(depth[w]) + "u";
+        gets << "        pipe.get<U>(" << slot << ", row, w" << w << ");\n";
+        gets_first << "        pipe.get<" << group << ">(" << slot << ", 0u, n" << w << ");\n";
+        gets_next << "        pipe.get<U>(" << slot << ", row_next, n" << w << ");\n";
+        take_next << "#pragma unroll\n        for (int j = 0; j < U; ++j) w" << w << "[j] = n" << w << "[j];\n";
+        cross_in.push_back(w);
         if (std::find(wait_in.begin(), wait_in.end(), prod_stage[w]) == wait_in.end()) wait_in.push_back(prod_stage[w]);
       }
     for (int idx : order) {
@@ -499,10 +506,18 @@ int fused_generate(const srk_patch& patch, const Program& prog, const FusedOptio
       for (size_t k = 0; k < used.size(); ++k) wires << (k ? ", " : "") << "w" << used[k] << "[U]";
       wires << ";\n";
     }
+    // Prefetch (staged kernels): the cross-stage inputs of group g + 1 are loaded at the top of group g -- ptxas does not
+    // move a load across the loop's back edge, and a stage that is one dependent chain (the ladder filter) otherwise
+    // waits out the shared-memory latency at the head of every group.  The last group of a tile re-reads itself.
+    const bool prefetch = opt.prefetch && S > 1 && group > 1 && !cross_in.empty();
     auto tick = [&](int U, bool fast) {
       std::ostringstream t;
-      t << "      {\n        constexpr int U = " << U << ";\n        constexpr bool FAST = " << (fast ? "true" : "false") << ";\n"
-        << wires.str() << body.str() << "      }\n";
+      t << "      {\n        constexpr int U = " << U << ";\n        constexpr bool FAST = " << (fast ? "true" : "false") << ";\n" << wires.str();
+      if (fast && prefetch)
+        t << take_next.str() << "        const u32 row_next = min(row + " << group << "u, rows - " << group << "u);\n" << gets_next.str();
+      else
+        t << gets.str();
+      t << body.str() << "      }\n";
       return t.str();
     };
     if (S > 1) src << "    case " << st << ": {\n";
@@ -519,8 +534,13 @@ int fused_generate(const srk_patch& patch, const Program& prog, const FusedOptio
     if (group > 1) {
       // the FAST body assumes what holds in all but a handful of tiles (no filter still on its all-zero coefficient
       // cache, noise counter a multiple of 4); a tile where it does not goes sample by sample through the generic body
-      src << "        if (!(false" << generic.str() << ")) {\n"
-          << "#pragma unroll 1\n"
+      src << "        if (!(false" << generic.str() << ")) {\n";
+      if (prefetch) {
+        src << "        float ";
+        for (size_t k = 0; k < cross_in.size(); ++k) src << (k ? ", " : "") << "n" << cross_in[k] << "[" << group << "]";
+        src << ";\n        if (rows >= " << group << "u) {\n" << gets_first.str() << "        }\n";
+      }
+      src << "#pragma unroll 1\n"
           << "        for (; row + " << group << "u <= rows; row += " << group << "u)\n" << tick(group, true)
           << "        }\n";
     }

@@ -119,6 +119,18 @@ std::string fused_key(const FusedSpec& spec) {
   return fused_hash(spec.source, kSalt);
 }
 
+std::string fused_tuned_dir() {
+  if (const char* e = std::getenv("SRK_TUNED_DIR")) return e;
+  Dl_info info;
+  std::string dir = ".";
+  if (dladdr(reinterpret_cast<const void*>(&fused_tuned_dir), &info) && info.dli_fname) {
+    dir = info.dli_fname;
+    const size_t slash = dir.rfind('/');
+    dir = slash == std::string::npos ? "." : dir.substr(0, slash);
+  }
+  return dir + "/tuned";
+}
+
 int fused_cubin(const FusedSpec& spec, std::vector<char>& cubin, std::string& key, bool* from_disk, double* compile_ms, std::string& err) {
   key = fused_key(spec);
   const std::string dir = fused_cache_dir();
