@@ -23,4 +23,9 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:"ren
     -f -o gpurun_out/prof_${TAG}_cfg2_4096 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_full_$TAG.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"render_voices|srk_fused" -s 3 -c 1 \
     -f -o gpurun_out/prof_${TAG}_cfg2_65536 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --voices-per-gpu 65536 >> gpurun_out/ncu_full_$TAG.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"render_voices|srk_fused" -s 3 -c 1 \
+    -f -o gpurun_out/prof_${TAG}_cfg4_32768 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --config cfg4 --voices-per-gpu 32768 >> gpurun_out/ncu_full_$TAG.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"render_voices|srk_fused" -s 3 -c 1 \
+    -f -o gpurun_out/prof_${TAG}_cfg3_65536 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --config cfg3 --voices-per-gpu 65536 >> gpurun_out/ncu_full_$TAG.log 2>&1
+grep -o '"kernel": "[^"]*"' gpurun_out/ncu_full_$TAG.log
 ls -la gpurun_out | tail -12
