@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Small renders of every BASELINE patch under every kernel family and launch shape, meant to be run under
 compute-sanitizer (memcheck / racecheck / synccheck) on the GPU box:
-    compute-sanitizer --tool racecheck python scripts/sanitize.py
+    compute-sanitizer --tool racecheck python scripts/sanitize.py [barriers|flags|all]
+`barriers`: every kernel whose warps synchronise through barriers only (fused one warp per group, the interpreter
+kernels); `flags`: the staged fused kernels, whose stages hand tiles over through acquire / release counters in shared
+memory -- racecheck models barriers, not flags, and reports that hand-over as hazards; memcheck and synccheck apply.
 Fused kernels: one warp per voice group, 3 and 5 pipeline stages (tile rings + acquire/release counters in shared
 memory), with the TMA stems path (voices % 4 == 0) and the per-lane store path; interpreter kernels: one warp per group
 and pipelined."""
@@ -34,14 +37,21 @@ def run(label, env, names, V, N=1500):
 
 
 ALL = ("cfg1", "cfg2", "cfg3", "cfg3b", "cfg4", "sequenced", "sampler")
+SECTION = sys.argv[1] if len(sys.argv) > 1 else "all"
 for stages in ("1", "3", "5"):
+    if (stages == "1" and SECTION == "flags") or (stages != "1" and SECTION == "barriers"):
+        continue
     run(f"fused stages<={stages} (TMA)", {"SRK_FUSED": "1", "SRK_FUSED_STAGES": stages}, ALL, 72)
     run(f"fused stages<={stages} (no TMA)", {"SRK_FUSED": "1", "SRK_FUSED_STAGES": stages}, ("cfg2", "cfg3b", "cfg4"), 70)
-run("fused stages<=4, groups of 8", {"SRK_FUSED": "1", "SRK_FUSED_STAGES": "4", "SRK_FUSED_GROUP": "8"}, ("cfg2", "cfg4", "cfg3b"), 72)
+if SECTION != "barriers":
+    run("fused stages<=4, groups of 8", {"SRK_FUSED": "1", "SRK_FUSED_STAGES": "4", "SRK_FUSED_GROUP": "8"}, ("cfg2", "cfg4", "cfg3b"), 72)
+    run("fused stages<=6, no coef split", {"SRK_FUSED": "1", "SRK_FUSED_STAGES": "6", "SRK_FUSED_SPLIT_MOOG": "0"}, ("cfg2", "cfg4"), 72)
 for warps in ("1", "16"):
+    if SECTION == "flags":
+        break
     run(f"interpreter warps<={warps}", {"SRK_FUSED": "0", "SRK_WARPS": warps}, ALL, 70)
 # several voice groups per block in the interpreter's one-warp schedule, ragged last block and a table reload
-for groups in ("3", "16"):
+for groups in ("3", "16") if SECTION != "flags" else ():
     for k in KNOBS:
         os.environ.pop(k, None)
     os.environ.update({"SRK_FUSED": "0", "SRK_WARPS": "1", "SRK_SOLO_GROUPS": groups})
