@@ -59,6 +59,7 @@ extern "C" {
                      sample_rate: u32, bits: c_int) -> c_int;
     fn srk_patch_load_srk(patch: *mut srk_patch, bytes: *const c_void, n_bytes: usize, n_skipped: *mut usize) -> c_int;
     fn srk_patch_save_srk(patch: *mut srk_patch, bytes: *mut *const c_void, n_bytes: *mut usize) -> c_int;
+    fn srk_state_epoch(patch: *const srk_patch) -> u64;
     fn srk_state_export(patch: *mut srk_patch, blob: *mut *const c_void, n_bytes: *mut usize) -> c_int;
     fn srk_state_import(patch: *mut srk_patch, blob: *const c_void, n_bytes: usize) -> c_int;
     fn srk_set_co_resident_voices(patch: *mut srk_patch, n_voices: usize) -> c_int;
@@ -233,6 +234,11 @@ impl Patch {
     /// Resume: the next `execute` of the blob's voice range continues bit for bit (`ui.rs:115-134`).
     pub fn state_import(&mut self, blob: &[u8]) -> Result<(), Error> {
         self.check(unsafe { srk_state_import(self.h, blob.as_ptr() as *const c_void, blob.len()) })
+    }
+
+    /// How often the voice state was (re)initialised -- implicitly too, by an `execute` of another voice range.
+    pub fn state_epoch(&self) -> u64 {
+        unsafe { srk_state_epoch(self.h) }
     }
 
     /// Voices other patches render on this device at the same time (the launch is scheduled for the sum).

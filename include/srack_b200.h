@@ -262,6 +262,12 @@ SRK_API int srk_render(srk_patch* patch, size_t n_voices, size_t voice_offset, s
 /* Same, enqueued on a caller-supplied cudaStream_t (passed as void*). */
 SRK_API int srk_render_on_stream(srk_patch* patch, size_t n_voices, size_t voice_offset, size_t n_samples,
                                  unsigned flags, float* stems, float* mix, void* cuda_stream);
+/* How often the voice state of this patch has been (re)initialised so far: by the first render, srk_reset(), a
+ * re-plan after a wiring change, srk_state_import() -- and IMPLICITLY whenever srk_render() is called with another
+ * n_voices or voice_offset than the call before (the state belongs to one voice range; alternate ranges through
+ * separate patches, or carry them with srk_state_export / srk_state_import).  A caller that streams a render in blocks
+ * can assert that the number does not move. */
+SRK_API uint64_t srk_state_epoch(const srk_patch* patch);
 SRK_API int srk_sync(srk_patch* patch);
 /* Back to X::new() state -- or the state a loaded .srk file carried -- for every module of every voice
  * (and empty feedback history). */

@@ -86,6 +86,7 @@ _SIGNATURES = {
     "srk_reset": (C.c_int, [_P]),
     "srk_last_render_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "srk_launch_count": (C.c_uint64, [_P]),
+    "srk_state_epoch": (C.c_uint64, [_P]),
     "srk_get_program_info": (C.c_int, [_P, C.c_size_t, C.POINTER(srk_program_info)]),
     "srk_fused_source": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t)]),
     "srk_precompile": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_int)]),

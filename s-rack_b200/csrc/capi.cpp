@@ -499,6 +499,7 @@ int srk_last_render_ms(srk_patch* p, float* kernel_ms, float* total_ms) {
 }
 
 uint64_t srk_launch_count(const srk_patch* p) { return p ? srk::engine_launches(p) : 0; }
+uint64_t srk_state_epoch(const srk_patch* p) { return p ? srk::engine_state_epoch(p) : 0; }
 
 int srk_get_program_info(srk_patch* p, size_t n_voices, srk_program_info* out) { return guarded(p, [&]() -> int {
   if (!p || !out) return SRK_ERR_ARG;

@@ -98,6 +98,7 @@ struct Engine {
   std::vector<uint4> blob;          // device image of the program (see RenderArgs::blob)
   size_t V = 0, voice_offset = 0;
   uint64_t n_abs = 0;  // samples rendered since reset
+  uint64_t state_epoch = 0;  // how often the voice state was (re)initialised: srk_state_epoch
   bool state_valid = false;
   DevBuf d_prog, d_state, d_state_init, d_params, d_rings, d_partial, d_stems, d_mix, d_waves;
   uint32_t* h_params = nullptr;  // pinned staging
@@ -469,6 +470,7 @@ static int reset_state(srk_patch* patch, Engine& e) {
     SRK_CUDA(cudaMemsetAsync(e.d_rings.p, 0, (size_t)e.prog.n_rings * e.prog.ring_len * e.V * sizeof(float), e.stream));
   e.n_abs = 0;
   e.state_valid = true;
+  ++e.state_epoch;
   return SRK_OK;
 }
 
@@ -1091,6 +1093,7 @@ int engine_last_ms(srk_patch* patch, float* kernel_ms, float* total_ms) {
 }
 
 uint64_t engine_launches(const srk_patch* patch) { return patch->engine ? patch->engine->launches : 0; }
+uint64_t engine_state_epoch(const srk_patch* patch) { return patch->engine ? patch->engine->state_epoch : 0; }
 
 // Compiles the planned patch the way a render of n_voices would (no device needed: the sm_100
 // limits are assumed when the patch has no engine yet).
@@ -1326,6 +1329,7 @@ int engine_state_import(srk_patch* patch, const void* blob, size_t n_bytes) {
   SRK_CUDA(cudaStreamSynchronize(e.stream));  // the caller's blob may go away
   e.n_abs = h.n_abs;
   e.state_valid = true;
+  ++e.state_epoch;
   // the imported play positions supersede a pending "rewind at the next render" of freshly loaded Sample tables
   for (srk_module* m : patch->modules)
     if (m->wave_new) { m->wave_new = false; ++patch->table_epoch; }

@@ -17,6 +17,7 @@ int engine_reset(srk_patch* patch);
 void engine_invalidate_state(srk_patch* patch);  // next render starts from X::new() state
 int engine_last_ms(srk_patch* patch, float* kernel_ms, float* total_ms);
 uint64_t engine_launches(const srk_patch* patch);
+uint64_t engine_state_epoch(const srk_patch* patch);
 int engine_program_info(srk_patch* patch, size_t n_voices, srk_program_info* out);
 int engine_fused_source(srk_patch* patch, size_t n_voices, std::string& source);
 int engine_precompile(srk_patch* patch, size_t n_voices, int* compiled);

@@ -402,6 +402,10 @@ class Patch:
     def launch_count(self):
         return lib.srk_launch_count(self._h)
 
+    def state_epoch(self):
+        """How often the voice state was (re)initialised (implicitly, too: a render of another voice range resets it)."""
+        return lib.srk_state_epoch(self._h)
+
 
 def plan_execution(patch):
     """synth.rs:128: output = first Output in the list (ui.rs:84-96), all_modules = the patch's list."""

@@ -725,6 +725,23 @@ def test_state_export_needs_a_render_and_shards_keep_their_offset(srk, orc, cuda
     assert (a.view(np.uint32) == b.view(np.uint32)).all()
 
 
+def test_state_epoch_counts_every_reset_including_the_implicit_ones(srk, cuda_device):
+    p = srk.Patch()
+    srk.patches.cfg2(p, 64)
+    p.plan()
+    assert p.state_epoch() == 0
+    p.render(64, 100)
+    p.render(64, 100)
+    assert p.state_epoch() == 1          # streaming the same range: the state carries over
+    p.render(32, 100, voice_offset=32)   # another voice range: implicit reset (documented in srack_b200.h)
+    assert p.state_epoch() == 2
+    p.reset()
+    assert p.state_epoch() == 3
+    blob = p.state_export()
+    p.state_import(blob)
+    assert p.state_epoch() == 4
+
+
 def test_no_voices_gives_a_silent_mix(srk, cuda_device):
     """A rank that got no voices (world size > voices) must contribute zeros to the NCCL sum."""
     p = srk.Patch()
