@@ -923,6 +923,13 @@ static int tune_schedule(srk_patch* patch, Engine& e, size_t n_voices, size_t vo
         if (rc == SRK_OK) cudaEventElapsedTime(&t[k], ev0, ev1);
         ++e.launches;
       }
+      if (rc != SRK_OK && i > 0) {  // an alternative that cannot be launched on this device is no candidate
+        cudaGetLastError();
+        cudaStreamSynchronize(e.stream);
+        report += std::string(i ? ", " : "") + c.id + " failed";
+        rc = SRK_OK;
+        continue;
+      }
       const double slope = (double)t[2] - (double)t[1];  // ms per K1 samples in steady state
       char buf[160];
       std::snprintf(buf, sizeof buf, "%s%s %.4f", i ? ", " : "", c.id.c_str(), slope);

@@ -818,9 +818,12 @@ def test_measured_schedule_choice_keeps_the_bits(srk, orc, cuda_device, monkeypa
         p = srk.Patch(srk.AudioConfig(48000, B, 2))
         builder(p, V)
         p.plan()
+        z = p.render(V, 333, stems=True)  # too short to measure on: the choice is made MID-STREAM, on the state this left
         a = p.render(V, N1, stems=True)
         b = p.render(V, N2, stems=True)   # (sampler: the table epoch moved after the first call: the kept shape is rebuilt)
-        out = (np.concatenate([a[0], b[0]], axis=1), np.concatenate([a[1], b[1]], axis=1), p.schedule_report(), p.kernel_id(V), p.program_info(V))
+        assert p.state_epoch() == 1       # no candidate run touched the voice state
+        out = (np.concatenate([z[0], a[0], b[0]], axis=1), np.concatenate([z[1], a[1], b[1]], axis=1), p.schedule_report(), p.kernel_id(V),
+               p.program_info(V))
         for k in env:
             monkeypatch.delenv(k)
         return out
