@@ -245,11 +245,7 @@ struct OscOp {
           pos = fmod1_exact(dadd(pos, dl[j]));
         }
       }
-      if (SINE) {
-#pragma unroll
-        for (int j = 0; j < U; ++j)
-          sine[(k0 + j) * L] = __double2float_rn(sin(dmul(dmul(ps[j], 3.14159265358979323846), 2.0)));
-      }
+      if (SINE) sine_port(ps, sine + k0 * L, L);  // (float) of glibc's f64 sin, libm_glibc.cuh
       if (SQUARE || SAW) {
         // polyBLEP corrections (:135-149) are zero unless a sample sits within dt of a
         // discontinuity: one test per group picks the plain or the corrected write-out.
@@ -544,11 +540,7 @@ struct OscShapeOp {
         ps[j] = __hiloint2double(__float_as_int(phi[(k0 + j) * L]), __float_as_int(plo[(k0 + j) * L]));
         dl[j] = EXT ? __hiloint2double(__float_as_int(dhi[(k0 + j) * L]), __float_as_int(dlo[(k0 + j) * L])) : delta_const;
       }
-      if (SINE) {  // (:133)
-#pragma unroll
-        for (int j = 0; j < U; ++j)
-          sine[(k0 + j) * L] = __double2float_rn(sin(dmul(dmul(ps[j], 3.14159265358979323846), 2.0)));
-      }
+      if (SINE) sine_port(ps, sine + k0 * L, L);  // (:133)
       if (SQUARE || SAW) {  // (:135-149), as OscOp::run_t
         double om[U], p2[U];
         bool near = false;

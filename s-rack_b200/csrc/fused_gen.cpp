@@ -435,8 +435,12 @@ int fused_generate(const srk_patch& patch, const Program& prog, const FusedOptio
 
   std::ostringstream src;
   src << "// generated by srack_b200 fused_gen.cpp -- the wiring of one patch; the DSP is fused_ops.cuh\n"
-      << "#define SRK_TILE " << tile << "\n"
-      << "#include \"fused_ops.cuh\"\n"
+      << "#define SRK_TILE " << tile << "\n";
+  // (tests: a wider band around the f32 rounding ties sends more -- at 0x10000000 all -- sine samples through the
+  //  device's restatement of glibc's sin, libm_glibc.cuh; part of the source, hence of the kernel id)
+  if (const char* e = std::getenv("SRK_FUSED_SIN_BAND"))
+    if (*e) src << "#define SRK_SIN_TIE_BAND " << std::min(0x10000000l, std::max(0l, std::atol(e))) << "\n";
+  src << "#include \"fused_ops.cuh\"\n"
       << "using namespace fz;\n"
       << "extern \"C\" __global__ void __launch_bounds__(" << std::max(kFusedMaxThreads, 32 * S) << ", "
       << std::max(1, min_blocks * kFusedMaxThreads / std::max(kFusedMaxThreads, 32 * S)) << ")\n"

@@ -138,10 +138,7 @@ struct Osc {
   template <int U>
   FZ_DEV void shape(const double (&ps)[U], const double (&dl)[U], float* sine, float* square, float* saw) {
     constexpr bool SINE = OUTS & 1, SQUARE = OUTS & 2, SAW = OUTS & 4;
-    if (SINE) {
-#pragma unroll
-      for (int j = 0; j < U; ++j) sine[j] = __double2float_rn(sin(dmul(dmul(ps[j], 3.14159265358979323846), 2.0)));
-    }
+    if (SINE) sine_port(ps, sine, 1);  // (float) of glibc's f64 sin, libm_glibc.cuh
     if (SQUARE || SAW) {
       double om[U], p2[U];
       bool near = false;
@@ -194,10 +191,7 @@ struct Osc {
       ps[j] = pos;
       pos = wrap01(dadd(pos, d0));
     }
-    if (SINE) {
-#pragma unroll
-      for (int j = 0; j < U; ++j) sine[j] = __double2float_rn(sin(dmul(dmul(ps[j], 3.14159265358979323846), 2.0)));
-    }
+    if (SINE) sine_port(ps, sine, 1);  // (float) of glibc's f64 sin, libm_glibc.cuh
     if (SQUARE || SAW) {
       double pb0[U];
       if (AA) {
@@ -253,10 +247,7 @@ struct Osc {
       last = false;  // with no sync input the detector sees 0.0 every sample
       if (__all_sync(0xFFFFFFFFu, plain)) {
         pos = wrap01(x);
-        if (SINE) {
-#pragma unroll
-          for (int j = 0; j < U; ++j) sine[j] = __double2float_rn(sin(dmul(dmul(ps[j], 3.14159265358979323846), 2.0)));
-        }
+        if (SINE) sine_port(ps, sine, 1);
         if (SQUARE) {
           const float base = ps[0] < 0.5 ? -1.0f : 1.0f;  // the whole group is on one side of 0.5
 #pragma unroll

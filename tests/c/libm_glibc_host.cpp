@@ -11,3 +11,13 @@ void t_powf_glibc(const float* x, const float* y, float* z, long n) {
   for (long i = 0; i < n; ++i) z[i] = powf_glibc(x[i], y[i]);
 }
 }
+extern "C" void t_sin_glibc(const double* x, double* y, long n) {
+  for (long i = 0; i < n; ++i) y[i] = sin_glibc(x[i]);
+}
+// the tie-band narrowing of the sine port, fed a `fast` sine that is `ulps[i]` bit patterns away from glibc's
+extern "C" void t_sin_settle(const double* x, const long* ulps, float* y, long n) {
+  for (long i = 0; i < n; ++i) {
+    const double g = std::sin(x[i]);
+    y[i] = lg_sin_settle(x[i], lg_f64(lg_bits(g) + (unsigned long long)ulps[i]));
+  }
+}

@@ -1,5 +1,6 @@
 """s-rack_b200/csrc/libm_glibc.cuh -- the operation-by-operation restatements of glibc 2.39's exp2 (f64: the oscillator's
-V/oct conversion, oscillator.rs:43-48) and powf (the Non-Linear module, math.rs:203-205) that the device computes with --
+V/oct conversion, oscillator.rs:43-48), sin (f64: the sine port, oscillator.rs:133) and powf (the Non-Linear module,
+math.rs:203-205) that the device computes with --
 compiled for the host (tests/c/libm_glibc_host.cpp: the same header, intrinsics swapped for plain arithmetic) and held to
 the platform's libm, bit for bit, over random and special inputs.  The platform's libm is what the CPU oracle calls, so
 this pins the device's arithmetic to the oracle's without a GPU; the GPU tests then check the device against the oracle
@@ -22,6 +23,8 @@ def host(tmp_path_factory):
     L = ctypes.CDLL(so)
     L.t_exp2_glibc.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
     L.t_powf_glibc.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
+    L.t_sin_glibc.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
+    L.t_sin_settle.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
     return L
 
 
@@ -32,6 +35,8 @@ def libm():
     m.exp2.argtypes = [ctypes.c_double]
     m.powf.restype = ctypes.c_float
     m.powf.argtypes = [ctypes.c_float, ctypes.c_float]
+    m.sin.restype = ctypes.c_double
+    m.sin.argtypes = [ctypes.c_double]
     m.gnu_get_libc_version = ctypes.CDLL("libc.so.6").gnu_get_libc_version
     m.gnu_get_libc_version.restype = ctypes.c_char_p
     return m
@@ -53,6 +58,66 @@ def test_exp2_f64_equals_glibc_bit_for_bit(host, libm):
     ref = np.array([libm.exp2(float(v)) for v in x])
     same = (y.view(np.uint64) == ref.view(np.uint64)) | (np.isnan(y) & np.isnan(ref))
     assert same.all(), f"glibc {libm.gnu_get_libc_version().decode()}: {int((~same).sum())} of {x.size} differ, e.g. x = {x[~same][:5]}"
+
+
+def test_sin_f64_equals_glibc_bit_for_bit(host, libm):
+    """`(pos * PI * 2.0).sin()` of the sine port (oscillator.rs:133): the argument is in [0, 2 pi); every branch of
+    s_sin.c below the huge-argument reduction is restated (and checked well beyond that range)."""
+    import math
+    rng = np.random.default_rng(3)
+    pos = np.concatenate([rng.uniform(0, 1, 300000), rng.uniform(0, 1, 50000) * 2.0 ** -rng.integers(1, 40, 50000),
+                          np.arange(0, 4096) / 4096.0, 1.0 - 2.0 ** -np.arange(1, 54.0)])
+    x = np.concatenate([pos * math.pi * 2.0,                       # exactly the products the oscillator forms
+                        rng.uniform(-7, 7, 100000), rng.uniform(-1e6, 1e6, 60000), rng.uniform(-0.2, 0.2, 60000),
+                        rng.standard_normal(20000) * 1e-8,
+                        np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 0.126, 0.12599999, 0.855469, 0.8554687, 2.426265, 2.4262647,
+                                  math.pi, 2 * math.pi, math.pi / 2, 1e-300, 2.0 ** -26, 2.0 ** -27, 105414349.0, -105414349.0])])
+    y = np.zeros_like(x)
+    host.t_sin_glibc(x.ctypes.data, y.ctypes.data, x.size)
+    ref = np.array([libm.sin(float(v)) for v in x])
+    same = (y.view(np.uint64) == ref.view(np.uint64)) | (np.isnan(y) & np.isnan(ref))
+    assert same.all(), f"{int((~same).sum())} of {x.size} differ, e.g. x = {[float(v).hex() for v in x[~same][:5]]}"
+
+
+def test_sine_port_narrowing_is_glibcs_for_any_fast_sine_within_three_ulp(host, libm):
+    """The sine port is `(float) sin(x)`.  The device takes CUDA's sin (<= 2 ulp) and goes through the restatement of
+    glibc's only where the value is within 16 bit patterns of an f32 rounding tie (lg_sin_settle).  Here the `fast`
+    sine is glibc's own moved by -6 .. +6 bit patterns (3 ulp across a binade boundary), on arguments whose sine sits
+    right at a tie: the narrowed result must be glibc's every time -- and would not be without the band."""
+    rng = np.random.default_rng(5)
+
+    def gsin(x):
+        y = np.zeros_like(x)
+        host.t_sin_glibc(x.ctypes.data, y.ctypes.data, x.size)  # == libm's sin (test above), vectorised
+        return y
+
+    # f32 rounding ties in (2^-30, 1): halfway between neighbouring f32 values
+    f = (rng.uniform(0, 1, 6000) * 2.0 ** -rng.integers(0, 30, 6000)).astype(np.float32)
+    f = f[(f > 0) & (f < 1)]
+    tie = (f.astype(np.float64) + np.nextafter(f, np.float32(2)).astype(np.float64)) / 2
+    cand = []
+    for x0 in (np.arcsin(tie), np.pi - np.arcsin(tie[tie > 0.4]), np.arcsin(tie[tie > 0.4]) - np.pi):
+        xb = x0.view(np.int64)[:, None] + np.arange(-24, 25)[None, :]  # neighbouring arguments
+        cand.append(xb.reshape(-1).view(np.float64))
+    x = np.concatenate(cand)
+    g = gsin(x)
+    low = g.view(np.uint64) & np.uint64(0x1fffffff)
+    at_tie = np.abs(low.astype(np.int64) - 0x10000000) <= 8
+    assert at_tie.sum() > 5000
+    x = np.concatenate([x[at_tie], rng.uniform(0, 2 * np.pi, 200000), rng.uniform(-1, 1, 2000) * 2.0 ** -rng.integers(20, 200, 2000),
+                        np.array([0.0, -0.0, 2.0 ** -26, 2.0 ** -27, 1e-300, 5e-324, np.pi, np.inf, np.nan])])
+    want = gsin(x).astype(np.float32)
+    changed = 0
+    for d in range(-6, 7):
+        ulps = np.full(x.size, d, np.int64)
+        got = np.zeros(x.size, np.float32)
+        host.t_sin_settle(x.ctypes.data, ulps.ctypes.data, got.ctypes.data, x.size)
+        same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
+        assert same.all(), f"fast sine {d} patterns off: {int((~same).sum())} differ, e.g. x = {[float(v).hex() for v in x[~same][:4]]}"
+        with np.errstate(invalid="ignore", over="ignore"):
+            moved = (gsin(x).view(np.int64) + d).view(np.float64).astype(np.float32)
+        changed += int(((moved.view(np.uint32) != want.view(np.uint32)) & np.isfinite(want) & (np.abs(x) > 2.0 ** -26)).sum())
+    assert changed > 1000, "the arguments did not exercise the band"  # plain narrowing of the moved value would have differed
 
 
 def test_powf_equals_glibc_bit_for_bit(host, libm):
