@@ -49,7 +49,7 @@ def test_cfg2_subtractive_is_bit_exact(srk, orc, cuda_device):
     assert_mix_parity(g_mix, o_mix, 100, what="cfg2 mix")
 
 
-@pytest.mark.parametrize("name,V,N", [("cfg1", 40, 48000), ("cfg3", 99, 8192), ("cfg4", 33, 6000)])
+@pytest.mark.parametrize("name,V,N", [("cfg1", 40, 48000), ("cfg3", 99, 8192), ("cfg4", 33, 16000)])
 def test_sine_port_through_the_restated_glibc_sin(srk, orc, cuda_device, monkeypatch, schedule, name, V, N):
     """With the tie band at its widest EVERY sine sample goes through the device's restatement of glibc's sin
     (libm_glibc.cuh: sin_glibc), the route a default build takes for 6e-8 of the samples: same bits as the oracle's
