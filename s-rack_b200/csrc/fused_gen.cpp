@@ -7,6 +7,7 @@
 #include "fused.hpp"
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -436,10 +437,21 @@ int fused_generate(const srk_patch& patch, const Program& prog, const FusedOptio
   std::ostringstream src;
   src << "// generated by srack_b200 fused_gen.cpp -- the wiring of one patch; the DSP is fused_ops.cuh\n"
       << "#define SRK_TILE " << tile << "\n";
-  // (tests: a wider band around the f32 rounding ties sends more -- at 0x10000000 all -- sine samples through the
-  //  device's restatement of glibc's sin, libm_glibc.cuh; part of the source, hence of the kernel id)
-  if (const char* e = std::getenv("SRK_FUSED_SIN_BAND"))
-    if (*e) src << "#define SRK_SIN_TIE_BAND " << std::min(0x10000000l, std::max(0l, std::atol(e))) << "\n";
+  // SRK_FUSED_DEFINE="NAME=VALUE,NAME2=VALUE2": macros ahead of the headers, part of the source and hence of the kernel
+  // id.  (tests: SRK_SIN_TIE_BAND=268435456 sends every sine sample through the device's restatement of glibc's sin,
+  // libm_glibc.cuh; experiments: SRK_SIN_COEF_SELECT=1)
+  if (const char* e = std::getenv("SRK_FUSED_DEFINE")) {
+    std::string item;
+    for (const char* c = e;; ++c) {
+      if (*c && *c != ',') { item += *c; continue; }
+      const size_t eq = item.find('=');
+      bool ok = !item.empty();
+      for (char ch : item) ok &= std::isalnum((unsigned char)ch) || ch == '_' || ch == '=';
+      if (ok) src << "#define " << item.substr(0, eq) << " " << (eq == std::string::npos ? "1" : item.substr(eq + 1)) << "\n";
+      item.clear();
+      if (!*c) break;
+    }
+  }
   src << "#include \"fused_ops.cuh\"\n"
       << "using namespace fz;\n"
       << "extern \"C\" __global__ void __launch_bounds__(" << std::max(kFusedMaxThreads, 32 * S) << ", "

@@ -520,32 +520,97 @@ LG_FN double sin_glibc(double x) {
 // ---------------------------------------------------------------------------------------------------------------------
 // The reference narrows the f64 sine to f32 at once, and only those 24 bits reach the rest of the patch.  Narrowing drops
 // 29 bits: two f64 values give different f32 values only when an f32 rounding tie (low 29 bits = 0x10000000) lies between
-// them or on one of them.  glibc's sin is within 1 ulp of the true value (libm-test-ulps, x86_64: sin 1) and CUDA's within
-// 2 (CUDA C Programming Guide, double-precision table: sin 2, full range), so the two are within 3 ulp of each other -- at
-// most 6 apart as bit patterns where a binade boundary lies between them.  A fast value further than kLgSinTieBand = 16
-// patterns from every tie therefore narrows to the f32 glibc's value narrows to, and the 33 in 2^29 that are nearer
-// (6e-8 of the samples) take the operation-by-operation restatement above, out of line.  Below 2^-26 glibc returns x
-// itself, and so does this.  The per-sample cost over CUDA's sin is five integer instructions and a branch never taken
-// by most warps; the result is glibc's for EVERY argument, not for most.  SRK_SIN_TIE_BAND widens the band (tests: at
-// 0x10000000 every sample takes the restatement on the device).
+// them or on one of them.  So the common route is a FAST sine that need only be CLOSE to glibc's, and the restatement
+// above runs, out of line, where that is not enough:
+//   lg_sin_fast    x - n pi/2 by Cody-Waite with the library's own four-piece pi/2 (n <= 2^17: the products are exact),
+//                  then ONE Horner chain whose seven coefficients are read from a two-row table -- fdlibm's minimax
+//                  sets for sin (k_sin.c S1..S6) and cos (k_cos.c C1..C6), both within 2^-58 on [-pi/4, pi/4] -- and one
+//                  closing fma: r + (z r) P(z) or 1 + z Q(z).  No branch, 15 f64 operations, every one an explicit
+//                  IEEE operation: host and device compute the same bits, so its distance from glibc's sin is a
+//                  property tests/test_libm_glibc.py MEASURES (at most LG_SIN_FAST_MAX_DIFF = 1 bit pattern over
+//                  2e8 arguments: random phases as the oscillator forms them, every f64 within 2000 patterns of a
+//                  multiple of pi/2, and the whole range up to 1e5), not a documented bound on somebody else's libm.
+//   lg_sin_near_tie  the fast value is within SRK_SIN_TIE_BAND = 16 patterns of a tie (sixteen times the
+//                  measured distance): 33 in 2^29 of the values, 6e-8 of the samples.  Those, and |x| >= 1e5, inf, NaN, take
+//                  sin_glibc.  Below 2^-26 glibc returns x itself, and so does this (keeps -0.0).
+// The result is glibc's for EVERY argument.  SRK_SIN_TIE_BAND widens the band (tests: at 0x10000000 every sample takes
+// the restatement on the device).
 #ifndef SRK_SIN_TIE_BAND
 #define SRK_SIN_TIE_BAND 16
 #endif
+#ifndef SRK_SIN_COEF_SELECT
+#define SRK_SIN_COEF_SELECT 0
+#endif
+#define LG_SIN_FAST_MAX_DIFF 1  // measured: tests/test_libm_glibc.py::test_fast_sine_is_close_to_glibcs
+// rows: sin {0, S6, S5, S4, S3, S2, S1}, cos {C6, C5, C4, C3, C2, C1, -1/2}; Horner from the left
+LG_TAB LG_ALIGN16 double kLgSinFastTab[16] = {
+    0.0, 0x1.5d93a5acfd57cp-33, -0x1.ae5e68a2b9cebp-26, 0x1.71de357b1fe7dp-19,
+    -0x1.a01a019c161d5p-13, 0x1.111111110f8a6p-7, -0x1.5555555555549p-3, 0.0,
+    -0x1.8fae9be8838d4p-37, 0x1.1ee9ebdb4b1c4p-29, -0x1.27e4f809c52adp-22, 0x1.a01a019cb1590p-16,
+    -0x1.6c16c16c15177p-10, 0x1.555555555554cp-5, -0x1.0000000000000p-1, 0.0,
+};
+#if defined(__CUDACC__) || defined(__CUDACC_RTC__)
+static __device__ __forceinline__ lg_dpair lg_ld_fast(unsigned k) {
+  const double2 v = __ldg(reinterpret_cast<const double2*>(&kLgSinFastTab[k]));
+  lg_dpair q; q.a = v.x; q.b = v.y; return q;
+}
+#else
+static inline lg_dpair lg_ld_fast(unsigned k) { lg_dpair q; q.a = kLgSinFastTab[k]; q.b = kLgSinFastTab[k + 1]; return q; }
+#endif
+LG_FN double lg_sin_fast(double x) {  // |x| < 1e5
+  const double t = lg_fma(x, 0x1.45f306dc9c883p-1, 0x1.8000000000000p+52);
+  const double xn = lg_sub(t, 0x1.8000000000000p+52);
+  const unsigned n = (unsigned)lg_bits(t);
+  double b = lg_fma(-xn, 0x1.921fb58000000p+0, x);   // exact
+  b = lg_fma(-xn, -0x1.dde973c000000p-27, b);
+  b = lg_fma(-xn, -0x1.cb3b398000000p-55, b);
+  b = lg_fma(-xn, -0x1.d747f23e32ed7p-83, b);
+  const double z = lg_mul(b, b);
+#if SRK_SIN_COEF_SELECT
+  // the row's coefficients by select instead of by load: two FSEL per coefficient, no registers held across the chain
+  // (same operations on the same values: same bits)
+  const bool cs = (n & 1u) != 0u;
+  double p = lg_fma(z, cs ? -0x1.8fae9be8838d4p-37 : 0.0, cs ? 0x1.1ee9ebdb4b1c4p-29 : 0x1.5d93a5acfd57cp-33);
+  p = lg_fma(z, p, cs ? -0x1.27e4f809c52adp-22 : -0x1.ae5e68a2b9cebp-26);
+  p = lg_fma(z, p, cs ? 0x1.a01a019cb1590p-16 : 0x1.71de357b1fe7dp-19);
+  p = lg_fma(z, p, cs ? -0x1.6c16c16c15177p-10 : -0x1.a01a019c161d5p-13);
+  p = lg_fma(z, p, cs ? 0x1.555555555554cp-5 : 0x1.111111110f8a6p-7);
+  p = lg_fma(z, p, cs ? -0x1.0000000000000p-1 : -0x1.5555555555549p-3);
+#else
+  const unsigned row = (n & 1u) << 3;
+  const lg_dpair c01 = lg_ld_fast(row), c23 = lg_ld_fast(row + 2u), c45 = lg_ld_fast(row + 4u), c6 = lg_ld_fast(row + 6u);
+  double p = lg_fma(z, c01.a, c01.b);
+  p = lg_fma(z, p, c23.a);
+  p = lg_fma(z, p, c23.b);
+  p = lg_fma(z, p, c45.a);
+  p = lg_fma(z, p, c45.b);
+  p = lg_fma(z, p, c6.a);
+#endif
+  const double a = (n & 1u) ? 1.0 : b;
+  const double r = lg_fma(lg_mul(z, a), p, a);
+  return lg_f64(lg_bits(r) ^ ((unsigned long long)(n & 2u) << 62));
+}
 LG_FN bool lg_sin_near_tie(double r) {
   const unsigned lo = (unsigned)lg_bits(r);
   return ((lo - (0x10000000u - (unsigned)(SRK_SIN_TIE_BAND))) & 0x1fffffffu) <= 2u * (unsigned)(SRK_SIN_TIE_BAND);
 }
 LG_COLD double lg_sin_exact(double x) { return sin_glibc(x); }
-// `fast`: sin(x) from any implementation within 3 ulp of glibc's
+// `fast`: sin(x) from an implementation within SRK_SIN_TIE_BAND bit patterns of glibc's for 2^-26 <= |x| < 1e5
 LG_FN double lg_sin_pick(double x, double fast) {
   const unsigned k = (unsigned)(lg_bits(x) >> 32) & 0x7fffffffu;
   return k < 0x3e500000u ? x : fast;
 }
+LG_FN bool lg_sin_unsure(double x, double r) {
+  const unsigned k = (unsigned)(lg_bits(x) >> 32) & 0x7fffffffu;
+  return lg_sin_near_tie(r) || k >= 0x40f86a00u;  // next to a tie, or |x| >= 1e5 / inf / NaN
+}
 LG_FN float lg_sin_settle(double x, double fast) {
   double r = lg_sin_pick(x, fast);
-  if (lg_sin_near_tie(r)) r = lg_sin_exact(x);
+  if (lg_sin_unsure(x, r)) r = lg_sin_exact(x);
   return lg_narrow(r);
 }
+// (float) sin(x), one sample
+LG_FN float sinf_of_f64_glibc(double x) { return lg_sin_settle(x, lg_sin_fast(x)); }
 #if defined(__CUDACC__) || defined(__CUDACC_RTC__)
 // U samples of a group: the fast values as straight-line code (the compiler interleaves the U chains), one branch for
 // the group
@@ -555,13 +620,13 @@ LG_FN void sin_f32_glibc(const double (&x)[U], float (&y)[U]) {
   bool any = false;
 #pragma unroll
   for (int j = 0; j < U; ++j) {
-    r[j] = lg_sin_pick(x[j], sin(x[j]));
-    any |= lg_sin_near_tie(r[j]);
+    r[j] = lg_sin_pick(x[j], lg_sin_fast(x[j]));
+    any |= lg_sin_unsure(x[j], r[j]);
   }
   if (any) {
 #pragma unroll
     for (int j = 0; j < U; ++j)
-      if (lg_sin_near_tie(r[j])) r[j] = lg_sin_exact(x[j]);
+      if (lg_sin_unsure(x[j], r[j])) r[j] = lg_sin_exact(x[j]);
   }
 #pragma unroll
   for (int j = 0; j < U; ++j) y[j] = lg_narrow(r[j]);

@@ -21,3 +21,35 @@ extern "C" void t_sin_settle(const double* x, const long* ulps, float* y, long n
     y[i] = lg_sin_settle(x[i], lg_f64(lg_bits(g) + (unsigned long long)ulps[i]));
   }
 }
+// the fast sine of the common route against the platform's: largest distance in bit patterns over
+//   mode 0: n arguments (float64)(pos * PI * 2.0), pos uniform in [0, 1) -- as the oscillator forms them
+//   mode 1: n arguments uniform in (-lim, lim)
+//   mode 2: every f64 within n patterns of k * pi / 2, k = 1 .. 8 (both signs)
+// and whether (float) of the settled value equals (float) of the platform's everywhere (-> *narrow_bad)
+#include <cstdint>
+extern "C" long t_sin_fast_scan(int mode, long n, double lim, unsigned long long seed, double* worst_x, long* narrow_bad) {
+  unsigned long long st = seed * 0x9E3779B97F4A7C15ull + 1;
+  auto rnd = [&st]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (double)(st >> 11) * 0x1p-53; };
+  long worst = 0, bad = 0;
+  auto one = [&](double x) {
+    const double g = std::sin(x), f = lg_sin_fast(x);
+    long d = (long)(lg_bits(f) - lg_bits(g));
+    if ((lg_bits(f) ^ lg_bits(g)) >> 63) d = (long)((lg_bits(f) & ~(1ull << 63)) + (lg_bits(g) & ~(1ull << 63)));  // across zero
+    if (d < 0) d = -d;
+    if (d > worst) { worst = d; *worst_x = x; }
+    const float a = sinf_of_f64_glibc(x), b = (float)g;
+    if (lg_bitsf(a) != lg_bitsf(b)) ++bad;
+  };
+  if (mode == 0) for (long i = 0; i < n; ++i) one(rnd() * 3.14159265358979323846 * 2.0);
+  if (mode == 1) for (long i = 0; i < n; ++i) one((rnd() * 2.0 - 1.0) * lim);
+  if (mode == 2)
+    for (int k = 1; k <= 8; ++k) {
+      const double c = k * 1.5707963267948966;
+      for (long i = -n; i <= n; ++i) { const double x = lg_f64(lg_bits(c) + (unsigned long long)i); one(x); one(-x); }
+    }
+  *narrow_bad = bad;
+  return worst;
+}
+extern "C" void t_sinf_of_f64(const double* x, float* y, long n) {
+  for (long i = 0; i < n; ++i) y[i] = sinf_of_f64_glibc(x[i]);
+}

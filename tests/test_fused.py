@@ -68,12 +68,20 @@ def test_every_baseline_kernel_compiles_for_sm_100a_with_tma_and_without_spills(
         pytest.skip(f"no NVRTC on this machine: {e}")
     cubins = sorted(glob.glob(str(tmp_path / "*.cubin")))
     assert n == len(cubins) and n >= 10  # cfg2 @ 4096 alone has eight fused candidates
+    # the kernels the cost model launches before anything is measured: no spills at all
+    first = {_patch(srk, _builders(srk)[name], V).kernel_id(V).split(":")[1]
+             for name, V in (("cfg2", 4096), ("cfg2", 65536), ("cfg4", 32768), ("cfg3b", 65536), ("sampler", 4096))}
     for f in cubins:
         sass = subprocess.run(["cuobjdump", "-sass", f], capture_output=True, text=True).stdout
         res = subprocess.run(["cuobjdump", "-res-usage", f], capture_output=True, text=True).stdout
         assert "sm_100a" in sass and "UTMASTG" in sass and "UTMACMDFLUSH" in sass, f  # TMA bulk tensor stores of the stems tiles
         regs, stack = int(re.search(r"REG:(\d+)", res).group(1)), int(re.search(r"STACK:(\d+)", res).group(1))
-        assert regs <= 128 and stack <= 96, (f, regs, stack)  # (the few stack bytes are libdevice's sin / division slow paths)
+        # 40 stack bytes are libdevice's (the huge-argument reduction behind lg_sin_huge, division slow paths).  An
+        # ALTERNATIVE launch shape (groups of 8 on a patch with four oscillators) may spill a few registers at the
+        # 128-register cap: it then loses the measurement that picks the shape, it is not an error
+        assert regs <= 128 and stack <= 160, (f, regs, stack)
+        if os.path.basename(f).split(".")[0] in first:
+            assert stack <= 48, (f, regs, stack)
     # a second request finds everything cached
     assert _patch(srk, _builders(srk)["cfg2"], 4096).precompile(4096) == 0
 

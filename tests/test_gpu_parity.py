@@ -57,7 +57,7 @@ def test_sine_port_through_the_restated_glibc_sin(srk, orc, cuda_device, monkeyp
     if schedule == "interp":
         pytest.skip("the band is part of a fused kernel's source; the interpreter kernels are built with the default")
     monkeypatch.setenv("SRK_FUSED", "1")
-    monkeypatch.setenv("SRK_FUSED_SIN_BAND", str(0x10000000))
+    monkeypatch.setenv("SRK_FUSED_DEFINE", f"SRK_SIN_TIE_BAND={0x10000000}")
     gp, op, g, g_mix, o, o_mix = render_pair(srk, orc, srk.patches.CONFIGS[name][0], V, N)
     assert np.abs(o).max() > 0.1
     assert_parity(g, o, exact=True, what=f"{name}, every sine restated")

@@ -15,16 +15,22 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module")
-def host(tmp_path_factory):
+@pytest.fixture(scope="module", params=["table", "select"])
+def host(tmp_path_factory, request):
+    """(both spellings of the fast sine's coefficient choice, SRK_SIN_COEF_SELECT)"""
     so = str(tmp_path_factory.mktemp("libm") / "libm_glibc_host.so")
     subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-mfma", "-shared", "-fPIC", "-o", so,
+                           f"-DSRK_SIN_COEF_SELECT={int(request.param == 'select')}",
                            os.path.join(ROOT, "tests", "c", "libm_glibc_host.cpp")])
     L = ctypes.CDLL(so)
     L.t_exp2_glibc.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
     L.t_powf_glibc.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
     L.t_sin_glibc.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
     L.t_sin_settle.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
+    L.t_sin_fast_scan.restype = ctypes.c_long
+    L.t_sin_fast_scan.argtypes = [ctypes.c_int, ctypes.c_long, ctypes.c_double, ctypes.c_ulonglong,
+                                  ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_long)]
+    L.t_sinf_of_f64.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
     return L
 
 
@@ -79,6 +85,23 @@ def test_sin_f64_equals_glibc_bit_for_bit(host, libm):
     assert same.all(), f"{int((~same).sum())} of {x.size} differ, e.g. x = {[float(v).hex() for v in x[~same][:5]]}"
 
 
+def test_fast_sine_is_close_to_glibcs(host, libm):
+    """lg_sin_fast -- the sine of the common route, explicit IEEE operations only, hence the same bits on the device --
+    stays within LG_SIN_FAST_MAX_DIFF = 1 bit pattern of the platform's sin, a sixteenth of the tie band; and the
+    settled, narrowed value is the platform's `(float) sin(x)` on every argument scanned.  (1.8e8 arguments gave the
+    same maximum; the run here is sized for the CPU suite.)"""
+    import re
+    src = open(os.path.join(ROOT, "s-rack_b200", "csrc", "libm_glibc.cuh")).read()
+    max_diff = int(re.search(r"#define LG_SIN_FAST_MAX_DIFF (\d+)", src).group(1))
+    band = int(re.search(r"#define SRK_SIN_TIE_BAND (\d+)", src).group(1))
+    assert band >= 8 * max_diff
+    for mode, n, lim in ((0, 30_000_000, 0.0), (1, 8_000_000, 7.0), (1, 8_000_000, 1e5), (1, 4_000_000, 1e-3), (2, 2000, 0.0)):
+        wx, bad = ctypes.c_double(), ctypes.c_long()
+        worst = host.t_sin_fast_scan(mode, n, lim, 11, ctypes.byref(wx), ctypes.byref(bad))
+        assert worst <= max_diff, f"mode {mode}: {worst} patterns from the platform's sin at x = {wx.value.hex()}"
+        assert bad.value == 0, f"mode {mode}: {bad.value} narrowed values differ"
+
+
 def test_sine_port_narrowing_is_glibcs_for_any_fast_sine_within_three_ulp(host, libm):
     """The sine port is `(float) sin(x)`.  The device takes CUDA's sin (<= 2 ulp) and goes through the restatement of
     glibc's only where the value is within 16 bit patterns of an f32 rounding tie (lg_sin_settle).  Here the `fast`
@@ -107,6 +130,9 @@ def test_sine_port_narrowing_is_glibcs_for_any_fast_sine_within_three_ulp(host, 
     x = np.concatenate([x[at_tie], rng.uniform(0, 2 * np.pi, 200000), rng.uniform(-1, 1, 2000) * 2.0 ** -rng.integers(20, 200, 2000),
                         np.array([0.0, -0.0, 2.0 ** -26, 2.0 ** -27, 1e-300, 5e-324, np.pi, np.inf, np.nan])])
     want = gsin(x).astype(np.float32)
+    got = np.zeros(x.size, np.float32)
+    host.t_sinf_of_f64(x.ctypes.data, got.ctypes.data, x.size)  # the composition the device runs: fast sine, settled
+    assert ((got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))).all()
     changed = 0
     for d in range(-6, 7):
         ulps = np.full(x.size, d, np.int64)
