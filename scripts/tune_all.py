@@ -15,6 +15,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+os.environ["SRK_TUNED_DIR"] = "/nonexistent"  # measure; do not read the decisions already shipped
 import torch
 
 import srack_b200 as srk
@@ -42,6 +43,61 @@ for name, V in shapes:
     print(f"{name}:{V:<6d} kernel {min(ms[1:]):8.3f} ms  {p.kernel_id(V)}\n    {p.schedule_report()}", flush=True)
     del stems, mix, p
     torch.cuda.empty_cache()
+
+
+# Second pass.  The library's own measurement is a short window at the start of the render (T(2K) - T(K), K <= 2048
+# samples: cheap enough for a first render) and resolves candidates about 2 % apart no better than a coin; the gate of
+# the BASELINE patches opens at sample 12000, which that window never sees.  For the decisions that SHIP, every
+# candidate renders the whole 48000 samples (SRK_TUNE_PICK forces one) and the fastest kernel time decides.
+def whole_render_ms(name, V, pick):
+    os.environ["SRK_TUNE_PICK"] = str(pick)
+    try:
+        p = srk.Patch(device=0)
+        builders[name](p, V)
+        p.plan()
+        stems = torch.empty((2, N, V), dtype=torch.float32, device="cuda:0")
+        mix = torch.empty((2, N), dtype=torch.float32, device="cuda:0")
+        ms = []
+        for i in range(3):
+            p.render_into(V, N, 0, stems.data_ptr(), mix.data_ptr(), device_out=True)
+            torch.cuda.synchronize()
+            ms.append(p.last_render_ms()[0])
+        kid = p.kernel_id(V)
+        del stems, mix, p
+        torch.cuda.empty_cache()
+        return min(ms[1:]), kid
+    finally:
+        del os.environ["SRK_TUNE_PICK"]
+
+
+by_shape = {}
+for f in glob.glob(os.path.join(cache, "*.tune")):
+    lines = open(f).read().splitlines()
+    by_shape[f] = (lines, [l for l in lines[2:-1]], lines[-1])
+for name, V in shapes:
+    # the decision file of this launch: the one whose candidates start with the model's choice for (name, V)
+    os.environ["SRK_TUNE"] = "0"
+    q = srk.Patch(device=0)
+    builders[name](q, V)
+    q.plan()
+    first = q.kernel_id(V)
+    del os.environ["SRK_TUNE"], q
+    hit = [f for f, (lines, cands, shape) in by_shape.items() if cands and cands[0] == first and shape.startswith(f"V={V} ")]
+    if len(hit) != 1:
+        print(f"{name}:{V}: {len(hit)} decision files match {first}; left as measured")
+        continue
+    lines, cands, shape = by_shape[hit[0]]
+    full = []
+    for i, c in enumerate(cands):
+        ms, kid = whole_render_ms(name, V, i)
+        full.append((ms, c if c.startswith("interpreter") or kid == c else f"{c}?{kid}"))
+    best = min(range(len(full)), key=lambda i: full[i][0] if i == 0 else full[i][0] / 0.995)  # an alternative has to win by 0.5 %
+    report = ", ".join(f"{c} {ms:.3f}" for ms, c in full)
+    lines[0] = cands[best]
+    lines[1] = f"whole-render kernel ms (48000 samples): {report}; window: {lines[1]}"
+    open(hit[0], "w").write("\n".join(lines) + "\n")
+    print(f"{name}:{V:<6d} ships {cands[best]}  {full[best][0]:.3f} ms   ({report})", flush=True)
+
 os.makedirs(out_dir, exist_ok=True)
 n = 0
 for f in glob.glob(os.path.join(cache, "*.tune")):
