@@ -61,7 +61,7 @@ struct Ctx {
 
 // f64 `x % 1.0` (Rust) == fmod(x, 1.0): x - trunc(x) is exact for finite x, NaN for +-inf.
 static __device__ __noinline__ double fmod1_exact(double x) { return dsub(x, trunc(x)); }
-FZ_DEV double wrap01(double x) { return x >= 1.0 ? dsub(x, 1.0) : x; }  // fmod(x, 1.0) for x in [0, 2)
+FZ_DEV double wrap01(double x) { return dsub(x, x >= 1.0 ? 1.0 : 0.0); }  // fmod(x, 1.0) for x in [0, 2); x - 0.0 is x, one select
 
 // OscillatorModule::poly_blep, src/synth/oscillator.rs:50-67 (select-based: one division serves either arm)
 FZ_DEV double blep_eval(double t, double dt, double one_minus_dt) {
@@ -284,11 +284,14 @@ struct Osc {
       // delta = 440 * 2^(cv + val) / sample_rate (:43-48, :132).  The divisor is constant over the render: Markstein's
       // division by a constant (five f64 instructions, no branch) whenever every numerator of the group is a normal number
       // whose quotient stays normal, IEEE division otherwise (2^x under- or overflowed, or the CV was not finite)
-      double num[U];
+      double num[U], oct[U], pw[U];
       bool tame = true;
 #pragma unroll
+      for (int j = 0; j < U; ++j) oct[j] = dadd((double)cv[j], val);
+      exp2_glibc_group(oct, pw);
+#pragma unroll
       for (int j = 0; j < U; ++j) {
-        num[j] = dmul(440.0, exp2_glibc(dadd((double)cv[j], val)));
+        num[j] = dmul(440.0, pw[j]);
         const u32 ex = ((u32)__double2hiint(num[j]) >> 20) & 0x7ffu;
         tame &= (ex - 64u) < 1920u;  // biased exponent in [64, 1984)
       }

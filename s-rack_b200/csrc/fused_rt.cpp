@@ -50,7 +50,10 @@ const Nvrtc& nvrtc() {
     Nvrtc r;
     std::vector<std::string> names;
     if (const char* e = std::getenv("SRK_NVRTC_LIB")) names.push_back(e);
-    for (const char* s : {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so"})
+    // The toolkit's library by PATH before any bare name: a bare "libnvrtc.so.12" resolves to whatever copy the process
+    // has already mapped -- `import torch` maps the 12.8 one of its own wheel -- and the same kernel id would then name two
+    // different cubins (seen: 128 registers without and with spills).  The version is part of the id as well (salt()).
+    for (const char* s : {"/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so", "libnvrtc.so"})
       names.push_back(s);
     for (const std::string& name : names) {
       r.handle = dlopen(name.c_str(), RTLD_NOW | RTLD_LOCAL);
@@ -79,6 +82,9 @@ std::string salt() {
   s += kFusedArgsSrc;
   s += kFusedLibmSrc;
   for (int i = 0; i < kNumNvrtcOptions; ++i) { s += kNvrtcOptions[i]; s += ' '; }
+  const Nvrtc& rt = nvrtc();  // (no NVRTC: nothing gets compiled under the id anyway)
+  int major = 0, minor = 0;
+  if (rt.ok() && rt.version(&major, &minor) == NVRTC_SUCCESS) s += "nvrtc " + std::to_string(major) + "." + std::to_string(minor);
   return s;
 }
 

@@ -186,6 +186,48 @@ LG_FN double exp2_glibc(double x) {
   return lg_add(scale, lg_mul(scale, tmp));
 }
 
+// U values of a sample group.  exp2_glibc's early returns are branches, one set per call, and keep the compiler from
+// interleaving the U dependent chains; here the main route runs for every argument as straight-line code and ONE
+// branch per group sends |x| >= 512, inf and NaN (biased exponent >= 0x408) through exp2_glibc itself, out of line.
+// Below 2^-54 the library returns 1 + x: 1.0 in round-to-nearest, and so is the main route's 1 + (x C1 + ..) there
+// (k = 0, r = x, scale = 1) -- tests/test_libm_glibc.py holds the group form to the platform's exp2 on the same
+// arguments as the scalar one.
+LG_COLD double lg_exp2_cold(double x) { return exp2_glibc(x); }
+LG_FN double lg_exp2_main(double x) {
+  const double shift = 0x1.8p+45;
+  double kd = lg_add(x, shift);
+  const unsigned long long ki = lg_bits(kd);
+  kd = lg_sub(kd, shift);
+  const double r = lg_sub(x, kd);
+  const lg_pair e = lg_ld_pair(&kLgExp2Tab[2u * (unsigned)(ki & 127u)]);
+  const double tail = lg_f64(e.lo);
+  const double scale = lg_f64(e.hi + (ki << 45));
+  const double r2 = lg_mul(r, r);
+  double tmp = lg_add(tail, lg_mul(r, 0x1.62e42fefa39efp-1));
+  tmp = lg_add(tmp, lg_mul(r2, lg_add(0x1.ebfbdff82c424p-3, lg_mul(r, 0x1.c6b08d70cf4b5p-5))));
+  tmp = lg_add(tmp, lg_mul(lg_mul(r2, r2), lg_add(0x1.3b2abd24650ccp-7, lg_mul(r, 0x1.5d7e09b4e3a84p-10))));
+  return lg_add(scale, lg_mul(scale, tmp));
+}
+LG_FN bool lg_exp2_off_main(double x) { return ((unsigned)(lg_bits(x) >> 52) & 0x7ffu) >= 0x408u; }
+template <int U>
+LG_FN void exp2_glibc_group(const double (&x)[U], double (&y)[U]) {
+  bool any = false;
+#if defined(__CUDACC__) || defined(__CUDACC_RTC__)
+#pragma unroll
+#endif
+  for (int j = 0; j < U; ++j) {
+    y[j] = lg_exp2_main(x[j]);
+    any |= lg_exp2_off_main(x[j]);
+  }
+  if (any) {
+#if defined(__CUDACC__) || defined(__CUDACC_RTC__)
+#pragma unroll
+#endif
+    for (int j = 0; j < U; ++j)
+      if (lg_exp2_off_main(x[j])) y[j] = lg_exp2_cold(x[j]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // powf (f32, computed in f64)
 // ---------------------------------------------------------------------------------------------------------------------
@@ -532,7 +574,7 @@ LG_FN double sin_glibc(double x) {
 //                  multiple of pi/2, and the whole range up to 1e5), not a documented bound on somebody else's libm.
 //   lg_sin_near_tie  the fast value is within SRK_SIN_TIE_BAND = 16 patterns of a tie (sixteen times the
 //                  measured distance): 33 in 2^29 of the values, 6e-8 of the samples.  Those, and |x| >= 1e5, inf, NaN, take
-//                  sin_glibc.  Below 2^-26 glibc returns x itself, and so does this (keeps -0.0).
+//                  sin_glibc.  Below 2^-26 glibc returns x itself, and so does lg_sin_fast (-0.0 included).
 // The result is glibc's for EVERY argument.  SRK_SIN_TIE_BAND widens the band (tests: at 0x10000000 every sample takes
 // the restatement on the device).
 #ifndef SRK_SIN_TIE_BAND
@@ -550,18 +592,23 @@ LG_TAB LG_ALIGN16 double kLgSinFastTab[16] = {
     -0x1.6c16c16c15177p-10, 0x1.555555555554cp-5, -0x1.0000000000000p-1, 0.0,
 };
 #if defined(__CUDACC__) || defined(__CUDACC_RTC__)
-static __device__ __forceinline__ lg_dpair lg_ld_fast(unsigned k) {
-  const double2 v = __ldg(reinterpret_cast<const double2*>(&kLgSinFastTab[k]));
-  lg_dpair q; q.a = v.x; q.b = v.y; return q;
-}
+// (one address for the row, the four 16-byte loads at immediate offsets from it)
+typedef const double2* lg_row;
+static __device__ __forceinline__ lg_row lg_fast_row(unsigned odd) { return reinterpret_cast<const double2*>(kLgSinFastTab) + (odd << 2); }
+static __device__ __forceinline__ lg_dpair lg_ld_row(lg_row t, int i) { const double2 v = __ldg(t + i); lg_dpair q; q.a = v.x; q.b = v.y; return q; }
 #else
-static inline lg_dpair lg_ld_fast(unsigned k) { lg_dpair q; q.a = kLgSinFastTab[k]; q.b = kLgSinFastTab[k + 1]; return q; }
+typedef const double* lg_row;
+static inline lg_row lg_fast_row(unsigned odd) { return kLgSinFastTab + (odd << 3); }
+static inline lg_dpair lg_ld_row(lg_row t, int i) { lg_dpair q; q.a = t[2 * i]; q.b = t[2 * i + 1]; return q; }
 #endif
+// sin is odd: the work is done on |x| and the sign put back at the end, so that -0.0 stays -0.0 and every |x| < 2^-26
+// comes back as x itself -- r = |x| + (|x|^3 P) rounds to |x| there -- which is what glibc returns for those
 LG_FN double lg_sin_fast(double x) {  // |x| < 1e5
-  const double t = lg_fma(x, 0x1.45f306dc9c883p-1, 0x1.8000000000000p+52);
+  const double ax = lg_abs(x);
+  const double t = lg_fma(ax, 0x1.45f306dc9c883p-1, 0x1.8000000000000p+52);
   const double xn = lg_sub(t, 0x1.8000000000000p+52);
   const unsigned n = (unsigned)lg_bits(t);
-  double b = lg_fma(-xn, 0x1.921fb58000000p+0, x);   // exact
+  double b = lg_fma(-xn, 0x1.921fb58000000p+0, ax);   // exact
   b = lg_fma(-xn, -0x1.dde973c000000p-27, b);
   b = lg_fma(-xn, -0x1.cb3b398000000p-55, b);
   b = lg_fma(-xn, -0x1.d747f23e32ed7p-83, b);
@@ -577,8 +624,8 @@ LG_FN double lg_sin_fast(double x) {  // |x| < 1e5
   p = lg_fma(z, p, cs ? 0x1.555555555554cp-5 : 0x1.111111110f8a6p-7);
   p = lg_fma(z, p, cs ? -0x1.0000000000000p-1 : -0x1.5555555555549p-3);
 #else
-  const unsigned row = (n & 1u) << 3;
-  const lg_dpair c01 = lg_ld_fast(row), c23 = lg_ld_fast(row + 2u), c45 = lg_ld_fast(row + 4u), c6 = lg_ld_fast(row + 6u);
+  const lg_row row = lg_fast_row(n & 1u);
+  const lg_dpair c01 = lg_ld_row(row, 0), c23 = lg_ld_row(row, 1), c45 = lg_ld_row(row, 2), c6 = lg_ld_row(row, 3);
   double p = lg_fma(z, c01.a, c01.b);
   p = lg_fma(z, p, c23.a);
   p = lg_fma(z, p, c23.b);
@@ -588,25 +635,25 @@ LG_FN double lg_sin_fast(double x) {  // |x| < 1e5
 #endif
   const double a = (n & 1u) ? 1.0 : b;
   const double r = lg_fma(lg_mul(z, a), p, a);
-  return lg_f64(lg_bits(r) ^ ((unsigned long long)(n & 2u) << 62));
+  // quadrants 2 and 3 are negative; so is a negative argument
+  return lg_f64(lg_bits(r) ^ ((((unsigned long long)n << 62) ^ lg_bits(x)) & 0x8000000000000000ull));
 }
 LG_FN bool lg_sin_near_tie(double r) {
   const unsigned lo = (unsigned)lg_bits(r);
   return ((lo - (0x10000000u - (unsigned)(SRK_SIN_TIE_BAND))) & 0x1fffffffu) <= 2u * (unsigned)(SRK_SIN_TIE_BAND);
 }
 LG_COLD double lg_sin_exact(double x) { return sin_glibc(x); }
-// `fast`: sin(x) from an implementation within SRK_SIN_TIE_BAND bit patterns of glibc's for 2^-26 <= |x| < 1e5
-LG_FN double lg_sin_pick(double x, double fast) {
+// `fast`: sin(x) from an implementation within SRK_SIN_TIE_BAND bit patterns of glibc's for |x| < 1e5.  BOUNDED: the
+// caller knows |x| < 1e5 or x is NaN (the sine port: pos is in [0, 1) or NaN, oscillator.rs:151-152)
+template <bool BOUNDED>
+LG_FN bool lg_sin_unsure(double x, double fast) {
+  if (BOUNDED) return lg_sin_near_tie(fast);
   const unsigned k = (unsigned)(lg_bits(x) >> 32) & 0x7fffffffu;
-  return k < 0x3e500000u ? x : fast;
-}
-LG_FN bool lg_sin_unsure(double x, double r) {
-  const unsigned k = (unsigned)(lg_bits(x) >> 32) & 0x7fffffffu;
-  return lg_sin_near_tie(r) || k >= 0x40f86a00u;  // next to a tie, or |x| >= 1e5 / inf / NaN
+  return lg_sin_near_tie(fast) || k >= 0x40f86a00u;  // next to a tie, or |x| >= 1e5 / inf / NaN
 }
 LG_FN float lg_sin_settle(double x, double fast) {
-  double r = lg_sin_pick(x, fast);
-  if (lg_sin_unsure(x, r)) r = lg_sin_exact(x);
+  double r = fast;
+  if (lg_sin_unsure<false>(x, r)) r = lg_sin_exact(x);
   return lg_narrow(r);
 }
 // (float) sin(x), one sample
@@ -614,19 +661,19 @@ LG_FN float sinf_of_f64_glibc(double x) { return lg_sin_settle(x, lg_sin_fast(x)
 #if defined(__CUDACC__) || defined(__CUDACC_RTC__)
 // U samples of a group: the fast values as straight-line code (the compiler interleaves the U chains), one branch for
 // the group
-template <int U>
+template <bool BOUNDED, int U>
 LG_FN void sin_f32_glibc(const double (&x)[U], float (&y)[U]) {
   double r[U];
   bool any = false;
 #pragma unroll
   for (int j = 0; j < U; ++j) {
-    r[j] = lg_sin_pick(x[j], lg_sin_fast(x[j]));
-    any |= lg_sin_unsure(x[j], r[j]);
+    r[j] = lg_sin_fast(x[j]);
+    any |= lg_sin_unsure<BOUNDED>(x[j], r[j]);
   }
   if (any) {
 #pragma unroll
     for (int j = 0; j < U; ++j)
-      if (lg_sin_unsure(x[j], r[j])) r[j] = lg_sin_exact(x[j]);
+      if (lg_sin_unsure<BOUNDED>(x[j], r[j])) r[j] = lg_sin_exact(x[j]);
   }
 #pragma unroll
   for (int j = 0; j < U; ++j) y[j] = lg_narrow(r[j]);
@@ -638,7 +685,7 @@ LG_FN void sine_port(const double (&pos)[U], float* sine, int stride) {
   float y[U];
 #pragma unroll
   for (int j = 0; j < U; ++j) x[j] = lg_mul(lg_mul(pos[j], 3.14159265358979323846), 2.0);
-  sin_f32_glibc(x, y);
+  sin_f32_glibc<true>(x, y);  // pos is in [0, 1) or NaN
 #pragma unroll
   for (int j = 0; j < U; ++j) sine[j * stride] = y[j];
 }

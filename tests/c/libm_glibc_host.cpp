@@ -53,3 +53,14 @@ extern "C" long t_sin_fast_scan(int mode, long n, double lim, unsigned long long
 extern "C" void t_sinf_of_f64(const double* x, float* y, long n) {
   for (long i = 0; i < n; ++i) y[i] = sinf_of_f64_glibc(x[i]);
 }
+// the sample-group form of exp2 (main route for all four, one branch for the group)
+extern "C" void t_exp2_group(const double* x, double* y, long n) {
+  long i = 0;
+  for (; i + 4 <= n; i += 4) {
+    const double a[4] = {x[i], x[i + 1], x[i + 2], x[i + 3]};
+    double b[4];
+    exp2_glibc_group(a, b);
+    for (int j = 0; j < 4; ++j) y[i + j] = b[j];
+  }
+  for (; i < n; ++i) { const double a[1] = {x[i]}; double b[1]; exp2_glibc_group(a, b); y[i] = b[0]; }
+}

@@ -24,6 +24,7 @@ def host(tmp_path_factory, request):
                            os.path.join(ROOT, "tests", "c", "libm_glibc_host.cpp")])
     L = ctypes.CDLL(so)
     L.t_exp2_glibc.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
+    L.t_exp2_group.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
     L.t_powf_glibc.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
     L.t_sin_glibc.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
     L.t_sin_settle.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
@@ -59,11 +60,15 @@ def test_exp2_f64_equals_glibc_bit_for_bit(host, libm):
         np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1024.0, 1023.9999999999999, -1075.0, -1074.9999, -1022.0, -1022.0000001, 928.0,
                   928.0000001, -928.5, 511.99999, 512.0, 1e-300, -1e-300, 2.0 ** -54, -(2.0 ** -54), 2.0 ** -55, 5e-324]),
     ])
-    y = np.zeros_like(x)
-    host.t_exp2_glibc(x.ctypes.data, y.ctypes.data, x.size)
+    x = np.concatenate([x, -2.0 ** -rng.uniform(50, 80, 3000), 2.0 ** -rng.uniform(50, 80, 3000)])  # around the 1 + x early return
     ref = np.array([libm.exp2(float(v)) for v in x])
-    same = (y.view(np.uint64) == ref.view(np.uint64)) | (np.isnan(y) & np.isnan(ref))
-    assert same.all(), f"glibc {libm.gnu_get_libc_version().decode()}: {int((~same).sum())} of {x.size} differ, e.g. x = {x[~same][:5]}"
+    for fn in (host.t_exp2_glibc, host.t_exp2_group):  # the scalar form and the sample-group form (exp2_glibc_group) the fused kernels use
+        for order in (np.arange(x.size), rng.permutation(x.size)):  # (groups of four: specials next to ordinary arguments)
+            xs = np.ascontiguousarray(x[order])
+            y = np.zeros_like(xs)
+            fn(xs.ctypes.data, y.ctypes.data, xs.size)
+            same = (y.view(np.uint64) == ref[order].view(np.uint64)) | (np.isnan(y) & np.isnan(ref[order]))
+            assert same.all(), f"glibc {libm.gnu_get_libc_version().decode()}: {int((~same).sum())} of {x.size} differ, e.g. x = {xs[~same][:5]}"
 
 
 def test_sin_f64_equals_glibc_bit_for_bit(host, libm):
@@ -128,7 +133,7 @@ def test_sine_port_narrowing_is_glibcs_for_any_fast_sine_within_three_ulp(host, 
     at_tie = np.abs(low.astype(np.int64) - 0x10000000) <= 8
     assert at_tie.sum() > 5000
     x = np.concatenate([x[at_tie], rng.uniform(0, 2 * np.pi, 200000), rng.uniform(-1, 1, 2000) * 2.0 ** -rng.integers(20, 200, 2000),
-                        np.array([0.0, -0.0, 2.0 ** -26, 2.0 ** -27, 1e-300, 5e-324, np.pi, np.inf, np.nan])])
+                        np.array([0.0, -0.0, 2.0 ** -26, 2.0 ** -27, 1e-300, -1e-300, 5e-324, -5e-324, 2.0 ** -26 * (1 - 2.0 ** -53), np.pi, -np.pi, np.inf, np.nan])])
     want = gsin(x).astype(np.float32)
     got = np.zeros(x.size, np.float32)
     host.t_sinf_of_f64(x.ctypes.data, got.ctypes.data, x.size)  # the composition the device runs: fast sine, settled
@@ -136,6 +141,7 @@ def test_sine_port_narrowing_is_glibcs_for_any_fast_sine_within_three_ulp(host, 
     changed = 0
     for d in range(-6, 7):
         ulps = np.full(x.size, d, np.int64)
+        ulps[np.abs(x) < 2.0 ** -1000] = 0  # (bit patterns of 0 and the subnormals cannot be moved by -6; the fast sine returns these exactly)
         got = np.zeros(x.size, np.float32)
         host.t_sin_settle(x.ctypes.data, ulps.ctypes.data, got.ctypes.data, x.size)
         same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
