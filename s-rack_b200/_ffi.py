@@ -100,12 +100,32 @@ _SIGNATURES = {
 }
 
 
+def _point_at_second_nvrtc():
+    """The library builds its patch-specialised kernels with the CUDA toolkit's NVRTC and, when ANOTHER version is at
+    hand, measures that one's code as well (csrc/fused_rt.cpp: neither version is faster everywhere).  A Python
+    environment with the nvidia-cuda-nvrtc wheel (torch's dependency) has one: name it, so that the choice does not
+    depend on whether torch happened to be imported first.  SRK_NVRTC_ALT=0 turns the second compiler off."""
+    if "SRK_NVRTC_ALT" in os.environ:
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.cuda_nvrtc")
+        for d in (spec.submodule_search_locations if spec else ()):
+            cand = os.path.join(d, "lib", "libnvrtc.so.12")
+            if os.path.exists(cand):
+                os.environ["SRK_NVRTC_ALT"] = cand
+                return
+    except Exception:
+        pass
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} is missing: build the CUDA extension first "
             "(python -c 'import __graft_entry__ as g; g.build()' or make -C s-rack_b200/csrc). "
             "srack_b200 has no CPU or pure-Python path.")
+    _point_at_second_nvrtc()
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here = header and library out of sync

@@ -494,8 +494,10 @@ static int engine_prepare(srk_patch* patch, size_t n_voices, size_t voice_offset
     if (!rewired && e.tuned && e.fused && e.have_forced) {
       // a table edit under a measured choice: the same launch shape around the new program image
       std::string why;
+      const int compiler = e.fspec.compiler;  // (the measured choice includes which NVRTC builds the kernel)
       rc = compile_program(*patch, 1, e.prog, err);
       if (rc == SRK_OK && fused_generate_fitting(*patch, e, e.prog, sv, e.fspec, why, &e.forced) != SRK_OK) { rc = SRK_ERR_LIMIT; err = why; }
+      e.fspec.compiler = compiler;
       if (rc == SRK_OK) { build_blob(e.prog, e.blob); e.chunk = e.fspec.tile; }
     } else if (!rewired && e.tuned && !e.fused) {
       rc = schedule_interpreter(*patch, e, sv, e.prog, e.blob, e.chunk, err);
@@ -564,7 +566,10 @@ static int engine_prepare(srk_patch* patch, size_t n_voices, size_t voice_offset
       // per-voice (or uniform again) selects another kernel
       FusedSpec spec;
       std::string why;
-      if (fused_generate_fitting(*patch, e, e.prog, sv, spec, why, e.have_forced ? &e.forced : nullptr) == SRK_OK && spec.source != e.fspec.source) {
+      spec.compiler = e.fspec.compiler;
+      const int rc_gen = fused_generate_fitting(*patch, e, e.prog, sv, spec, why, e.have_forced ? &e.forced : nullptr);
+      spec.compiler = e.fspec.compiler;
+      if (rc_gen == SRK_OK && spec.source != e.fspec.source) {
         const FusedKernel* k = nullptr;
         if (fused_kernel(spec, &k, why) == SRK_OK) {
           e.fspec = std::move(spec);
@@ -799,6 +804,24 @@ static void schedule_candidates(const srk_patch& patch, const Engine& lim, size_
     if (fused_mode() != 0 && compile_program(patch, 1, one, err) == SRK_OK && fused_generate_fitting(patch, lim, one, sv, spec, why) == SRK_OK) {
       add_fused(spec.stages, 4, spec.tile, spec.split_moog);
       add_fused(spec.stages, 8, spec.tile, spec.split_moog);
+    }
+  }
+  // every fused candidate once more as the other NVRTC version builds it, when there is one (fused_rt.cpp: neither is
+  // better everywhere)
+  if (fused_compilers() > 1) {
+    const size_t n = out.size();
+    for (size_t i = 0; i < n; ++i) {
+      if (!out[i].fused) continue;
+      Schedule s = out[i];
+      s.fspec.compiler = 1;
+      s.fkernel = nullptr;
+      if (!s.forced) {  // the cost model's own shape, spelled out so that a later regeneration keeps it
+        s.fopt.group = s.fspec.group; s.fopt.min_blocks = s.fspec.min_blocks; s.fopt.stages = s.fspec.stages;
+        s.fopt.exact_stages = true; s.fopt.tile = s.fspec.tile; s.fopt.split_moog = s.fspec.split_moog;
+        s.forced = true;
+      }
+      s.id = "fused:" + fused_key(s.fspec);
+      out.push_back(std::move(s));
     }
   }
 }

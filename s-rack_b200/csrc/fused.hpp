@@ -29,6 +29,7 @@ struct FusedSpec {
   int n_cross = 0;               // wires that cross a stage boundary
   int n_cross_tiles = 0;         // ... and the tiles of their rings (stages spanned + 1 each)
   size_t smem_per_group = 0;
+  int compiler = 0;              // which NVRTC builds it (fused_rt.cpp: 0 = the toolkit's, 1 = another version, if present)
 };
 
 struct FusedOptions {
@@ -47,6 +48,8 @@ int fused_generate(const srk_patch& patch, const Program& prog, const FusedOptio
 std::string fused_hash(const std::string& text, const std::string& salt);
 // cache key of a generated kernel: hash of its source, the op headers and the compiler options
 std::string fused_key(const FusedSpec& spec);
+int fused_compilers();                           // NVRTC versions available: 0, 1 or 2
+std::string fused_compiler_name(int compiler);   // "nvrtc 12.9"
 
 struct FusedKernel {
   void* library = nullptr;  // cudaLibrary_t

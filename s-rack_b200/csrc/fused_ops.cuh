@@ -61,7 +61,9 @@ struct Ctx {
 
 // f64 `x % 1.0` (Rust) == fmod(x, 1.0): x - trunc(x) is exact for finite x, NaN for +-inf.
 static __device__ __noinline__ double fmod1_exact(double x) { return dsub(x, trunc(x)); }
-FZ_DEV double wrap01(double x) { return dsub(x, x >= 1.0 ? 1.0 : 0.0); }  // fmod(x, 1.0) for x in [0, 2); x - 0.0 is x, one select
+// fmod(x, 1.0) for x in [0, 2).  (x - (x >= 1 ? 1 : 0) is one select fewer but puts the compare IN the phase
+// recurrence's dependent chain instead of beside the subtraction: cfg4 @ 16384 13.1 -> 14.7 ms, profiles/r06f_tune_all.txt)
+FZ_DEV double wrap01(double x) { return x >= 1.0 ? dsub(x, 1.0) : x; }
 
 // OscillatorModule::poly_blep, src/synth/oscillator.rs:50-67 (select-based: one division serves either arm)
 FZ_DEV double blep_eval(double t, double dt, double one_minus_dt) {

@@ -45,46 +45,73 @@ struct Nvrtc {
   bool ok() const { return handle != nullptr; }
 };
 
-const Nvrtc& nvrtc() {
-  static Nvrtc n = [] {
+void bind(Nvrtc& r, const std::vector<std::string>& names, const char* missing) {
+  for (const std::string& name : names) {
+    r.handle = dlopen(name.c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (r.handle) break;
+  }
+  if (!r.handle) { r.why = missing; return; }
+#define SRK_SYM(field, name)                                                   \
+  r.field = reinterpret_cast<decltype(r.field)>(dlsym(r.handle, #name));       \
+  if (!r.field) { r.why = "libnvrtc lacks " #name; r.handle = nullptr; return; }
+  SRK_SYM(create, nvrtcCreateProgram)
+  SRK_SYM(compile, nvrtcCompileProgram)
+  SRK_SYM(cubin_size, nvrtcGetCUBINSize)
+  SRK_SYM(cubin, nvrtcGetCUBIN)
+  SRK_SYM(log_size, nvrtcGetProgramLogSize)
+  SRK_SYM(log, nvrtcGetProgramLog)
+  SRK_SYM(destroy, nvrtcDestroyProgram)
+  SRK_SYM(version, nvrtcVersion)
+#undef SRK_SYM
+}
+
+std::string version_of(const Nvrtc& rt) {
+  int major = 0, minor = 0;
+  if (!rt.ok() || rt.version(&major, &minor) != NVRTC_SUCCESS) return "";
+  return std::to_string(major) + "." + std::to_string(minor);
+}
+
+// Compiler 0: the toolkit's library by PATH before any bare name.  A bare "libnvrtc.so.12" resolves to whatever copy the
+// process has already mapped -- `import torch` maps the 12.8 one of its own wheel -- and the same kernel id would then
+// name two different cubins (seen: 128 registers without and with spills).  The version is part of the id (salt()).
+// Compiler 1, when there is one: ANOTHER version of the library -- SRK_NVRTC_ALT, else whatever the bare soname gives
+// if that differs from compiler 0.  Measured on B200 (profiles/r06h_tune_all*.txt): 12.8 schedules the staged kernels
+// better (cfg2 @ 4096 2.50 against 2.59 ms, cfg4 @ 16384 12.9 against 15.1), 12.9 the one-warp sine kernels (gated sine
+// @ 32768 7.2 against 7.9), so the compiler is one more dimension of the measured schedule choice (engine.cu).
+const Nvrtc& nvrtc(int which) {
+  static Nvrtc first = [] {
     Nvrtc r;
     std::vector<std::string> names;
     if (const char* e = std::getenv("SRK_NVRTC_LIB")) names.push_back(e);
-    // The toolkit's library by PATH before any bare name: a bare "libnvrtc.so.12" resolves to whatever copy the process
-    // has already mapped -- `import torch` maps the 12.8 one of its own wheel -- and the same kernel id would then name two
-    // different cubins (seen: 128 registers without and with spills).  The version is part of the id as well (salt()).
     for (const char* s : {"/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so", "libnvrtc.so"})
       names.push_back(s);
-    for (const std::string& name : names) {
-      r.handle = dlopen(name.c_str(), RTLD_NOW | RTLD_LOCAL);
-      if (r.handle) break;
-    }
-    if (!r.handle) { r.why = "libnvrtc.so.12 not found (set SRK_NVRTC_LIB)"; return r; }
-#define SRK_SYM(field, name)                                                   \
-  r.field = reinterpret_cast<decltype(r.field)>(dlsym(r.handle, #name));       \
-  if (!r.field) { r.why = "libnvrtc lacks " #name; r.handle = nullptr; return r; }
-    SRK_SYM(create, nvrtcCreateProgram)
-    SRK_SYM(compile, nvrtcCompileProgram)
-    SRK_SYM(cubin_size, nvrtcGetCUBINSize)
-    SRK_SYM(cubin, nvrtcGetCUBIN)
-    SRK_SYM(log_size, nvrtcGetProgramLogSize)
-    SRK_SYM(log, nvrtcGetProgramLog)
-    SRK_SYM(destroy, nvrtcDestroyProgram)
-    SRK_SYM(version, nvrtcVersion)
-#undef SRK_SYM
+    bind(r, names, "libnvrtc.so.12 not found (set SRK_NVRTC_LIB)");
     return r;
   }();
-  return n;
+  if (which == 0) return first;
+  static Nvrtc second = [] {
+    Nvrtc r;
+    const char* off = std::getenv("SRK_NVRTC_ALT");
+    if (!first.ok() || (off && off[0] == '0' && !off[1])) { r.why = "no alternative compiler"; return r; }
+    std::vector<std::string> names;
+    if (off && *off) names.push_back(off);
+    names.push_back("libnvrtc.so.12");
+    bind(r, names, "no alternative compiler");
+    if (r.ok() && (r.handle == first.handle || version_of(r) == version_of(first) || version_of(r).empty())) {
+      r.handle = nullptr;
+      r.why = "no alternative compiler";
+    }
+    return r;
+  }();
+  return second;
 }
 
-std::string salt() {
+std::string salt(int compiler) {
   std::string s(kFusedOpsSrc);
   s += kFusedArgsSrc;
   s += kFusedLibmSrc;
   for (int i = 0; i < kNumNvrtcOptions; ++i) { s += kNvrtcOptions[i]; s += ' '; }
-  const Nvrtc& rt = nvrtc();  // (no NVRTC: nothing gets compiled under the id anyway)
-  int major = 0, minor = 0;
-  if (rt.ok() && rt.version(&major, &minor) == NVRTC_SUCCESS) s += "nvrtc " + std::to_string(major) + "." + std::to_string(minor);
+  s += "nvrtc " + version_of(nvrtc(compiler));  // (no NVRTC: nothing gets compiled under the id anyway)
   return s;
 }
 
@@ -121,9 +148,13 @@ std::string fused_cache_dir() {
 }
 
 std::string fused_key(const FusedSpec& spec) {
-  static const std::string kSalt = salt();
-  return fused_hash(spec.source, kSalt);
+  static const std::string kSalt[2] = {salt(0), salt(1)};
+  return fused_hash(spec.source, kSalt[spec.compiler ? 1 : 0]);
 }
+
+int fused_compilers() { return nvrtc(1).ok() ? 2 : (nvrtc(0).ok() ? 1 : 0); }
+
+std::string fused_compiler_name(int compiler) { return "nvrtc " + version_of(nvrtc(compiler ? 1 : 0)); }
 
 std::string fused_tuned_dir() {
   if (const char* e = std::getenv("SRK_TUNED_DIR")) return e;
@@ -148,7 +179,7 @@ int fused_cubin(const FusedSpec& spec, std::vector<char>& cubin, std::string& ke
     if (from_disk) *from_disk = true;
     return SRK_OK;
   }
-  const Nvrtc& rt = nvrtc();
+  const Nvrtc& rt = nvrtc(spec.compiler ? 1 : 0);
   if (!rt.ok()) { err = "fused kernels unavailable: " + rt.why; return SRK_ERR_UNSUPPORTED; }
   const auto t0 = std::chrono::steady_clock::now();
   nvrtcProgram prog = nullptr;

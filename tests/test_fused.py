@@ -7,11 +7,14 @@ import glob
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
 
 from util import assert_parity, build_both
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _builders(srk):
@@ -84,6 +87,33 @@ def test_every_baseline_kernel_compiles_for_sm_100a_with_tma_and_without_spills(
             assert stack <= 48, (f, regs, stack)
     # a second request finds everything cached
     assert _patch(srk, _builders(srk)["cfg2"], 4096).precompile(4096) == 0
+
+
+def test_second_nvrtc_version_doubles_the_fused_candidates(srk, tmp_path):
+    """Neither NVRTC 12.8 nor 12.9 schedules every kernel better (profiles/r06h_tune_all*.txt), so each fused candidate
+    is built by both when both are at hand and the measurement picks; SRK_NVRTC_ALT=0 leaves the toolkit's alone.
+    The version is part of the kernel id."""
+    code = ("import srack_b200 as s; p = s.Patch(); s.patches.cfg2(p, 65536); p.plan(); "
+            "print('N', p.precompile(65536), p.kernel_id(65536))")
+    out = {}
+    for alt in ("0", None):
+        env = dict(os.environ, SRK_KERNEL_CACHE=str(tmp_path / f"alt{alt}"))
+        env.pop("SRK_NVRTC_ALT", None)
+        if alt is not None:
+            env["SRK_NVRTC_ALT"] = alt
+        os.makedirs(env["SRK_KERNEL_CACHE"], exist_ok=True)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT)
+        assert r.returncode == 0, r.stderr
+        line = [l for l in r.stdout.splitlines() if l.startswith("N ")][0].split()
+        out[alt] = (int(line[1]), line[2], set(os.path.basename(f) for f in glob.glob(os.path.join(env["SRK_KERNEL_CACHE"], "*.cubin"))))
+    n0, id0, files0 = out["0"]
+    n1, id1, files1 = out[None]
+    if n0 == 0:
+        pytest.skip("no NVRTC on this machine")
+    assert id0 == id1  # the cost model's first choice is the toolkit compiler's kernel either way
+    if n1 == n0:
+        pytest.skip("no second NVRTC version in this environment")
+    assert n1 == 2 * n0 and files0 < files1 and len(files1) == 2 * len(files0)
 
 
 def test_forced_knobs_reach_the_generator(srk, monkeypatch):

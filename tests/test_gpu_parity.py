@@ -827,7 +827,7 @@ def test_measured_schedule_choice_keeps_the_bits(srk, orc, cuda_device, monkeypa
     base_st, base_mix, rep0, _, _ = render({"SRK_TUNE": "0"})
     assert rep0 == ""
     ids = set()
-    for pick in range(6):
+    for pick in (0, 1, 2, 3, 4, 5, 7, 10, 13):  # (with a second NVRTC version at hand the list is twice as long)
         st, mix, rep, kid, info = render({"SRK_TUNE_PICK": str(pick)})
         assert "picked" in rep or "no alternative" in rep
         assert (st.view(np.uint32) == base_st.view(np.uint32)).all(), (pick, rep)
