@@ -17,7 +17,7 @@ import numpy as np
 
 import srack_b200 as srk
 
-KNOBS = ("SRK_FUSED", "SRK_FUSED_STAGES", "SRK_FUSED_GROUP", "SRK_WARPS", "SRK_SOLO_GROUPS")
+KNOBS = ("SRK_FUSED", "SRK_FUSED_STAGES", "SRK_FUSED_GROUP", "SRK_WARPS", "SRK_SOLO_GROUPS", "SRK_FUSED_DEFINE", "SRK_FUSED_SPLIT_MOOG")
 
 
 def run(label, env, names, V, N=1500):
@@ -38,6 +38,15 @@ def run(label, env, names, V, N=1500):
 
 ALL = ("cfg1", "cfg2", "cfg3", "cfg3b", "cfg4", "sequenced", "sampler")
 SECTION = sys.argv[1] if len(sys.argv) > 1 else "all"
+if SECTION == "libm":
+    # the table-driven libm restatements (libm_glibc.cuh): the fast sine's coefficient rows and exp2's table on the common
+    # route, and -- with the tie band at its widest -- glibc's sin restated (the 440-entry __sincostab) on every sample
+    run("fused, sine: fast + ties", {"SRK_FUSED": "1", "SRK_FUSED_STAGES": "1"}, ("cfg1", "cfg3", "cfg3b", "cfg4"), 72, N=6000)
+    run("fused, sine: all restated", {"SRK_FUSED": "1", "SRK_FUSED_STAGES": "1", "SRK_FUSED_DEFINE": "SRK_SIN_TIE_BAND=268435456"},
+        ("cfg1", "cfg3", "cfg3b", "cfg4"), 72, N=6000)
+    run("fused staged, all restated", {"SRK_FUSED": "1", "SRK_FUSED_STAGES": "4", "SRK_FUSED_DEFINE": "SRK_SIN_TIE_BAND=268435456"}, ("cfg4",), 72, N=3000)
+    run("interpreter", {"SRK_FUSED": "0", "SRK_WARPS": "16"}, ("cfg1", "cfg3", "cfg4"), 70, N=3000)
+    sys.exit(0)
 for stages in ("1", "3", "5"):
     if (stages == "1" and SECTION == "flags") or (stages != "1" and SECTION == "barriers"):
         continue
