@@ -317,15 +317,17 @@ SRK_API int srk_fused_source(srk_patch* patch, size_t n_voices, const char** sou
 /* Compiles that kernel -- and the alternative launch shapes a long render measures against it (srk_schedule_report) --
  * for sm_100a into the on-disk cubin cache (kernel_cache/ next to the library, or $SRK_KERNEL_CACHE) so that the first
  * render does not pay for NVRTC.  Needs no GPU.  *compiled = the number of kernels compiled now (0: all cached already,
- * or the launch would not use a fused kernel). */
+ * or the launch would not use a fused kernel).  NVRTC is the CUDA toolkit's libnvrtc.so.12, loaded by path
+ * (/usr/local/cuda/lib64; $SRK_NVRTC_LIB overrides); when $SRK_NVRTC_ALT names a copy of ANOTHER version every
+ * candidate is built by both and the measurement picks between them as well ($SRK_NVRTC_ALT=0: never). */
 SRK_API int srk_precompile(srk_patch* patch, size_t n_voices, int* compiled);
 /* Identity of the kernel image a render of n_voices would launch: "fused:<hash of generated source + op headers +
- * compiler options>" or "interpreter:<hash of the kernel sources at build time>:<pipelined|solo|solo_full>".  Profiles
+ * compiler options + NVRTC version>" or "interpreter:<hash of the kernel sources at build time>:<pipelined|solo|solo_full>".  Profiles
  * are stamped with it.  Valid until the next call on the patch. */
 SRK_API int srk_kernel_id(srk_patch* patch, size_t n_voices, const char** id);
 /* How the launch shape in use was chosen.  The first render of at least 16384 samples after a (re)plan measures the
  * plausible launch shapes (fused kernel with 4 or 8 samples per straight-line group, one more pipeline stage, the
- * interpreter's pipeline) for a few thousand samples each on a scratch copy of the voice state and keeps the fastest;
+ * interpreter's pipeline; each fused one as either NVRTC version builds it) for a few thousand samples each on a scratch copy of the voice state and keeps the fastest;
  * every shape computes the same bits.  *report: "" before that, else the winner and the measured times (or the cached
  * decision, kernel_cache/<key>.tune).  SRK_TUNE=0 in the environment, or any forced schedule knob, disables it.
  * srk_get_program_info / srk_kernel_id describe the shape in use once a render has happened.  Valid until the next call. */
